@@ -1,0 +1,73 @@
+"""CPU: pin the numpy oracle against outputs of the unmodified reference (tests/golden)."""
+import numpy as np
+
+from oracle import nsnet_oracle as oracle
+
+
+def _assemble(g, ck):
+    return oracle.assemble_channels(
+        g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], g.get("anns"),
+        int(ck["coverage_thr"]), bool(ck.get("normalize_channels", False)))
+
+
+def test_assemble_channels_bit_exact(golden):
+    name, g, ck = golden
+    x = _assemble(g, ck)
+    assert x.dtype == np.float32 and x.shape[1] == (119 if "anns" in g else 26)
+    # the reference's NeuSomaticDataset output for the first candidates: bit-exact
+    np.testing.assert_array_equal(x[:4], g["x_first"])
+    nt = oracle.non_transformed(g["matrices"][:8], g["center"][:8])
+    np.testing.assert_array_equal(nt, g["non_transformed_first"])
+
+
+def test_forward_matches_reference(golden):
+    name, g, ck = golden
+    p = oracle.normalize_state_dict(ck["state_dict"])
+    (o1, o2, o3), internals = oracle.forward(p, _assemble(g, ck), return_internals=True)
+    # fp32 summation-order noise only (reference = PyTorch CPU fp32)
+    np.testing.assert_allclose(internals[0][:2], g["pool1_first"], atol=2e-5)
+    np.testing.assert_allclose(internals[1][:8], g["res_first"], atol=1e-4)
+    np.testing.assert_allclose(internals[3][:8], g["fc1_first"], atol=1e-4)
+    np.testing.assert_allclose(o1, g["o1"], atol=2e-4)
+    np.testing.assert_allclose(o2, g["o2"], atol=2e-4)
+    np.testing.assert_allclose(o3, g["o3"], atol=2e-4)
+    assert (o1.argmax(1) == g["o1"].argmax(1)).all()
+    assert (o3.argmax(1) == g["o3"].argmax(1)).all()
+    assert np.abs(oracle.softmax(o1) - oracle.softmax(g["o1"])).max() < 1e-4
+
+
+def test_forward_fp64_noise_floor(golden):
+    name, g, ck = golden
+    p64 = oracle.normalize_state_dict(ck["state_dict"], np.float64)
+    o1, o2, o3 = oracle.forward(p64, _assemble(g, ck)[:32])
+    np.testing.assert_allclose(o1, g["o1"][:32], atol=3e-4)
+    np.testing.assert_allclose(o2, g["o2"][:32], atol=3e-4)
+
+
+def test_tsv_roundtrip_and_tag_parse(golden):
+    name, g, ck = golden
+    anns = g.get("anns")
+    for i in (0, 5, 17):
+        line = oracle.encode_tsv_line(i, str(g["tags"][i]), g["matrices"][i],
+                                      None if anns is None else anns[i])
+        tag, im, a = oracle.decode_tsv_line(line)
+        assert tag == str(g["tags"][i])
+        np.testing.assert_array_equal(im, g["matrices"][i])
+        if anns is not None:
+            np.testing.assert_array_equal(np.float32(a), anns[i])
+        vt, center, length, tc, nc = oracle.parse_tag(tag)
+        assert (center, tc, nc) == (g["center"][i], g["tumor_cov"][i], g["normal_cov"][i])
+        assert vt in oracle.VARTYPE_CLASSES
+
+
+def test_call_variants_contract(golden):
+    name, g, ck = golden
+    tags = [str(t) for t in g["tags"]]
+    final, none = oracle.call_variants(g["o1"], g["o2"], g["o3"], tags)
+    assert len(final) + len(none) == len(set(tags))
+    for d, is_none in ((final, False), (none, True)):
+        for k, e in d.items():
+            assert (e[0] == "NONE") == is_none
+            assert isinstance(e[3][0], np.float32) and len(e[3]) == 4 and len(e[6]) == 4
+            assert e[1].shape == (1,)
+            assert abs(sum(float(v) for v in e[3]) - 1.0) < 1e-3
