@@ -1,0 +1,162 @@
+/*
+ * libneusomatic_cuda -- C ABI of the B200-native NeuSomatic candidate-scoring path.
+ *
+ * The reference (bioinform/neusomatic) has no FFI: its seam for this path is the Python
+ * class neusomatic/python/network.py:39-78 (NeuSomaticNet) driven by call.py:54-118
+ * (call_variants) and fed by dataloader.py:245-417 (NeuSomaticDataset.__getitem__).
+ * Every entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero NSC_E_* code otherwise;
+ *     nsc_last_error() then returns a thread-local, NUL-terminated description;
+ *   - plain pointers and sizes only; the caller owns every buffer it passes in; the
+ *     library owns only its packed weights and its per-model device workspace;
+ *   - "dev" pointers are CUDA device pointers on the model's device, "host" pointers are
+ *     host memory (pinned memory makes the copies asynchronous, pageable also works);
+ *   - nsc_forward_* enqueue all work on `stream` (a cudaStream_t passed as void*, NULL =
+ *     the legacy default stream) and do not synchronise; nsc_score_host_* synchronise
+ *     before returning because their results land in host memory;
+ *   - one thread at a time per nsc_model handle;
+ *   - there is NO CPU fallback: without a CUDA device nsc_model_create fails.
+ */
+#ifndef NEUSOMATIC_CUDA_H_
+#define NEUSOMATIC_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSC_ABI_VERSION 1
+
+/* error codes */
+#define NSC_OK 0
+#define NSC_E_INVALID 1   /* bad argument / unknown parameter name / wrong size            */
+#define NSC_E_STATE 2     /* model not finalized, missing parameters ...                   */
+#define NSC_E_CUDA 3      /* a CUDA runtime / driver call failed (text in nsc_last_error)  */
+#define NSC_E_NOMEM 4
+
+/* arithmetic of the convolution stack (nsc_model_set_precision) */
+#define NSC_PREC_SPLIT_BF16 0 /* tcgen05 implicit GEMM, hi+lo bf16 operands, 3 MMAs, fp32 accumulate:
+                                 the parity mode (default)                                   */
+#define NSC_PREC_BF16 1       /* tcgen05, single-pass bf16 operands: fast, FAILS the parity bar */
+#define NSC_PREC_FP32 2       /* fp32 FFMA kernels (CUDA cores): bit-stable reference path    */
+
+typedef struct nsc_model nsc_model;
+
+int nsc_abi_version(void);
+const char* nsc_last_error(void);
+
+/* NeuSomaticNet.__init__ (network.py:41-64) + `.cuda()` (call.py:411-413).
+ * num_channels: 26 (standalone) or 119 (ensemble) (call.py:409-410); any value in [1,128]
+ * is accepted.  `device` is a CUDA ordinal. */
+int nsc_model_create(nsc_model** out, int device, int num_channels);
+
+/* net.load_state_dict (call.py:441-460): one call per tensor of the reference state_dict.
+ * `name` is the reference key WITHOUT a "module." prefix ("conv1.weight",
+ * "res_layers.2.bn_r1.running_var", "fc4.bias", ...; network.py:41-64); `data` is a host
+ * pointer to `numel` contiguous fp32 values in PyTorch layout.  `*.num_batches_tracked`
+ * is accepted and ignored.  Unknown names / wrong sizes fail with NSC_E_INVALID. */
+int nsc_model_set_param(nsc_model* m, const char* name, const float* data, int64_t numel);
+
+/* Folds every BatchNorm2d (eval mode, network.py:24,27,46; eps as nn.BatchNorm2d) into the
+ * preceding convolution, packs the weights for the kernels (tap-major slices, hi/lo
+ * split) and uploads them.  Idempotent; must be called after the last set_param and
+ * before the first forward.  Fails with NSC_E_STATE if a parameter is missing. */
+int nsc_model_finalize(nsc_model* m, float bn_eps);
+
+/* Selects the arithmetic of the convolution stack (NSC_PREC_*). */
+int nsc_model_set_precision(nsc_model* m, int precision);
+int nsc_model_get_precision(const nsc_model* m);
+
+/* checkpoint["normalize_channels"] (call.py:437-439; dataloader.py:386-388): scale the odd /
+ * even auxiliary channels 3..22 by the tumor / normal count channel.  Default 0 (every
+ * bundled model).  Only affects nsc_forward_u8 / nsc_score_host_u8. */
+int nsc_model_set_normalize_channels(nsc_model* m, int on);
+
+/* Keep fp32 copies of the internal activations of the first `n` candidates of each forward
+ * chunk for nsc_debug_internal (0 switches it off). */
+int nsc_model_set_debug(nsc_model* m, int64_t n);
+
+/* NeuSomaticNet.forward (network.py:66-78) on the assembled fp32 input.
+ *   x_dev        [B, C, 5, 32] fp32, contiguous NCHW (what call.py:74-77 feeds the net)
+ *   type_logits  [B,4]  o1 = fc2 (DEL, INS, NONE, SNP; call.py:407)
+ *   pos          [B,1]  o2 = fc3
+ *   len_logits   [B,4]  o3 = fc4
+ * Optional (may be NULL) fused extras replacing the per-candidate softmax / torch.max of
+ * call.py:80-83,97-100:
+ *   type_prob [B,4], len_prob [B,4]   softmax over the 4 logits
+ *   type_argmax [B], len_argmax [B]   first maximal index (torch.max semantics)
+ * All outputs are device pointers.  B may be 0. */
+int nsc_forward_f32(nsc_model* m, const float* x_dev, int64_t B,
+                    float* type_logits, float* pos, float* len_logits,
+                    float* type_prob, float* len_prob,
+                    int32_t* type_argmax, int32_t* len_argmax, void* stream);
+
+/* NeuSomaticDataset.__getitem__ (is_test branch, dataloader.py:383-417, including the
+ * matrix_transform of dataloader.py:25-36 / call.py:408) fused in front of forward():
+ *   matrices_dev [B,5,32,23] uint8  the stored pileup image (dataloader.py:38-39)
+ *   meta_dev     [B,3] int32        (center, tumor_cov, normal_cov) parsed from the tag
+ *                                   (dataloader.py:267-274)
+ *   anns255_dev  [B, C-26] fp32     ensemble annotation channels exactly as the reference stores
+ *                                   them in its float64 matrix, cast to fp32:
+ *                                   float(double(ann) * 255.0) (dataloader.py:395-396); NULL
+ *                                   when C == 26
+ *   coverage_thr                    checkpoint["coverage_thr"] (call.py:434-436)
+ * Channel assembly happens on the device; outputs as nsc_forward_f32. */
+int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* meta_dev,
+                   const float* anns255_dev, float coverage_thr, int64_t B,
+                   float* type_logits, float* pos, float* len_logits,
+                   float* type_prob, float* len_prob,
+                   int32_t* type_argmax, int32_t* len_argmax, void* stream);
+
+/* The batch step of call_variants (call.py:68-83) with HOST buffers: copies the inputs to the
+ * device in chunks (double-buffered on internal streams), runs forward, copies the
+ * results back and synchronises.  Output pointers are host pointers with the shapes of
+ * nsc_forward_f32; the optional ones may be NULL. */
+int nsc_score_host_f32(nsc_model* m, const float* x_host, int64_t B,
+                       float* type_logits, float* pos, float* len_logits,
+                       float* type_prob, float* len_prob,
+                       int32_t* type_argmax, int32_t* len_argmax);
+int nsc_score_host_u8(nsc_model* m, const uint8_t* matrices_host, const int32_t* meta_host,
+                      const float* anns255_host, float coverage_thr, int64_t B,
+                      float* type_logits, float* pos, float* len_logits,
+                      float* type_prob, float* len_prob,
+                      int32_t* type_argmax, int32_t* len_argmax);
+
+/* Test / profiling hooks (no reference equivalent; network.py:78 returns internal_outs that
+ * every caller discards).  Copies an internal activation of the LAST forward chunk to a
+ * device buffer as fp32 NCHW: which = 0 -> pool1 output [B,64,5,32]; 1..4 -> output of
+ * res_layers[which-1]; 5 -> relu(fc1) [B,240].  `n` candidates starting at 0. */
+int nsc_debug_internal(nsc_model* m, int which, float* out_dev, int64_t n, void* stream);
+
+/* Test hook: runs only the channel-assembly kernel of nsc_forward_u8 and writes the fp32
+ * [B,C,5,32] tensor it feeds the network to x_out_dev (checked bit-for-bit against the
+ * reference's NeuSomaticDataset output in tests/). */
+int nsc_debug_assemble(nsc_model* m, const uint8_t* matrices_dev, const int32_t* meta_dev,
+                       const float* anns255_dev, float coverage_thr, int64_t B, float* x_out_dev,
+                       void* stream);
+
+/* Per-kernel device timing (bench.py `roofline`): while switched on, every kernel launch of
+ * the forward path is bracketed by CUDA events on the launching stream.
+ * nsc_model_get_profile synchronises the device, adds the elapsed milliseconds and launch
+ * counts per slot to ms[] / launches[] (NSC_PROF_SLOTS entries each) and resets the record.
+ * Slots: 0 channel assembly, 1 conv1 stage, 2+2*i+j = res_layers[i].conv_r{j+1} stage
+ * (i = 0..3, j = 0..1, epilogues fused), 10 fc1+heads, 11 input packing (tensor path). */
+#define NSC_PROF_SLOTS 16
+int nsc_model_set_profile(nsc_model* m, int on);
+int nsc_model_get_profile(nsc_model* m, double* ms, int64_t* launches);
+const char* nsc_profile_slot_name(int slot);
+
+/* Number of kernel launches issued by this model since creation (bench.py `gpu_launches`). */
+int64_t nsc_model_launch_count(const nsc_model* m);
+/* Name of the dominant (conv) kernel family used by the current precision mode. */
+const char* nsc_model_kernel_name(const nsc_model* m);
+
+int nsc_model_destroy(nsc_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUSOMATIC_CUDA_H_ */

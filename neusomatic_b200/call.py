@@ -1,0 +1,153 @@
+"""Host-side mirror of the scoring part of the reference's ``call.py``.
+
+  * ``call_variants``       -- call.py:54-118, same signature and the same
+                               ``(final_preds, none_preds, true_path)`` dictionaries, but one
+                               fused device call + one D2H per batch and a vectorised
+                               post-loop instead of 2 kernels + 4 syncs per candidate.
+  * ``load_checkpoint``     -- call.py:424-460 (``module.`` prefix reconciliation, coverage_thr,
+                               normalize_channels).
+  * ``CandidateScorer``     -- the compact path: uint8 matrices + tag fields in host memory ->
+                               ``nsc_score_host_u8`` (channel assembly fused on the device).
+  * ``shard_ranges``        -- contiguous per-rank candidate ranges for multi-GPU scoring
+                               (no collective; replaces nn.DataParallel of call.py:417-419).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from .engine import Engine, VARTYPE_CLASSES, anns_to_255
+
+logger = logging.getLogger(__name__)
+
+
+def load_checkpoint(path_or_dict, map_location="cpu"):
+    """Returns (state_dict without ``module.`` prefix, meta dict) -- call.py:424-460."""
+    ck = path_or_dict
+    if not isinstance(ck, dict):
+        ck = torch.load(path_or_dict, map_location=map_location, weights_only=True)
+    sd = {}
+    for k, v in ck["state_dict"].items():
+        sd[k[len("module."):] if k.startswith("module.") else k] = v
+    meta = {
+        "tag": ck.get("tag", ""),
+        "epoch": ck.get("epoch", 0),
+        "coverage_thr": ck["coverage_thr"],                                # call.py:434-436
+        "normalize_channels": bool(ck.get("normalize_channels", False)),   # call.py:437-439
+    }
+    return sd, meta
+
+
+def build_pred_dicts(o1, o2, o3, p1, p3, arg1, arg3, paths, vartype_classes=VARTYPE_CLASSES,
+                     final_preds=None, none_preds=None):
+    """Vectorised restatement of call.py:86-114 on host arrays.
+
+    ``round(np.float32, 4)`` of the reference is numpy's float32 rounding; ``np.round`` on a
+    float32 array applies the same ufunc element-wise."""
+    final_preds = {} if final_preds is None else final_preds
+    none_preds = {} if none_preds is None else none_preds
+    o1 = np.asarray(o1, np.float32)
+    o2 = np.asarray(o2, np.float32)
+    o3 = np.asarray(o3, np.float32)
+    r_p1, r_p3 = np.round(np.asarray(p1, np.float32), 4), np.round(np.asarray(p3, np.float32), 4)
+    r_o1, r_o3 = np.round(o1, 4), np.round(o3, 4)
+    arg1 = np.asarray(arg1)
+    arg3 = np.asarray(arg3)
+    for i, path_ in enumerate(paths):
+        path = path_.split("/")[-1]
+        vt = vartype_classes[int(arg1[i])]
+        entry = [vt, o2[i], arg3[i], list(r_p1[i]), list(r_p3[i]), list(r_o1[i]), list(r_o3[i])]
+        if vt != "NONE":
+            final_preds[path] = entry
+        else:
+            none_preds[path] = entry
+    return final_preds, none_preds
+
+
+def call_variants(net, vartype_classes, call_loader, out_dir, model_tag, use_cuda):
+    """call.py:54-118.  ``net`` is a ``neusomatic_b200.network.NeuSomaticNet`` (possibly wrapped
+    in nn.DataParallel).  ``true_path`` maps each non-NONE candidate to its in-memory
+    ``non_transformed[:, :, 0:3]`` uint8 matrix (the reference writes it to a PNG, a lossless
+    round trip: call.py:89-95,128)."""
+    if not use_cuda:
+        raise RuntimeError("neusomatic_b200 scores on CUDA only")
+    net.eval()
+    final_preds, none_preds, true_path = {}, {}, {}
+    iii = j = 0
+    for data in call_loader:
+        (matrices, labels, var_pos_s, var_len_s, non_transformed_matrices), (paths) = data
+        iii += 1
+        j += len(paths[0])
+        matrices = matrices.cuda(non_blocking=True)
+        with torch.no_grad():
+            outputs, _ = net(matrices)
+        o1, o2, o3 = outputs
+        # one D2H per batch; softmax / argmax batched on the device
+        packed = torch.cat([o1, o2, o3, torch.softmax(o1, 1), torch.softmax(o3, 1),
+                            torch.max(o1, 1)[1].float()[:, None], torch.max(o3, 1)[1].float()[:, None]], 1).cpu().numpy()
+        n_before = len(final_preds)
+        build_pred_dicts(packed[:, 0:4], packed[:, 4:5], packed[:, 5:9], packed[:, 9:13], packed[:, 13:17],
+                         packed[:, 17].astype(np.int64), packed[:, 18].astype(np.int64), paths[0],
+                         vartype_classes, final_preds, none_preds)
+        if len(final_preds) != n_before:
+            nt = np.asarray(non_transformed_matrices)
+            for i, path_ in enumerate(paths[0]):
+                path = path_.split("/")[-1]
+                if path in final_preds and path not in true_path:
+                    true_path[path] = np.array(nt[i, :, :, 0:3])
+        if iii % 10 == 0:
+            logger.info("Called {} candidates in this batch.".format(j))
+    logger.info("Called {} candidates in this batch.".format(j))
+    return final_preds, none_preds, true_path
+
+
+def shard_ranges(n, world_size):
+    """Contiguous candidate ranges per rank: sizes differ by at most one."""
+    base, rem = divmod(n, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        size = base + (1 if r < rem else 0)
+        out.append((start, start + size))
+        start += size
+    return out
+
+
+class CandidateScorer:
+    """Scores compact candidates (uint8 [N,5,32,23] + center/coverages [+ annotations]) held in
+    host memory through ``nsc_score_host_u8``: the B200 replacement of the
+    DataLoader -> ``.cuda()`` -> ``net()`` -> per-candidate softmax chain of call.py:68-114."""
+
+    def __init__(self, checkpoint, ensemble=None, device=0, precision=None):
+        sd, meta = load_checkpoint(checkpoint)
+        C = sd["conv1.weight"].shape[1]
+        if ensemble is not None and C != (119 if ensemble else 26):
+            raise ValueError("checkpoint has %d input channels" % C)
+        self.meta = meta
+        self.coverage_thr = float(meta["coverage_thr"])
+        self.engine = Engine(sd, C, device=device, precision=precision,
+                             normalize_channels=meta["normalize_channels"])
+        self.C = C
+
+    def score(self, matrices, center, tumor_cov, normal_cov, anns=None):
+        """Returns dict of numpy arrays: o1,o2,o3 (logits), p1,p3 (softmax), arg1,arg3."""
+        n = matrices.shape[0]
+        m8 = np.ascontiguousarray(matrices, np.uint8)
+        meta = np.ascontiguousarray(np.stack([center, tumor_cov, normal_cov], 1), np.int32)
+        a255 = None
+        if self.C > 26:
+            if anns is None:
+                raise ValueError("ensemble model needs annotations")
+            a255 = np.ascontiguousarray(anns_to_255(anns))
+        outs = self.engine.score_host_u8(m8, meta, a255, self.coverage_thr, extras=True)
+        names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
+        res = {k: t.numpy() for k, t in zip(names, outs)}
+        assert res["o1"].shape[0] == n
+        return res
+
+    def call(self, cand, final_preds=None, none_preds=None):
+        """Candidates (neusomatic_b200.synth.Candidates-like) -> (final_preds, none_preds)."""
+        r = self.score(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, cand.anns)
+        return build_pred_dicts(r["o1"], r["o2"], r["o3"], r["p1"], r["p3"], r["arg1"], r["arg3"], cand.tags,
+                                VARTYPE_CLASSES, final_preds, none_preds)

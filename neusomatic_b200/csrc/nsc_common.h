@@ -1,0 +1,132 @@
+// Shared declarations of libneusomatic_cuda (internal; the public surface is
+// include/neusomatic_cuda.h).  Network constants follow the reference's
+// neusomatic/python/network.py:41-64.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "neusomatic_cuda.h"
+
+namespace nsc {
+
+constexpr int kDim = 64;       // network.py:43
+constexpr int kH = 5;          // pileup rows: gap, A, C, G, T
+constexpr int kW = 32;         // matrix width (generate_dataset.py matrix_window_size)
+constexpr int kFcIn = 1280;    // network.py:59-60
+constexpr int kFcHidden = 240; // network.py:61
+constexpr int kHeads = 9;      // fc2 (4) + fc3 (1) + fc4 (4), network.py:62-64
+constexpr int kStoredCh = 23;  // channels stored on disk (dataloader.py:38-39)
+constexpr int kBaseCh = 26;    // + center marker + two coverage channels (dataloader.py:390-394)
+
+// (ks_1, ks_2, dl_1, dl_2, mp_st) per NSBlock, network.py:48-53
+struct BlockSpec { int k1, k2, d1, d2, pool; };
+static const BlockSpec kBlocks[4] = {{3, 5, 1, 1, 1}, {3, 5, 1, 1, 2}, {3, 5, 2, 1, 2}, {3, 5, 4, 2, 2}};
+
+void set_error(const char* fmt, ...);
+
+#define NSC_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      nsc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                     __LINE__);                                                         \
+      return NSC_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
+struct Outputs {
+  float* type_logits;
+  float* pos;
+  float* len_logits;
+  float* type_prob;
+  float* len_prob;
+  int32_t* type_argmax;
+  int32_t* len_argmax;
+  Outputs offset(int64_t n) const {
+    Outputs o = *this;
+    if (o.type_logits) o.type_logits += 4 * n;
+    if (o.pos) o.pos += n;
+    if (o.len_logits) o.len_logits += 4 * n;
+    if (o.type_prob) o.type_prob += 4 * n;
+    if (o.len_prob) o.len_prob += 4 * n;
+    if (o.type_argmax) o.type_argmax += n;
+    if (o.len_argmax) o.len_argmax += n;
+    return o;
+  }
+};
+
+// ---- fp32 (CUDA-core) path: device weights -------------------------------------------------
+struct Fp32Weights {
+  float* conv1_w = nullptr;       // [3][C][64]  BN-folded, tap-major, cout innermost
+  float* conv1_b = nullptr;       // [64]
+  float* res_w[4][2] = {};        // [k*k][64][64]
+  float* res_b[4][2] = {};        // [64]
+  float* fc1_wt = nullptr;        // [1280][240] (transposed)
+  float* fc1_b = nullptr;         // [240]
+  float* head_w = nullptr;        // [9][240]  rows: fc2(4), fc3(1), fc4(4)
+  float* head_b = nullptr;        // [9]
+};
+
+}  // namespace nsc
+
+struct nsc_model {
+  int device = 0;
+  int C = 26;
+  int precision = NSC_PREC_FP32;
+  bool finalized = false;
+  bool normalize_channels = false;                     // checkpoint["normalize_channels"]
+  std::map<std::string, std::vector<float>> params;   // host copy of the state_dict
+  nsc::Fp32Weights w32;
+  // per-model device workspace (sized for chunk_cap candidates)
+  int64_t chunk_cap = 0;
+  float* act[3] = {nullptr, nullptr, nullptr};         // fp32 NCHW ping-pong buffers
+  float* fc1_out = nullptr;                            // [chunk_cap,240]
+  float* xin = nullptr;                                // assembled input for the u8 path
+  // debug copies (nsc_debug_internal)
+  bool debug = false;
+  int64_t debug_n = 0;
+  float* dbg[5] = {};
+  // host path (nsc_score_host_*)
+  cudaStream_t hstream[3] = {nullptr, nullptr, nullptr};   // h2d, compute, d2h
+  cudaEvent_t hevent[8] = {};   // in_ready[2], in_free[2], out_ready[2], out_free[2]
+  void* hstage_in[2] = {nullptr, nullptr};
+  void* hstage_out[2] = {nullptr, nullptr};
+  size_t hstage_in_bytes = 0;
+  int64_t launches = 0;
+  // per-kernel event timing (nsc_model_set_profile)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
+  std::vector<int> prof_slots;
+  size_t prof_used = 0;
+};
+
+namespace nsc {
+// nsc_api.cu: event bracket around one kernel launch when profiling is on
+void prof_begin(nsc_model* m, int slot, cudaStream_t s);
+void prof_end(nsc_model* m, cudaStream_t s);
+struct ProfScope {
+  nsc_model* m;
+  cudaStream_t s;
+  ProfScope(nsc_model* m_, int slot, cudaStream_t s_) : m(m_), s(s_) { if (m->profile) prof_begin(m, slot, s); }
+  ~ProfScope() { if (m->profile) prof_end(m, s); }
+};
+// nsc_fp32.cu
+int fp32_upload_weights(nsc_model* m, float bn_eps);
+void fp32_free_weights(nsc_model* m);
+int fp32_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
+// nsc_assemble.cu
+int assemble_channels(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255,
+                      float coverage_thr, int64_t n, float* x_out, cudaStream_t s);
+// folded parameters (host, double precision fold -> fp32)
+struct Folded {
+  std::vector<float> w;   // same layout as the PyTorch weight [Co][Ci][kh][kw]
+  std::vector<float> b;   // [Co]
+};
+int fold_conv_bn(const nsc_model* m, const std::string& conv, const std::string& bn, float eps,
+                 Folded* out);
+}  // namespace nsc

@@ -1,0 +1,136 @@
+"""Drop-in for the reference's ``network.py`` (neusomatic/python/network.py:17-78).
+
+Same class names, constructor, parameter / buffer names and shapes (so the bundled ``.pth``
+files load unchanged, with or without a ``module.`` prefix -- call.py:441-460) and the same
+return structure ``([o1, o2, o3], internal_outs)``.  In eval mode on a CUDA tensor the forward
+pass is ONE call into libneusomatic_cuda (hand-written sm_100a kernels) through the PyTorch
+custom op ``neusomatic_b200::forward_f32``; there is no CPU / eager fallback for inference.
+(Training mode keeps the plain ``nn`` layers so autograd works; the train step is outside this
+round's hot path.)
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .engine import Engine
+
+_ENGINES = {}   # id -> Engine, addressed from inside the custom op by an integer key
+
+
+@torch.library.custom_op("neusomatic_b200::forward_f32", mutates_args=())
+def _forward_f32_op(x: torch.Tensor, engine_key: int) -> list[torch.Tensor]:
+    eng = _ENGINES[engine_key]
+    return eng.forward_f32(x, extras=False)[:3]
+
+
+@_forward_f32_op.register_fake
+def _(x, engine_key):
+    B = x.shape[0]
+    return [x.new_empty((B, 4)), x.new_empty((B, 1)), x.new_empty((B, 4))]
+
+
+class NSBlock(nn.Module):
+    """network.py:17-36 (module structure only; the fused kernels implement the forward)."""
+
+    def __init__(self, dim, ks_1=3, ks_2=3, dl_1=1, dl_2=1, mp_ks=3, mp_st=1):
+        super().__init__()
+        self.dim = dim
+        self.conv_r1 = nn.Conv2d(dim, dim, kernel_size=ks_1, dilation=dl_1, padding=(dl_1 * (ks_1 - 1)) // 2)
+        self.bn_r1 = nn.BatchNorm2d(dim)
+        self.conv_r2 = nn.Conv2d(dim, dim, kernel_size=ks_2, dilation=dl_2, padding=(dl_2 * (ks_2 - 1)) // 2)
+        self.bn_r2 = nn.BatchNorm2d(dim)
+        self.pool_r2 = nn.MaxPool2d((1, mp_ks), padding=(0, (mp_ks - 1) // 2), stride=(1, mp_st))
+
+    def forward(self, x):
+        y1 = F.relu(self.bn_r1(self.conv_r1(x)))
+        y2 = self.bn_r2(self.conv_r2(y1))
+        return self.pool_r2(x + y2)
+
+
+class NeuSomaticNet(nn.Module):
+    def __init__(self, num_channels):
+        super().__init__()
+        dim = 64
+        self.num_channels = num_channels
+        self.conv1 = nn.Conv2d(num_channels, dim, kernel_size=(1, 3), padding=(0, 1), stride=1)
+        self.bn1 = nn.BatchNorm2d(dim)
+        self.pool1 = nn.MaxPool2d((1, 3), padding=(0, 1), stride=(1, 1))
+        self.nsblocks = [[3, 5, 1, 1, 3, 1], [3, 5, 1, 1, 3, 2], [3, 5, 2, 1, 3, 2], [3, 5, 4, 2, 3, 2]]
+        self.res_layers = nn.Sequential(*[NSBlock(dim, *spec) for spec in self.nsblocks])
+        ds = int(np.prod([s[5] for s in self.nsblocks]))
+        self.fc_dim = dim * 32 * 5 // ds
+        self.fc1 = nn.Linear(self.fc_dim, 240)
+        self.fc2 = nn.Linear(240, 4)
+        self.fc3 = nn.Linear(240, 1)
+        self.fc4 = nn.Linear(240, 4)
+        # Shared (by reference) with nn.DataParallel replicas, whose __dict__ is a shallow copy
+        # (call.py:417-419): lets a replica find the original parameters and reuse one packed
+        # engine per device instead of re-packing on every forward.
+        self._nsc = {"origin": weakref.ref(self), "engines": {}, "precision": None, "internals": False}
+
+    # -- engine management ------------------------------------------------------------------
+    def set_precision(self, precision):
+        """NSC_PREC_* of include/neusomatic_cuda.h (None = library default)."""
+        self._nsc["precision"] = precision
+        for key, _sig in self._nsc["engines"].values():
+            _ENGINES[key].set_precision(precision)
+
+    def return_internals(self, on=True):
+        """Also return [pool1_out, res_out, flat, fc1_out] like network.py:78 (debug; off by default
+        because every reference caller discards them: call.py:77, train.py:96,430)."""
+        self._nsc["internals"] = bool(on)
+
+    def _signature(self, origin):
+        return tuple((t.data_ptr(), t._version) for t in list(origin.parameters()) + list(origin.buffers()))
+
+    def engine(self, device):
+        origin = self._nsc["origin"]() or self
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        sig = self._signature(origin)
+        ent = self._nsc["engines"].get(idx)
+        if ent is not None and ent[1] == sig:
+            return ent[0]
+        if ent is not None:
+            _ENGINES.pop(ent[0]).close()
+        sd = {k: v for k, v in origin.state_dict().items()}
+        eng = Engine(sd, self.num_channels, device=idx, precision=self._nsc["precision"])
+        key = id(eng)
+        _ENGINES[key] = eng
+        self._nsc["engines"][idx] = (key, sig)
+        return key
+
+    # -- forward ------------------------------------------------------------------------------
+    def _forward_layers(self, x):
+        x = self.pool1(F.relu(self.bn1(self.conv1(x))))
+        internal_outs = [x]
+        x = self.res_layers(x)
+        internal_outs.append(x)
+        x2 = x.view(-1, self.fc_dim)
+        x3 = F.relu(self.fc1(x2))
+        internal_outs.extend([x2, x3])
+        return [self.fc2(x3), self.fc3(x3), self.fc4(x3)], internal_outs
+
+    def forward(self, x):
+        if self.training:
+            return self._forward_layers(x)
+        if not x.is_cuda:
+            raise RuntimeError("neusomatic_b200.NeuSomaticNet scores on CUDA only (sm_100a kernels); "
+                               "there is no CPU fallback -- move the batch to the GPU")
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        key = self.engine(x.device)
+        if self._nsc["internals"]:
+            _ENGINES[key].set_debug(x.shape[0])
+        outs = _forward_f32_op(x, key)
+        internals = []
+        if self._nsc["internals"]:
+            eng = _ENGINES[key]
+            internals = [eng.internal(0, x.shape[0]), eng.internal(4, x.shape[0])]
+            internals += [internals[1].reshape(-1, self.fc_dim), eng.internal(5, x.shape[0])]
+        return list(outs), internals

@@ -71,3 +71,15 @@ def test_call_variants_contract(golden):
             assert isinstance(e[3][0], np.float32) and len(e[3]) == 4 and len(e[6]) == 4
             assert e[1].shape == (1,)
             assert abs(sum(float(v) for v in e[3]) - 1.0) < 1e-3
+
+
+def test_torch_port_matches_reference(golden):
+    """oracle/torch_port.py (the timed CPU baseline) against the reference's own outputs."""
+    import torch
+    from oracle import torch_port
+    name, g, ck = golden
+    p = torch_port.prepare(ck["state_dict"])
+    o1, o2, o3 = torch_port.forward(p, torch.from_numpy(_assemble(g, ck)))
+    np.testing.assert_allclose(o1.numpy(), g["o1"], atol=1e-5)
+    np.testing.assert_allclose(o2.numpy(), g["o2"], atol=1e-5)
+    np.testing.assert_allclose(o3.numpy(), g["o3"], atol=1e-5)
