@@ -31,7 +31,7 @@ conv_fp32_kernel(const float* __restrict__ in,     // [B,Cin,5,W]
   constexpr int WP = W + 2 * PW;
   extern __shared__ float smem[];
   const int in_elems = Cin * kH * CPB * WP;
-  const int stage_elems = in_elems > kDim * kH * 32 ? in_elems : kDim * kH * 32;
+  const int stage_elems = ((in_elems > kDim * kH * 32 ? in_elems : kDim * kH * 32) + 3) & ~3;   // keeps w_s 16-B aligned
   float* in_s = smem;                 // [Cin][5][CPB][WP], zero padded in W
   float* w_s = smem + stage_elems;    // [KH*KW][kCiChunk][64]
   const int tid = threadIdx.x;
@@ -233,7 +233,7 @@ static int launch_conv(nsc_model* m, int slot, const float* in, const float* wt,
   constexpr int PW = DIL * (KW - 1) / 2;
   constexpr int WP = W + 2 * PW;
   int in_elems = Cin * kH * CPB * WP;
-  int stage = in_elems > kDim * kH * 32 ? in_elems : kDim * kH * 32;
+  int stage = ((in_elems > kDim * kH * 32 ? in_elems : kDim * kH * 32) + 3) & ~3;
   size_t smem = (size_t)(stage + KH * KW * kCiChunk * 64) * sizeof(float);
   auto kern = conv_fp32_kernel<KH, KW, DIL, W>;
   NSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
