@@ -143,7 +143,7 @@ int nsc_debug_assemble(nsc_model* m, const uint8_t* matrices_dev, const int32_t*
  * nsc_model_get_profile synchronises the device, adds the elapsed milliseconds and launch
  * counts per slot to ms[] / launches[] (NSC_PROF_SLOTS entries each) and resets the record.
  * Slots: 0 channel assembly, 1 conv1 stage, 2+2*i+j = res_layers[i].conv_r{j+1} stage
- * (i = 0..3, j = 0..1, epilogues fused), 10 fc1+heads, 11 input packing (tensor path). */
+ * (i = 0..3, j = 0..1, epilogues fused), 10 fc1+heads, 11 input packing, 12 max-pools (tensor path). */
 #define NSC_PROF_SLOTS 16
 int nsc_model_set_profile(nsc_model* m, int on);
 int nsc_model_get_profile(nsc_model* m, double* ms, int64_t* launches);

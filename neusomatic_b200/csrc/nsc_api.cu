@@ -130,22 +130,44 @@ static void free_workspace(nsc_model* m) {
   cudaFree(m->xin); m->xin = nullptr;
   for (int i = 0; i < 5; ++i) { cudaFree(m->dbg[i]); m->dbg[i] = nullptr; }
   m->chunk_cap = 0;
+  m->fp32_cap = 0;
+  m->xin_cap = 0;
+  m->fc1_cap = 0;
 }
 
+// Allocates the workspace of the ACTIVE precision mode and sets m->chunk_cap to its chunk size.
 static int ensure_workspace(nsc_model* m) {
-  if (m->chunk_cap > 0) return NSC_OK;
-  int64_t cap = 4096;
-  if (const char* e = getenv("NSC_CHUNK")) cap = std::max<int64_t>(64, atoll(e));
-  const size_t act_bytes = (size_t)cap * kDim * kH * kW * sizeof(float);
-  for (int i = 0; i < 3; ++i) NSC_CUDA_TRY(cudaMalloc((void**)&m->act[i], act_bytes));
-  NSC_CUDA_TRY(cudaMalloc((void**)&m->fc1_out, (size_t)cap * kFcHidden * sizeof(float)));
+  int64_t cap;
+  if (m->precision == NSC_PREC_FP32) {
+    if (m->fp32_cap == 0) {
+      cap = 4096;
+      if (const char* e = getenv("NSC_CHUNK")) cap = std::max<int64_t>(64, atoll(e));
+      const size_t act_bytes = (size_t)cap * kDim * kH * kW * sizeof(float);
+      for (int i = 0; i < 3; ++i) NSC_CUDA_TRY(cudaMalloc((void**)&m->act[i], act_bytes));
+      m->fp32_cap = cap;
+    }
+    cap = m->fp32_cap;
+  } else {
+    int c = umma_max_chunk(m);
+    if (c < 0) return NSC_E_CUDA;
+    cap = c;
+  }
+  if (m->fc1_cap < cap) {
+    cudaFree(m->fc1_out);
+    m->fc1_out = nullptr;
+    NSC_CUDA_TRY(cudaMalloc((void**)&m->fc1_out, (size_t)cap * kFcHidden * sizeof(float)));
+    m->fc1_cap = cap;
+  }
   m->chunk_cap = cap;
   return NSC_OK;
 }
 
 static int ensure_xin(nsc_model* m) {
-  if (m->xin) return NSC_OK;
+  if (m->xin && m->xin_cap >= m->chunk_cap) return NSC_OK;
+  cudaFree(m->xin);
+  m->xin = nullptr;
   NSC_CUDA_TRY(cudaMalloc((void**)&m->xin, (size_t)m->chunk_cap * m->C * kH * kW * sizeof(float)));
+  m->xin_cap = m->chunk_cap;
   return NSC_OK;
 }
 
@@ -153,8 +175,11 @@ static int forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs&
   switch (m->precision) {
     case NSC_PREC_FP32:
       return fp32_forward_chunk(m, x, n, o, s);
+    case NSC_PREC_SPLIT_BF16:
+    case NSC_PREC_BF16:
+      return umma_forward_chunk(m, x, n, o, s);
     default:
-      set_error("precision mode %d is not available in this build", m->precision);
+      set_error("unknown precision mode %d", m->precision);
       return NSC_E_STATE;
   }
 }
@@ -232,6 +257,7 @@ int nsc_model_finalize(nsc_model* m, float bn_eps) {
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
   int rc = fp32_upload_weights(m, bn_eps);
   if (rc != NSC_OK) return rc;
+  if ((rc = umma_upload_weights(m, bn_eps)) != NSC_OK) return rc;
   NSC_CUDA_TRY(cudaDeviceSynchronize());
   m->finalized = true;
   return NSC_OK;
@@ -239,7 +265,10 @@ int nsc_model_finalize(nsc_model* m, float bn_eps) {
 
 int nsc_model_set_precision(nsc_model* m, int precision) {
   if (!m) { set_error("model is NULL"); return NSC_E_INVALID; }
-  if (precision != NSC_PREC_FP32) { set_error("precision mode %d is not available in this build", precision); return NSC_E_INVALID; }
+  if (precision != NSC_PREC_FP32 && precision != NSC_PREC_SPLIT_BF16 && precision != NSC_PREC_BF16) {
+    set_error("unknown precision mode %d", precision);
+    return NSC_E_INVALID;
+  }
   m->precision = precision;
   return NSC_OK;
 }
@@ -339,7 +368,9 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
       cudaFree(m->hstage_in[i]);
       m->hstage_in[i] = nullptr;
       NSC_CUDA_TRY(cudaMalloc(&m->hstage_in[i], in_bytes));
-      if (!m->hstage_out[i]) NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
+      cudaFree(m->hstage_out[i]);
+      m->hstage_out[i] = nullptr;
+      NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
     }
     m->hstage_in_bytes = in_bytes;
   }
@@ -452,7 +483,7 @@ int nsc_model_get_profile(nsc_model* m, double* ms, int64_t* launches) {
 const char* nsc_profile_slot_name(int slot) {
   static const char* names[NSC_PROF_SLOTS] = {
       "assemble", "conv1", "res0.conv_r1", "res0.conv_r2", "res1.conv_r1", "res1.conv_r2", "res2.conv_r1",
-      "res2.conv_r2", "res3.conv_r1", "res3.conv_r2", "fc_heads", "pack_input", "", "", "", ""};
+      "res2.conv_r2", "res3.conv_r1", "res3.conv_r2", "fc_heads", "pack_input", "pool", "", "", ""};
   return (slot >= 0 && slot < NSC_PROF_SLOTS) ? names[slot] : "";
 }
 
@@ -471,6 +502,7 @@ int nsc_model_destroy(nsc_model* m) {
   DeviceGuard g(m->device);
   cudaDeviceSynchronize();
   fp32_free_weights(m);
+  umma_free(m);
   free_workspace(m);
   for (int i = 0; i < 2; ++i) { cudaFree(m->hstage_in[i]); cudaFree(m->hstage_out[i]); }
   for (int i = 0; i < 3; ++i) if (m->hstream[i]) cudaStreamDestroy(m->hstream[i]);

@@ -3,6 +3,7 @@
 // neusomatic/python/network.py:41-64.
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,18 +73,30 @@ struct Fp32Weights {
   float* head_b = nullptr;        // [9]
 };
 
+// ---- tensor-core (tcgen05) path: packed weights + packed hi/lo activation buffers ----------------
+struct UmmaState {
+  uint8_t* wpk[4][2] = {};              // per conv: swizzled bf16 hi/lo weight stages (nsc_umma.cu)
+  __nv_bfloat16* buf[4][2] = {};        // 4 activation tensors x (hi, lo): [cap/8][5][32][8][64]
+  float* conv1_out = nullptr;           // fp32 NCHW output of the conv1 stage
+  float* fc_in = nullptr;               // fp32 [cap,1280] input of fc1
+  int64_t cap = 0;
+  int num_sms = 148;
+};
+
 }  // namespace nsc
 
 struct nsc_model {
   int device = 0;
   int C = 26;
-  int precision = NSC_PREC_FP32;
+  int precision = NSC_PREC_SPLIT_BF16;
   bool finalized = false;
   bool normalize_channels = false;                     // checkpoint["normalize_channels"]
   std::map<std::string, std::vector<float>> params;   // host copy of the state_dict
   nsc::Fp32Weights w32;
+  nsc::UmmaState umma;
   // per-model device workspace (sized for chunk_cap candidates)
-  int64_t chunk_cap = 0;
+  int64_t chunk_cap = 0;                               // chunk size of the active precision mode
+  int64_t fp32_cap = 0, xin_cap = 0, fc1_cap = 0;
   float* act[3] = {nullptr, nullptr, nullptr};         // fp32 NCHW ping-pong buffers
   float* fc1_out = nullptr;                            // [chunk_cap,240]
   float* xin = nullptr;                                // assembled input for the u8 path
@@ -119,6 +132,13 @@ struct ProfScope {
 int fp32_upload_weights(nsc_model* m, float bn_eps);
 void fp32_free_weights(nsc_model* m);
 int fp32_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
+int fp32_conv1(nsc_model* m, const float* x, float* out, int64_t n, cudaStream_t s);
+int fp32_fc_heads(nsc_model* m, const float* x2, int64_t n, const Outputs& o, cudaStream_t s);
+// nsc_umma.cu
+int umma_upload_weights(nsc_model* m, float bn_eps);
+void umma_free(nsc_model* m);
+int umma_max_chunk(nsc_model* m);
+int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
 // nsc_assemble.cu
 int assemble_channels(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255,
                       float coverage_thr, int64_t n, float* x_out, cudaStream_t s);

@@ -277,9 +277,18 @@ int fp32_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o
   NSC_RUN((launch_conv<5, 5, 2, 8>(m, 9, A, w.res_w[3][1], w.res_b[3][1], Cc, Bf, n, 64, 0, 2, s)));
   NSC_RUN(dbg_copy(m, 4, Bf, n, 64 * 5 * 4, s));
 #undef NSC_RUN
+  return fp32_fc_heads(m, Bf, n, o, s);
+}
+
+int fp32_conv1(nsc_model* m, const float* x, float* out, int64_t n, cudaStream_t s) {
+  return launch_conv<1, 3, 1, 32>(m, 1, x, m->w32.conv1_w, m->w32.conv1_b, nullptr, out, n, m->C, 1, 1, s);
+}
+
+int fp32_fc_heads(nsc_model* m, const float* x2, int64_t n, const Outputs& o, cudaStream_t s) {
+  const Fp32Weights& w = m->w32;
   int64_t grid = (n + kFcCands - 1) / kFcCands;
   ProfScope prof(m, 10, s);
-  fc_heads_fp32_kernel<<<(unsigned)grid, 256, 0, s>>>(Bf, w.fc1_wt, w.fc1_b, w.head_w, w.head_b, m->fc1_out,
+  fc_heads_fp32_kernel<<<(unsigned)grid, 256, 0, s>>>(x2, w.fc1_wt, w.fc1_b, w.head_w, w.head_b, m->fc1_out,
                                                       (int)n, o);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches++;
