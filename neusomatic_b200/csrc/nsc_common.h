@@ -3,7 +3,6 @@
 // neusomatic/python/network.py:41-64.
 #pragma once
 
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -75,12 +74,15 @@ struct Fp32Weights {
 
 // ---- tensor-core (tcgen05) path: packed weights + packed hi/lo activation buffers ----------------
 struct UmmaState {
-  uint8_t* wpk[4][2] = {};              // per conv: swizzled bf16 hi/lo weight stages (nsc_umma.cu)
-  __nv_bfloat16* buf[4][2] = {};        // 4 activation tensors x (hi, lo): [cap/8][5][32][8][64]
-  float* conv1_out = nullptr;           // fp32 NCHW output of the conv1 stage
+  uint8_t* wpk1 = nullptr;              // conv1: swizzled fp16 hi/lo weight stages (nsc_umma.cu)
+  uint8_t* wpk[4][2] = {};              // res_layers[i].conv_r{1,2}
+  int nk1 = 1;                          // 32-channel input slices of conv1 (C = 26 -> 1, C = 119 -> 4)
+  uint16_t* xin[2] = {};                // packed network input (hi, lo): [cap/8][5][32][8][32*nk1]
+  uint16_t* buf[3][2] = {};             // 3 packed activation tensors x (hi, lo): [cap/8][5][32][8][64]
   float* fc_in = nullptr;               // fp32 [cap,1280] input of fc1
   int64_t cap = 0;
   int num_sms = 148;
+  bool weights_fit_fp16 = true;
 };
 
 }  // namespace nsc

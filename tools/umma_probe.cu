@@ -187,6 +187,80 @@ static bool run_mma_test(const char* name, MmaParams p, bool discover) {
   return ok;
 }
 
+// ---- operand-format probe: fp16 subnormals and mixed fp16 x bf16 operands ---------------------------
+__global__ void __launch_bounds__(128) probe_fmt(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B,
+                                                 float* __restrict__ D, int a_fmt, int b_fmt) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;
+  uint8_t* sB = base + 128 * 32;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * 16; i += 128) *(uint16_t*)(sA + swz_offset<32>(i / 16, (i % 16) / 8) + (i % 8) * 2) = A[i];
+  for (int i = tid; i < 64 * 16; i += 128) *(uint16_t*)(sB + swz_offset<32>(i / 16, (i % 16) / 8) + (i % 8) * 2) = B[i];
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    umma_f16(tmem, make_smem_desc(smem_u32(sA), 16, 256, kSwizzle32), make_smem_desc(smem_u32(sB), 16, 256, kSwizzle32), idesc, 0u);
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after_sync();
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * 64 + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+#include <cuda_fp16.h>
+static void run_fmt_test(const char* name, int a_fmt, int b_fmt, float a_scale) {
+  // A[m][k] = a_scale * (1 + m/256) for k == m % 16 else 0  ;  B[n][k] = (n + 1) for all k
+  std::vector<uint16_t> A(128 * 16, 0), B(64 * 16);
+  std::vector<float> Af(128 * 16, 0.f), Bf(64 * 16);
+  auto enc = [](float v, int fmt) -> uint16_t {
+    if (fmt == 1) return f2bf(v);
+    __half h = __float2half_rn(v);
+    uint16_t u; memcpy(&u, &h, 2); return u;
+  };
+  auto dec = [](uint16_t u, int fmt) -> float {
+    if (fmt == 1) return bf2f(u);
+    __half h; memcpy(&h, &u, 2); return __half2float(h);
+  };
+  for (int m = 0; m < 128; ++m) { int k = m % 16; A[m * 16 + k] = enc(a_scale * (1.f + m / 256.f), a_fmt); Af[m * 16 + k] = dec(A[m * 16 + k], a_fmt); }
+  for (int n = 0; n < 64; ++n) for (int k = 0; k < 16; ++k) { B[n * 16 + k] = enc((float)(n + 1), b_fmt); Bf[n * 16 + k] = dec(B[n * 16 + k], b_fmt); }
+  uint16_t *dA, *dB; float* dD;
+  CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dD, 128 * 64 * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(probe_fmt, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+  probe_fmt<<<1, 128, 16384>>>(dA, dB, dD, a_fmt, b_fmt);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("[fmt %s] kernel error: %s\n", name, cudaGetErrorString(e)); exit(3); }
+  std::vector<float> D(128 * 64);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  double maxrel = 0; int zeros = 0;
+  for (int m = 0; m < 128; ++m) for (int n = 0; n < 64; ++n) {
+    float ref = Af[m * 16 + m % 16] * Bf[n * 16 + m % 16];
+    if (D[m * 64 + n] == 0.f && ref != 0.f) zeros++;
+    maxrel = fmax(maxrel, fabs(D[m * 64 + n] - ref) / fabs(ref));
+  }
+  printf("[fmt %s] a_fmt=%d b_fmt=%d a_scale=%g: max rel err %.3g, outputs flushed to zero: %d / 8192 (ref sample %g got %g)\n",
+         name, a_fmt, b_fmt, a_scale, maxrel, zeros, Af[0] * Bf[0], D[0]);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
 // ---- issue-rate probe --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) probe_rate(int N, int M, int nacc, int iters, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -372,6 +446,13 @@ int main(int argc, char** argv) {
   run_mma_test("sw128 M64 N64 K64 (layout discovery)", {128, 64, 64, 64, 128, 0, 0, 1}, true);
   // 7. N=128 / N=256
   run_mma_test("sw128 M128 N128 K64", {128, 128, 128, 64, 128, 0, 0, 1}, false);
+  // 7b. operand formats
+  run_fmt_test("fp16 normal", 0, 0, 1.0f);
+  run_fmt_test("fp16 subnormal A (2^-18)", 0, 0, 3.814697265625e-06f);
+  run_fmt_test("fp16 subnormal A (2^-22)", 0, 0, 2.384185791015625e-07f);
+  run_fmt_test("A fp16 x B bf16", 0, 1, 1.0f);
+  run_fmt_test("A bf16 x B fp16", 1, 0, 1.0f);
+  run_fmt_test("A bf16 tiny (2^-30) x B fp16", 1, 0, 9.313225746154785e-10f);
   // 8. TMA
   run_tma_test(32, 64);
   run_tma_test(32, 32);
