@@ -184,6 +184,16 @@ static int forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs&
   }
 }
 
+static int ws_acquire(nsc_model* m, cudaStream_t s) {
+  if (!m->ws_event) NSC_CUDA_TRY(cudaEventCreateWithFlags(&m->ws_event, cudaEventDisableTiming));
+  NSC_CUDA_TRY(cudaStreamWaitEvent(s, m->ws_event, 0));
+  return NSC_OK;
+}
+static int ws_release(nsc_model* m, cudaStream_t s) {
+  NSC_CUDA_TRY(cudaEventRecord(m->ws_event, s));
+  return NSC_OK;
+}
+
 static int check_ready(nsc_model* m, int64_t B) {
   if (m == nullptr) { set_error("model is NULL"); return NSC_E_INVALID; }
   if (!m->finalized) { set_error("nsc_model_finalize has not been called"); return NSC_E_STATE; }
@@ -305,11 +315,12 @@ int nsc_forward_f32(nsc_model* m, const float* x_dev, int64_t B, float* type_log
   if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
   cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = ws_acquire(m, s)) != NSC_OK) return rc;
   for (int64_t i = 0; i < B; i += m->chunk_cap) {
     int64_t n = std::min<int64_t>(m->chunk_cap, B - i);
     if ((rc = forward_chunk(m, x_dev + i * m->C * kH * kW, n, o.offset(i), s)) != NSC_OK) return rc;
   }
-  return NSC_OK;
+  return ws_release(m, s);
 }
 
 int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* meta_dev, const float* anns255_dev,
@@ -328,6 +339,7 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
   cudaStream_t s = (cudaStream_t)stream;
   const int na = m->C - kBaseCh;
+  if ((rc = ws_acquire(m, s)) != NSC_OK) return rc;
   for (int64_t i = 0; i < B; i += m->chunk_cap) {
     int64_t n = std::min<int64_t>(m->chunk_cap, B - i);
     if ((rc = assemble_channels(m, matrices_dev + i * (kH * kW * kStoredCh), meta_dev + i * 3,
@@ -335,7 +347,7 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
       return rc;
     if ((rc = forward_chunk(m, m->xin, n, o.offset(i), s)) != NSC_OK) return rc;
   }
-  return NSC_OK;
+  return ws_release(m, s);
 }
 
 // --- host-buffer scoring: H2D / compute / D2H on three internal streams, two slots -----------
@@ -375,6 +387,7 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
     m->hstage_in_bytes = in_bytes;
   }
   cudaStream_t s_in = m->hstream[0], s_cmp = m->hstream[1], s_out = m->hstream[2];
+  if ((rc = ws_acquire(m, s_cmp)) != NSC_OK) return rc;
   cudaEvent_t* in_ready = &m->hevent[0];
   cudaEvent_t* in_free = &m->hevent[2];
   cudaEvent_t* out_ready = &m->hevent[4];
@@ -417,6 +430,7 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
     if (oh.len_argmax) NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_argmax + i, od.len_argmax, 4 * n, cudaMemcpyDeviceToHost, s_out));
     NSC_CUDA_TRY(cudaEventRecord(out_free[slot], s_out));
   }
+  if ((rc = ws_release(m, s_cmp)) != NSC_OK) return rc;
   NSC_CUDA_TRY(cudaStreamSynchronize(s_out));
   NSC_CUDA_TRY(cudaStreamSynchronize(s_cmp));
   return NSC_OK;
@@ -508,6 +522,7 @@ int nsc_model_destroy(nsc_model* m) {
   for (int i = 0; i < 3; ++i) if (m->hstream[i]) cudaStreamDestroy(m->hstream[i]);
   for (int i = 0; i < 8; ++i) if (m->hevent[i]) cudaEventDestroy(m->hevent[i]);
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
+  if (m->ws_event) cudaEventDestroy(m->ws_event);
   delete m;
   return NSC_OK;
 }

@@ -74,6 +74,7 @@ struct Fp32Weights {
 
 // ---- tensor-core (tcgen05) path: packed weights + packed hi/lo activation buffers ----------------
 struct UmmaState {
+  uint8_t* w1pk = nullptr;              // fc1: [2][20] tiles of [240][64] fp16, swizzle-128B (nsc_fc_umma.cu)
   uint8_t* wpk1 = nullptr;              // conv1: swizzled fp16 hi/lo weight stages (nsc_umma.cu)
   uint8_t* wpk[4][2] = {};              // res_layers[i].conv_r{1,2}
   int nk1 = 1;                          // 32-channel input slices of conv1 (C = 26 -> 1, C = 119 -> 4)
@@ -112,6 +113,9 @@ struct nsc_model {
   void* hstage_in[2] = {nullptr, nullptr};
   void* hstage_out[2] = {nullptr, nullptr};
   size_t hstage_in_bytes = 0;
+  // orders successive uses of the (single) workspace across streams: every entry point waits for it on
+  // its stream before touching the workspace and records it when its work is enqueued
+  cudaEvent_t ws_event = nullptr;
   int64_t launches = 0;
   // per-kernel event timing (nsc_model_set_profile)
   bool profile = false;
@@ -141,6 +145,9 @@ int umma_upload_weights(nsc_model* m, float bn_eps);
 void umma_free(nsc_model* m);
 int umma_max_chunk(nsc_model* m);
 int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
+// nsc_fc_umma.cu
+int fc_umma_upload_weights(nsc_model* m);
+int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);
 // nsc_assemble.cu
 int assemble_channels(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255,
                       float coverage_thr, int64_t n, float* x_out, cudaStream_t s);

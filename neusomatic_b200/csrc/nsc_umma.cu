@@ -572,12 +572,13 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
       if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 2, &max_abs))) != NSC_OK) return rc;
     }
   u.weights_fit_fp16 = max_abs < 6.0e4f;
-  return NSC_OK;
+  return fc_umma_upload_weights(m);
 }
 
 void umma_free(nsc_model* m) {
   UmmaState& u = m->umma;
   cudaFree(u.wpk1); u.wpk1 = nullptr;
+  cudaFree(u.w1pk); u.w1pk = nullptr;
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j) { cudaFree(u.wpk[i][j]); u.wpk[i][j] = nullptr; }
   for (int i = 0; i < 3; ++i)
@@ -718,12 +719,9 @@ int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o
   NSC_RUN(dbg_unpack(m, 3, X, 8, n, s));
   // block 3 (3x3 d4, 5x5 d2, pool stride 2) -> fp32 [B,1280] for fc1
   NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 2, 0, false>>(m, 8, X, u.wpk[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 2, 2, true>>(m, 9, Y, u.wpk[3][1], w.res_b[3][1], nullptr, u.fc_in, X, n, 0, s)));
-  if (m->debug) {
-    const int64_t k = std::min<int64_t>(n, m->debug_n);
-    NSC_CUDA_TRY(cudaMemcpyAsync(m->dbg[4], u.fc_in, (size_t)k * kFcIn * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  }
-  NSC_RUN(fp32_fc_heads(m, u.fc_in, n, o, s));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 2, 2, false>>(m, 9, Y, u.wpk[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s)));
+  NSC_RUN(dbg_unpack(m, 4, N, 4, n, s));
+  NSC_RUN(fc_umma_forward(m, N, n, o, s));
 #undef NSC_RUN
   return NSC_OK;
 }
