@@ -312,8 +312,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     float* stash_f = reinterpret_cast<float*>(stash);       // [2 cols][5][8 g][64 ch] fp32
     uint32_t u_it = 0;
     long long t_epi = 0, t_full = 0;
+    uint2 res_h[ITEMS][2], res_l[ITEMS][2];     // residual operands of the NEXT row to be processed
+    auto load_res = [&](int grp_, int sub_, uint32_t u_, int idx_) {
+      const int slot_ = (u_ & 1) ? idx_ : (idx_ < 2 ? 3 + idx_ : idx_ - 2);
+      const int h_ = slot_row<DIL>(slot_);
+      const size_t tile_ = ((((size_t)grp_ * kH + h_) * W + sub_ * Cfg::TW) * 8) * 64;
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = et + k * kEpiThreads, rr = i >> 3, ch = i & 7;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const size_t go = tile_ + rr * 64 + hh * 32 + ch * 4;
+          res_h[k][hh] = *reinterpret_cast<const uint2*>(args.res_hi + go);
+          res_l[k][hh] = *reinterpret_cast<const uint2*>(args.res_lo + go);
+        }
+      }
+    };
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
       for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
+        if (args.res_hi != nullptr) load_res(grp, sub, u_it, 0);
         long long t_c = clock64();
         mbar_wait(acc_full, u_it & 1);
         t_full += clock64() - t_c;
@@ -321,15 +338,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         tc_fence_after_sync();
         const uint32_t acc0 = tmem + (u_it & 1) * 192 + ((uint32_t)(q * 32) << 16) + half * 32;
         const int w0 = sub * Cfg::TW;
+        // the two accumulators the NEXT unit shares with this one are pulled into registers first and released
+        // immediately, so that the MMA issuer can start on them while this unit is still being post-processed
+        uint32_t r[32], rb[32];
+        tmem_ld_32x32b_x32(acc0 + ((u_it & 1) ? 0 : 3) * 64, r);
+        tmem_ld_32x32b_x32(acc0 + ((u_it & 1) ? 1 : 4) * 64, rb);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(shared_free);
 #pragma unroll 1
         for (int idx = 0; idx < kH; ++idx) {
-          // drain order: the two accumulators the NEXT unit shares with this one first
           const int slot = (u_it & 1) ? idx : (idx < 2 ? 3 + idx : idx - 2);
           const int h = slot_row<DIL>(slot);
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(acc0 + slot * 64, r);
-          tmem_ld_wait();
-          if (idx == 1) { tc_fence_before_sync(); mbar_arrive(shared_free); }
+          if (idx == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = rb[j];
+          } else if (idx >= 2) {
+            tmem_ld_32x32b_x32(acc0 + slot * 64, r);
+            tmem_ld_wait();
+          }
           if (idx == kH - 1) { tc_fence_before_sync(); mbar_arrive(all_free + 8 * (u_it & 1)); }
           // ---- phase A: this thread's row, 32 channels
           if (active) {
@@ -346,7 +373,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           }
           epi_bar();
           const size_t in_tile = ((((size_t)grp * kH + h) * W + w0) * 8) * 64;   // element offset of the tile
-          // ---- phase B1: residual add (coalesced items)
+          // ---- phase B1: residual add (coalesced items; the operands were prefetched one row ahead)
           if (args.res_hi != nullptr) {
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
@@ -354,15 +381,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
               float* p0 = stg + rr * 64 + ((ch ^ (rr & 7)) << 2);
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
-                const size_t go = in_tile + rr * 64 + hh * 32 + ch * 4;
-                const uint2 xh = *reinterpret_cast<const uint2*>(args.res_hi + go);
-                const uint2 xl = *reinterpret_cast<const uint2*>(args.res_lo + go);
-                const float2 a = join2(xh.x, xl.x), b = join2(xh.y, xl.y);
+                const float2 a = join2(res_h[k][hh].x, res_l[k][hh].x), b = join2(res_h[k][hh].y, res_l[k][hh].y);
                 float4 v = *reinterpret_cast<float4*>(p0 + hh * 32);
                 v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
                 *reinterpret_cast<float4*>(p0 + hh * 32) = v;
               }
             }
+            if (idx + 1 < kH) load_res(grp, sub, u_it, idx + 1);
             epi_bar();
           }
           // ---- phase B2: (pool and) split to hi/lo and store (coalesced items)
@@ -595,7 +620,7 @@ static int umma_ensure_workspace(nsc_model* m) {
     set_error("folded convolution weights exceed the fp16 range; use NSC_PREC_FP32 for this checkpoint");
     return NSC_E_STATE;
   }
-  int64_t cap = 8192;
+  int64_t cap = 32768;   // candidates per pass over the layer kernels (workspace: ~125 KB per candidate)
   if (const char* e = getenv("NSC_CHUNK")) cap = std::max<int64_t>(64, atoll(e));
   cap = (cap + 7) / 8 * 8;
   const size_t bytes = (size_t)cap * kH * 32 * 64 * sizeof(uint16_t);
