@@ -13,9 +13,11 @@ per GPU (default 65536: 1.09 GB of fp32 input, larger than the 126 MB L2); the d
 
 Printed JSON (one line, rank 0):
   value   candidates/s, whole job, inputs resident in HBM (nsc_forward_f32 on device tensors)
-  e2e     candidates/s through the C-ABI host call (nsc_score_host_f32: pinned host fp32
-          matrices in, host results out, H2D/D2H inside the timed region); e2e_u8 is the
-          compact uint8 interface (nsc_score_host_u8, channel assembly on the device)
+  e2e     candidates/s through the C-ABI host call nsc_score_host_u8 (call.py:68-83 batch step): pinned
+          host uint8 pileup matrices + tag fields in (what the TSV decoder yields, dataloader.py:38-58),
+          host results out, H2D/D2H inside the timed region, channel assembly on the device;
+          e2e_f32 is the same through nsc_score_host_f32 (assembled fp32 [B,C,5,32] matrices in,
+          PCIe-bound at 16.6 KB per candidate)
   roofline  tensor roofline of the dominant kernel family, timed live with CUDA events
   cpu_baseline  oracle/torch_port.py (the reference's forward restated on the PyTorch CPU
           operators the reference itself runs) on a bounded sample, rank 0 / N=1 only
@@ -251,10 +253,10 @@ def main():
                 dist.all_reduce(el, op=dist.ReduceOp.MAX)
             res[name] = world * B * k / float(el.item())
         d2h = B * 19 * 4
-        e2e = {"value": res["f32"], "unit": "candidates/s", "h2d_bytes_per_step": B * C * 160 * 4,
-               "d2h_bytes_per_step": d2h, "api": "nsc_score_host_f32 (pinned fp32 [B,26,5,32] in, host results out)"}
-        e2e_u8 = {"value": res["u8"], "unit": "candidates/s", "h2d_bytes_per_step": B * (3680 + 12),
-                  "d2h_bytes_per_step": d2h, "api": "nsc_score_host_u8 (pinned uint8 [B,5,32,23] + meta in)"}
+        e2e = {"value": res["u8"], "unit": "candidates/s", "h2d_bytes_per_step": B * (3680 + 12),
+               "d2h_bytes_per_step": d2h, "api": "nsc_score_host_u8 (pinned uint8 [B,5,32,23] + int32 [B,3] in, host results out)"}
+        e2e_u8 = {"value": res["f32"], "unit": "candidates/s", "h2d_bytes_per_step": B * C * 160 * 4,
+                  "d2h_bytes_per_step": d2h, "api": "nsc_score_host_f32 (pinned fp32 [B,26,5,32] in, host results out)"}
 
     # ---- roofline of the dominant kernel family (the eight 64->64 convolutions) -------------------
     pk = peaks()
@@ -292,7 +294,7 @@ def main():
                        "batch_per_gpu": B, "candidates_per_step": world * B,
                        "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
                        "sharding": "contiguous candidate ranges per rank, no collective on the data path"},
-            "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_f32": e2e_u8, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
             "clocks": clocks,
         }), flush=True)
     if world > 1:

@@ -171,6 +171,10 @@ static int ensure_xin(nsc_model* m) {
   return NSC_OK;
 }
 
+// uint8 interface: assemble into m->xin + forward (fp32 path) or the fused assemble+pack (tensor path)
+static int forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float thr, int64_t n,
+                            const Outputs& o, cudaStream_t s);
+
 static int forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s) {
   switch (m->precision) {
     case NSC_PREC_FP32:
@@ -182,6 +186,15 @@ static int forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs&
       set_error("unknown precision mode %d", m->precision);
       return NSC_E_STATE;
   }
+}
+
+static int forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float thr, int64_t n,
+                            const Outputs& o, cudaStream_t s) {
+  if (m->precision != NSC_PREC_FP32) return umma_forward_chunk_u8(m, mat, meta, anns255, thr, n, o, s);
+  int rc = ensure_xin(m);
+  if (rc != NSC_OK) return rc;
+  if ((rc = assemble_channels(m, mat, meta, anns255, thr, n, m->xin, s)) != NSC_OK) return rc;
+  return forward_chunk(m, m->xin, n, o, s);
 }
 
 static int ws_acquire(nsc_model* m, cudaStream_t s) {
@@ -335,17 +348,15 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
   DeviceGuard g(m->device);
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
   if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
-  if ((rc = ensure_xin(m)) != NSC_OK) return rc;
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
   cudaStream_t s = (cudaStream_t)stream;
   const int na = m->C - kBaseCh;
   if ((rc = ws_acquire(m, s)) != NSC_OK) return rc;
   for (int64_t i = 0; i < B; i += m->chunk_cap) {
     int64_t n = std::min<int64_t>(m->chunk_cap, B - i);
-    if ((rc = assemble_channels(m, matrices_dev + i * (kH * kW * kStoredCh), meta_dev + i * 3,
-                                anns255_dev ? anns255_dev + i * na : nullptr, coverage_thr, n, m->xin, s)) != NSC_OK)
+    if ((rc = forward_chunk_u8(m, matrices_dev + i * (kH * kW * kStoredCh), meta_dev + i * 3,
+                               anns255_dev ? anns255_dev + i * na : nullptr, coverage_thr, n, o.offset(i), s)) != NSC_OK)
       return rc;
-    if ((rc = forward_chunk(m, m->xin, n, o.offset(i), s)) != NSC_OK) return rc;
   }
   return ws_release(m, s);
 }
@@ -367,8 +378,9 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
   if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
   if ((rc = ensure_host_path(m)) != NSC_OK) return rc;
-  if (u8 && (rc = ensure_xin(m)) != NSC_OK) return rc;
-  const int64_t cap = m->chunk_cap;
+  // slice size of the copy/compute pipeline: small enough that the first H2D does not delay the first kernel,
+  // large enough to keep the layer kernels efficient
+  const int64_t cap = std::min<int64_t>(m->chunk_cap, u8 ? 16384 : 8192);
   const int na = m->C - kBaseCh;
   const size_t in_per = u8 ? (size_t)kH * kW * kStoredCh : (size_t)m->C * kH * kW * sizeof(float);
   const size_t meta_per = u8 ? 3 * sizeof(int32_t) : 0;
@@ -380,11 +392,16 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
       cudaFree(m->hstage_in[i]);
       m->hstage_in[i] = nullptr;
       NSC_CUDA_TRY(cudaMalloc(&m->hstage_in[i], in_bytes));
+    }
+    m->hstage_in_bytes = in_bytes;
+  }
+  if (m->hstage_out_cap < cap) {
+    for (int i = 0; i < 2; ++i) {
       cudaFree(m->hstage_out[i]);
       m->hstage_out[i] = nullptr;
       NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
     }
-    m->hstage_in_bytes = in_bytes;
+    m->hstage_out_cap = cap;
   }
   cudaStream_t s_in = m->hstream[0], s_cmp = m->hstream[1], s_out = m->hstream[2];
   if ((rc = ws_acquire(m, s_cmp)) != NSC_OK) return rc;
@@ -412,9 +429,8 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
     Outputs od{dout, dout + 4 * cap, dout + 5 * cap, dout + 9 * cap, dout + 13 * cap,
                (int32_t*)(dout + 17 * cap), (int32_t*)(dout + 18 * cap)};
     if (u8) {
-      if ((rc = assemble_channels(m, (const uint8_t*)din, (const int32_t*)dmeta, ann_per ? (const float*)dann : nullptr,
-                                  coverage_thr, n, m->xin, s_cmp)) != NSC_OK) return rc;
-      if ((rc = forward_chunk(m, m->xin, n, od, s_cmp)) != NSC_OK) return rc;
+      if ((rc = forward_chunk_u8(m, (const uint8_t*)din, (const int32_t*)dmeta, ann_per ? (const float*)dann : nullptr,
+                                 coverage_thr, n, od, s_cmp)) != NSC_OK) return rc;
     } else {
       if ((rc = forward_chunk(m, (const float*)din, n, od, s_cmp)) != NSC_OK) return rc;
     }

@@ -113,6 +113,7 @@ struct nsc_model {
   void* hstage_in[2] = {nullptr, nullptr};
   void* hstage_out[2] = {nullptr, nullptr};
   size_t hstage_in_bytes = 0;
+  int64_t hstage_out_cap = 0;
   // orders successive uses of the (single) workspace across streams: every entry point waits for it on
   // its stream before touching the workspace and records it when its work is enqueued
   cudaEvent_t ws_event = nullptr;
@@ -145,12 +146,16 @@ int umma_upload_weights(nsc_model* m, float bn_eps);
 void umma_free(nsc_model* m);
 int umma_max_chunk(nsc_model* m);
 int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
+int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float coverage_thr,
+                          int64_t n, const Outputs& o, cudaStream_t s);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);
 // nsc_assemble.cu
 int assemble_channels(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255,
                       float coverage_thr, int64_t n, float* x_out, cudaStream_t s);
+int assemble_pack(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float coverage_thr, int64_t n,
+                  uint16_t* hi, uint16_t* lo, int Cpad, cudaStream_t s);
 // folded parameters (host, double precision fold -> fp32)
 struct Folded {
   std::vector<float> w;   // same layout as the PyTorch weight [Co][Ci][kh][kw]

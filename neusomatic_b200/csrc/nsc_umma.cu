@@ -706,19 +706,38 @@ int umma_max_chunk(nsc_model* m) {
   return rc == NSC_OK ? (int)m->umma.cap : -1;
 }
 
+static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s);
+
 int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s) {
   if (n == 0) return NSC_OK;
   int rc;
   if ((rc = umma_ensure_workspace(m)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
-  const Fp32Weights& w = m->w32;
-#define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
   {
     ProfScope prof(m, 11, s);
     pack_nchw_kernel<<<(unsigned)(((n + 7) / 8) * kH * u.nk1), 256, 0, s>>>(x, u.xin[0], u.xin[1], (int)n, m->C, u.nk1 * 32);
     NSC_CUDA_TRY(cudaGetLastError());
     m->launches++;
   }
+  return umma_run(m, n, o, s);
+}
+
+// uint8 interface: channel assembly (dataloader.py:383-417) fused with the hi/lo packing
+int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float coverage_thr,
+                          int64_t n, const Outputs& o, cudaStream_t s) {
+  if (n == 0) return NSC_OK;
+  int rc;
+  if ((rc = umma_ensure_workspace(m)) != NSC_OK) return rc;
+  UmmaState& u = m->umma;
+  if ((rc = assemble_pack(m, mat, meta, anns255, coverage_thr, n, u.xin[0], u.xin[1], u.nk1 * 32, s)) != NSC_OK) return rc;
+  return umma_run(m, n, o, s);
+}
+
+static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
+  int rc;
+  UmmaState& u = m->umma;
+  const Fp32Weights& w = m->w32;
+#define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
   uint16_t** X = u.buf[0];   // block input (and residual)
   uint16_t** Y = u.buf[1];   // relu(bn(conv_r1))
   uint16_t** N = u.buf[2];   // pooled block output
