@@ -264,11 +264,15 @@ def main():
     conv_launches = sum(v[1] for k_, v in prof.items() if k_.startswith("res"))
     total_ms = sum(v[0] for v in prof.values())
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]     # ncu capture, 32768-candidate launches
     if conv_ms > 0:
         cands = B * args.steps
         achieved = cands * 2 * CONV_STACK_MACS / (conv_ms / 1000.0) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                 "kernel": eng.kernel_name, "kernel_launches": conv_launches,
                 "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                 "kernel_share_of_step": conv_ms / total_ms if total_ms else None,
