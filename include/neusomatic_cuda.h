@@ -156,6 +156,24 @@ const char* nsc_model_kernel_name(const nsc_model* m);
 
 int nsc_model_destroy(nsc_model* m);
 
+/* ---- candidate TSV decoder (host side; no GPU involved) -------------------------------------------------
+ * Replaces extract_zlib / candidate_loader_tsv / extract_info_tsv (dataloader.py:38-123) and the tag parsing
+ * of NeuSomaticDataset.__getitem__ (dataloader.py:267-274) for inference: mmaps a candidates_*.tsv
+ * (generate_dataset.py:1569-1581), indexes its lines itself (the pickled .idx is not needed) and inflates a
+ * range of candidates, multi-threaded, straight into the batch buffers nsc_score_host_u8 consumes. */
+typedef struct nsc_tsv nsc_tsv;
+int nsc_tsv_open(nsc_tsv** out, const char* path);
+int64_t nsc_tsv_count(const nsc_tsv* t);
+/* matrices [n,5,32,23] uint8; meta [n,3] int32 = (center, tumor_cov, normal_cov); anns255 [n,num_anns] fp32 =
+ * float(double(text) * 255.0) or NULL when num_anns == 0; labels [n,2] int32 = (type index in
+ * DEL,INS,NONE,SNP or -1, length) or NULL.  num_threads <= 0: all hardware threads.  Fails (NSC_E_INVALID,
+ * text in nsc_last_error) on malformed lines, like the reference's worker returning None. */
+int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* matrices, int32_t* meta,
+                   float* anns255, int32_t* labels, int num_threads);
+/* pointer into the mapped file + length of candidate i's tag (field 3 of the line; not NUL-terminated) */
+int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len);
+int nsc_tsv_close(nsc_tsv* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,11 @@ SIGNATURES = {
     "nsc_model_launch_count": (_i64, [_vp]),
     "nsc_model_kernel_name": (C.c_char_p, [_vp]),
     "nsc_model_destroy": (_i32, [_vp]),
+    "nsc_tsv_open": (_i32, [C.POINTER(_vp), C.c_char_p]),
+    "nsc_tsv_count": (_i64, [_vp]),
+    "nsc_tsv_decode": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32]),
+    "nsc_tsv_tag": (_i32, [_vp, _i64, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
+    "nsc_tsv_close": (_i32, [_vp]),
 }
 
 _lib = None

@@ -25,7 +25,7 @@ def _nvcc():
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def is_stale():
@@ -41,7 +41,7 @@ def build_lib(force=False, verbose=False):
     """Compile every .cu under csrc/ for sm_100a into one shared library."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + sources() + ["-lz"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)

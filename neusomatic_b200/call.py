@@ -130,16 +130,18 @@ class CandidateScorer:
                              normalize_channels=meta["normalize_channels"])
         self.C = C
 
-    def score(self, matrices, center, tumor_cov, normal_cov, anns=None):
-        """Returns dict of numpy arrays: o1,o2,o3 (logits), p1,p3 (softmax), arg1,arg3."""
+    def score(self, matrices, center, tumor_cov, normal_cov, anns=None, anns255=None):
+        """Returns dict of numpy arrays: o1,o2,o3 (logits), p1,p3 (softmax), arg1,arg3.
+        ``anns`` are the annotation values of the TSV (dataloader.py:44-58); ``anns255`` the pre-scaled
+        float(double(ann) * 255.0) the C++ decoder emits."""
         n = matrices.shape[0]
         m8 = np.ascontiguousarray(matrices, np.uint8)
         meta = np.ascontiguousarray(np.stack([center, tumor_cov, normal_cov], 1), np.int32)
         a255 = None
         if self.C > 26:
-            if anns is None:
+            if anns is None and anns255 is None:
                 raise ValueError("ensemble model needs annotations")
-            a255 = np.ascontiguousarray(anns_to_255(anns))
+            a255 = np.ascontiguousarray(anns255 if anns255 is not None else anns_to_255(anns), np.float32)
         outs = self.engine.score_host_u8(m8, meta, a255, self.coverage_thr, extras=True)
         names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
         res = {k: t.numpy() for k, t in zip(names, outs)}
@@ -148,6 +150,20 @@ class CandidateScorer:
 
     def call(self, cand, final_preds=None, none_preds=None):
         """Candidates (neusomatic_b200.synth.Candidates-like) -> (final_preds, none_preds)."""
-        r = self.score(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, cand.anns)
+        r = self.score(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, cand.anns,
+                       getattr(cand, "anns255", None))
         return build_pred_dicts(r["o1"], r["o2"], r["o3"], r["p1"], r["p3"], r["arg1"], r["arg3"], cand.tags,
                                 VARTYPE_CLASSES, final_preds, none_preds)
+
+    def call_tsv(self, path, batch=65536, num_threads=0, final_preds=None, none_preds=None):
+        """call.py:504-534 for one candidates_*.tsv: C++ decode (csrc/nsc_tsv.cpp) -> nsc_score_host_u8 ->
+        (final_preds, none_preds), in slices of ``batch`` candidates."""
+        from .tsv import CandidateTSV
+        tsv = CandidateTSV(path, num_anns=self.C - 26, num_threads=num_threads)
+        final_preds = {} if final_preds is None else final_preds
+        none_preds = {} if none_preds is None else none_preds
+        for first in range(0, len(tsv), batch):
+            cand = tsv.decode(first, min(batch, len(tsv) - first))
+            self.call(cand, final_preds, none_preds)
+        tsv.close()
+        return final_preds, none_preds

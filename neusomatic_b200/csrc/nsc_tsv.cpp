@@ -1,0 +1,279 @@
+// Candidate-TSV decoder (host side): the C++ restatement of the reference's
+// neusomatic/python/dataloader.py:38-58 (extract_zlib, candidate_loader_tsv) and of the tag parsing in
+// NeuSomaticDataset.__getitem__ (dataloader.py:267-274).  File format (generate_dataset.py:654-657,
+// 1569-1581): one line per candidate,
+//     "{i}\t1\t{tag}\t{base64(zlib(uint8[5,32,23]))}[\t{ann} ...]\n"
+//     tag = "{chrom}.{pos}.{ref}.{alt}.{DEL|INS|NONE|SNP}.{center}.{len}.{tumor_cov}.{normal_cov}"
+// The decoder mmaps the file, indexes the lines and inflates a range of candidates straight into the
+// caller's (pinned) batch buffers in the layout nsc_score_host_u8 / nsc_forward_u8 consume.
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "neusomatic_cuda.h"
+
+namespace nsc {
+void set_error(const char* fmt, ...);
+}
+
+struct nsc_tsv {
+  int fd = -1;
+  const char* data = nullptr;
+  size_t size = 0;
+  std::vector<size_t> line_start;   // offsets of non-empty lines (+ sentinel = size)
+};
+
+namespace {
+
+constexpr int kMatrixBytes = 5 * 32 * 23;
+
+struct Field { const char* p; size_t n; };
+
+// split on runs of whitespace (python str.split() semantics used by dataloader.py:44)
+inline bool next_field(const char*& p, const char* end, Field* f) {
+  while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+  if (p >= end) return false;
+  const char* s = p;
+  while (p < end && *p != ' ' && *p != '\t' && *p != '\r') ++p;
+  f->p = s;
+  f->n = (size_t)(p - s);
+  return true;
+}
+
+struct B64 {
+  int8_t t[256];
+  B64() {
+    memset(t, -1, sizeof t);
+    const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    for (int i = 0; i < 64; ++i) t[(unsigned char)a[i]] = (int8_t)i;
+  }
+};
+const B64 kB64;
+
+// returns decoded length or -1
+inline int b64_decode(const char* s, size_t n, uint8_t* out, size_t cap) {
+  while (n > 0 && s[n - 1] == '=') --n;
+  size_t o = 0;
+  uint32_t acc = 0;
+  int bits = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const int v = kB64.t[(unsigned char)s[i]];
+    if (v < 0) return -1;
+    acc = (acc << 6) | (uint32_t)v;
+    bits += 6;
+    if (bits >= 8) {
+      bits -= 8;
+      if (o >= cap) return -1;
+      out[o++] = (uint8_t)(acc >> bits);
+    }
+  }
+  return (int)o;
+}
+
+inline bool parse_int(const char* p, size_t n, long* v) {
+  if (n == 0 || n > 18) return false;
+  char buf[24];
+  memcpy(buf, p, n);
+  buf[n] = 0;
+  char* e;
+  *v = strtol(buf, &e, 10);
+  return *e == 0;
+}
+
+const char* kTypes[4] = {"DEL", "INS", "NONE", "SNP"};   // call.py:407
+
+struct DecodeJob {
+  const nsc_tsv* t;
+  int64_t first, n;
+  int num_anns;
+  uint8_t* matrices;
+  int32_t* meta;
+  float* anns255;
+  int32_t* labels;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> failed{0};
+  std::string err;
+};
+
+void decode_range(DecodeJob* job) {
+  std::vector<uint8_t> comp(16384);
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit(&zs) != Z_OK) { job->failed = 1; return; }
+  for (;;) {
+    const int64_t k0 = job->next.fetch_add(64);
+    if (k0 >= job->n || job->failed.load()) break;
+    const int64_t k1 = std::min<int64_t>(job->n, k0 + 64);
+    for (int64_t k = k0; k < k1; ++k) {
+      const size_t li = (size_t)(job->first + k);
+      const char* p = job->t->data + job->t->line_start[li];
+      const char* end = job->t->data + job->t->line_start[li + 1];
+      while (end > p && (end[-1] == '\n' || end[-1] == '\r')) --end;
+      Field f[4];
+      bool ok = true;
+      for (int i = 0; i < 4 && ok; ++i) ok = next_field(p, end, &f[i]);
+      char msg[160] = "";
+      if (!ok) snprintf(msg, sizeof msg, "line %zu: fewer than 4 fields", li);
+      // tag: the last five dot-separated fields are type.center.length.tumor_cov.normal_cov (dataloader.py:267-274)
+      long center = 0, length = 0, tcov = 0, ncov = 0;
+      int type_idx = -1;
+      if (ok) {
+        const char* tb = f[2].p;
+        const char* te = tb + f[2].n;
+        for (const char* q = te; q > tb; --q)
+          if (q[-1] == '/') { tb = q; break; }        // path_.split("/")[-1]
+        const char* dots[5];
+        int nd = 0;
+        for (const char* q = te; q > tb && nd < 5; --q)
+          if (q[-1] == '.') dots[nd++] = q - 1;
+        // the reference unpacks exactly 9 fields
+        int total_dots = 0;
+        for (const char* q = tb; q < te; ++q) total_dots += *q == '.';
+        if (nd < 5 || total_dots != 8) { ok = false; snprintf(msg, sizeof msg, "line %zu: tag does not have 9 fields", li); }
+        if (ok) {
+          ok = parse_int(dots[0] + 1, (size_t)(te - dots[0] - 1), &ncov) && parse_int(dots[1] + 1, (size_t)(dots[0] - dots[1] - 1), &tcov) &&
+               parse_int(dots[2] + 1, (size_t)(dots[1] - dots[2] - 1), &length) && parse_int(dots[3] + 1, (size_t)(dots[2] - dots[3] - 1), &center);
+          const size_t tn = (size_t)(dots[3] - dots[4] - 1);
+          for (int i = 0; i < 4; ++i)
+            if (strlen(kTypes[i]) == tn && memcmp(kTypes[i], dots[4] + 1, tn) == 0) type_idx = i;
+          if (!ok) snprintf(msg, sizeof msg, "line %zu: non-integer tag field", li);
+        }
+      }
+      // image: base64 -> zlib -> uint8[5,32,23]  (dataloader.py:38-39)
+      if (ok) {
+        const size_t need = f[3].n * 3 / 4 + 4;
+        if (comp.size() < need) comp.resize(need);
+        const int clen = b64_decode(f[3].p, f[3].n, comp.data(), comp.size());
+        if (clen < 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: invalid base64", li); }
+        if (ok) {
+          inflateReset(&zs);
+          zs.next_in = comp.data();
+          zs.avail_in = (uInt)clen;
+          zs.next_out = job->matrices + (size_t)k * kMatrixBytes;
+          zs.avail_out = kMatrixBytes;
+          const int rc = inflate(&zs, Z_FINISH);
+          if (rc != Z_STREAM_END || zs.total_out != (uLong)kMatrixBytes) {
+            ok = false;
+            snprintf(msg, sizeof msg, "line %zu: zlib stream does not hold %d bytes", li, kMatrixBytes);
+          }
+        }
+      }
+      if (ok) {
+        job->meta[k * 3 + 0] = (int32_t)center;
+        job->meta[k * 3 + 1] = (int32_t)tcov;
+        job->meta[k * 3 + 2] = (int32_t)ncov;
+        if (job->labels) { job->labels[k * 2 + 0] = type_idx; job->labels[k * 2 + 1] = (int32_t)length; }
+        // annotations: float(text) * 255.0 in float64, cast to fp32 (dataloader.py:395-396, then .float())
+        int na = 0;
+        Field a;
+        while (next_field(p, end, &a)) {
+          if (na < job->num_anns && job->anns255) {
+            char buf[64];
+            const size_t m = a.n < 63 ? a.n : 63;
+            memcpy(buf, a.p, m);
+            buf[m] = 0;
+            char* e;
+            const double v = strtod(buf, &e);
+            if (*e != 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: bad annotation '%s'", li, buf); break; }
+            job->anns255[(size_t)k * job->num_anns + na] = (float)(v * 255.0);
+          }
+          ++na;
+        }
+        if (ok && na != job->num_anns) { ok = false; snprintf(msg, sizeof msg, "line %zu: %d annotations, expected %d", li, na, job->num_anns); }
+      }
+      if (!ok) {
+        if (job->failed.exchange(1) == 0) job->err = msg;
+        break;
+      }
+    }
+  }
+  inflateEnd(&zs);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nsc_tsv_open(nsc_tsv** out, const char* path) {
+  if (!out || !path) { nsc::set_error("NULL argument"); return NSC_E_INVALID; }
+  *out = nullptr;
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { nsc::set_error("cannot open '%s'", path); return NSC_E_INVALID; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); nsc::set_error("fstat failed on '%s'", path); return NSC_E_INVALID; }
+  nsc_tsv* t = new nsc_tsv();
+  t->fd = fd;
+  t->size = (size_t)st.st_size;
+  if (t->size > 0) {
+    void* p = mmap(nullptr, t->size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) { close(fd); delete t; nsc::set_error("mmap failed on '%s'", path); return NSC_E_NOMEM; }
+    t->data = (const char*)p;
+    madvise(p, t->size, MADV_SEQUENTIAL);
+  }
+  size_t pos = 0;
+  while (pos < t->size) {
+    const char* nl = (const char*)memchr(t->data + pos, '\n', t->size - pos);
+    const size_t e = nl ? (size_t)(nl - t->data) + 1 : t->size;
+    bool blank = true;
+    for (size_t i = pos; i < e && blank; ++i) blank = t->data[i] == '\n' || t->data[i] == '\r' || t->data[i] == ' ' || t->data[i] == '\t';
+    if (!blank) t->line_start.push_back(pos);
+    pos = e;
+  }
+  t->line_start.push_back(t->size);
+  *out = t;
+  return NSC_OK;
+}
+
+int64_t nsc_tsv_count(const nsc_tsv* t) { return t ? (int64_t)t->line_start.size() - 1 : -1; }
+
+int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* matrices, int32_t* meta, float* anns255,
+                   int32_t* labels, int num_threads) {
+  if (!t || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("candidate range out of bounds"); return NSC_E_INVALID; }
+  if (n == 0) return NSC_OK;
+  if (!matrices || !meta || num_anns < 0 || (num_anns > 0 && !anns255)) { nsc::set_error("NULL output buffer"); return NSC_E_INVALID; }
+  DecodeJob job;
+  job.t = t; job.first = first; job.n = n; job.num_anns = num_anns;
+  job.matrices = matrices; job.meta = meta; job.anns255 = anns255; job.labels = labels;
+  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min<int>(nt, (int)((n + 63) / 64)));
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) th.emplace_back(decode_range, &job);
+  decode_range(&job);
+  for (auto& x : th) x.join();
+  if (job.failed.load()) { nsc::set_error("%s", job.err.empty() ? "TSV decode failed" : job.err.c_str()); return NSC_E_INVALID; }
+  return NSC_OK;
+}
+
+int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len) {
+  if (!t || !tag || !len || i < 0 || i >= nsc_tsv_count(t)) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  const char* p = t->data + t->line_start[(size_t)i];
+  const char* end = t->data + t->line_start[(size_t)i + 1];
+  Field f;
+  for (int k = 0; k < 3; ++k)
+    if (!next_field(p, end, &f)) { nsc::set_error("line %lld: no tag field", (long long)i); return NSC_E_INVALID; }
+  *tag = f.p;
+  *len = (int32_t)f.n;
+  return NSC_OK;
+}
+
+int nsc_tsv_close(nsc_tsv* t) {
+  if (!t) return NSC_OK;
+  if (t->data) munmap((void*)t->data, t->size);
+  if (t->fd >= 0) close(t->fd);
+  delete t;
+  return NSC_OK;
+}
+
+}  // extern "C"

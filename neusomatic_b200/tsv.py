@@ -1,0 +1,65 @@
+"""Candidate TSV reader on top of the C++ decoder (csrc/nsc_tsv.cpp): the inference-side replacement of
+the reference's ``extract_info_tsv`` / ``candidate_loader_tsv`` / tag parsing (dataloader.py:38-123,
+267-274).  Decodes ranges of candidates into (optionally pinned) batch buffers in the layout
+``nsc_score_host_u8`` consumes."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .synth import Candidates
+
+
+class CandidateTSV:
+    def __init__(self, path, num_anns=0, num_threads=0):
+        self.lib = _lib.load()
+        self.num_anns = int(num_anns)
+        self.num_threads = int(num_threads)
+        h = C.c_void_p()
+        _lib.check(self.lib.nsc_tsv_open(C.byref(h), str(path).encode()))
+        self.h = h
+
+    def __len__(self):
+        return int(self.lib.nsc_tsv_count(self.h))
+
+    def tag(self, i):
+        p, n = C.c_char_p(), C.c_int32()
+        _lib.check(self.lib.nsc_tsv_tag(self.h, i, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value).decode()
+
+    def decode(self, first=0, n=None, out=None, with_tags=True):
+        """Returns Candidates(matrices uint8 [n,5,32,23], center, tumor_cov, normal_cov, anns255-or-None, tags).
+        ``out`` may hold preallocated (pinned) arrays: dict(matrices=, meta=, anns255=)."""
+        n = len(self) - first if n is None else n
+        out = out or {}
+        m = out.get("matrices")
+        if m is None:
+            m = np.empty((n, 5, 32, 23), np.uint8)
+        meta = out.get("meta")
+        if meta is None:
+            meta = np.empty((n, 3), np.int32)
+        a255 = out.get("anns255")
+        if a255 is None and self.num_anns:
+            a255 = np.empty((n, self.num_anns), np.float32)
+        labels = np.empty((n, 2), np.int32)
+        _lib.check(self.lib.nsc_tsv_decode(self.h, first, n, self.num_anns, _lib.ptr(m), _lib.ptr(meta),
+                                           _lib.ptr(a255) if self.num_anns else None, labels.ctypes.data, self.num_threads))
+        tags = [self.tag(first + i) for i in range(n)] if with_tags else []
+        meta_np = np.asarray(meta)
+        c = Candidates(m, meta_np[:, 0], meta_np[:, 1], meta_np[:, 2], None, tags)
+        c.anns255 = a255
+        c.labels = labels
+        return c
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nsc_tsv_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

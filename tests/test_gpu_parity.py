@@ -228,3 +228,23 @@ def test_call_variants_loop_matches_oracle(golden):
     assert set(final) == set(f_ref) and set(none) == set(n_ref) and set(true_path) == set(final)
     for k in final:
         assert final[k][0] == f_ref[k][0] and true_path[k].shape == (5, 32, 3)
+
+
+def test_call_tsv_end_to_end(tmp_path, golden):
+    """TSV file -> C++ decoder -> nsc_score_host_u8 -> dictionaries == the array path (call.py:504-534)."""
+    from neusomatic_b200.call import CandidateScorer
+    name, g, ck = golden
+    tags = [str(t) for t in g["tags"]]
+    anns = g.get("anns")
+    p = str(tmp_path / "candidates_0.tsv")
+    with open(p, "w") as f:
+        for i in range(len(tags)):
+            f.write(oracle.encode_tsv_line(i, tags[i], g["matrices"][i], None if anns is None else anns[i]))
+    sc = CandidateScorer(ck)
+    f1, n1 = sc.call_tsv(p, batch=50, num_threads=2)
+    f2, n2 = sc.call(synth.Candidates(g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], anns, tags))
+    assert set(f1) == set(f2) and set(n1) == set(n2)
+    for d1, d2 in ((f1, f2), (n1, n2)):
+        for k in d2:
+            assert d1[k][0] == d2[k][0] and [float(v) for v in d1[k][5]] == [float(v) for v in d2[k][5]]
+    sc.engine.close()

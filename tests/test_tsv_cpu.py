@@ -1,0 +1,83 @@
+"""CPU: the C++ candidate-TSV decoder (csrc/nsc_tsv.cpp) against the oracle restatement of
+dataloader.py:38-58 / 267-274 on reference-format files (generate_dataset.py:1569-1581)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nsnet_oracle as oracle
+from neusomatic_b200 import anns_to_255, synth
+
+
+@pytest.fixture(scope="module")
+def built():
+    from neusomatic_b200 import build
+    build.build_lib()
+
+
+def _write(path, cand, with_anns):
+    with open(path, "w") as f:
+        for i in range(len(cand)):
+            f.write(oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i], cand.anns[i] if with_anns else None))
+
+
+@pytest.mark.parametrize("ensemble", [False, True])
+def test_decode_matches_oracle(tmp_path, built, ensemble):
+    from neusomatic_b200.tsv import CandidateTSV
+    cand = synth.structured_pileups(300, seed=9, ensemble=ensemble)
+    p = str(tmp_path / "candidates_0.tsv")
+    _write(p, cand, ensemble)
+    tsv = CandidateTSV(p, num_anns=93 if ensemble else 0, num_threads=4)
+    assert len(tsv) == 300
+    got = tsv.decode()
+    lines = open(p).read().splitlines()
+    for i in (0, 1, 150, 299):
+        tag, im, anns = oracle.decode_tsv_line(lines[i])
+        assert got.tags[i] == tag == cand.tags[i]
+        np.testing.assert_array_equal(got.matrices[i], im)
+        vt, center, length, tc, nc = oracle.parse_tag(tag)
+        assert (got.center[i], got.tumor_cov[i], got.normal_cov[i]) == (center, tc, nc)
+        assert oracle.VARTYPE_CLASSES[got.labels[i, 0]] == vt and got.labels[i, 1] == length
+        if ensemble:
+            np.testing.assert_array_equal(got.anns255[i], anns_to_255(np.float64(anns)))
+    np.testing.assert_array_equal(got.matrices, cand.matrices)
+    np.testing.assert_array_equal(got.center, cand.center)
+    # ranges and single-thread decode give the same bytes
+    part = CandidateTSV(p, num_anns=93 if ensemble else 0, num_threads=1).decode(37, 100)
+    np.testing.assert_array_equal(part.matrices, cand.matrices[37:137])
+    assert part.tags == cand.tags[37:137]
+
+
+def test_annotation_text_is_parsed_like_python_float(tmp_path, built):
+    """dataloader.py:44-58: anns = float(text); matrix value = a * 255.0 in float64, then .float()."""
+    from neusomatic_b200.tsv import CandidateTSV
+    cand = synth.structured_pileups(2, seed=3, ensemble=True)
+    texts = ["0.1234", "1e-3", "0.3333333333333333", "1", "0"] + ["0.5"] * 88
+    p = str(tmp_path / "c.tsv")
+    with open(p, "w") as f:
+        for i in range(2):
+            line = oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i], None).rstrip("\n")
+            f.write(line + "\t" + "\t".join(texts) + "\n")
+    got = CandidateTSV(p, num_anns=93).decode()
+    ref = (np.array([float(t) for t in texts], np.float64) * 255.0).astype(np.float32)
+    np.testing.assert_array_equal(got.anns255[0], ref)
+
+
+def test_empty_and_malformed_files(tmp_path, built):
+    from neusomatic_b200.tsv import CandidateTSV
+    from neusomatic_b200._lib import NscError
+    p = str(tmp_path / "empty.tsv")
+    open(p, "w").close()
+    assert len(CandidateTSV(p)) == 0
+    cand = synth.structured_pileups(3, seed=4)
+    good = [oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i]) for i in range(3)]
+    for bad in ("0\t1\tonly.three.fields\n", good[1].replace(cand.tags[1], "21.5.A.C.SNP.7.1.30"),   # 8 tag fields
+                good[1][:-20] + "\n"):                                                                   # truncated image
+        q = str(tmp_path / "bad.tsv")
+        with open(q, "w") as f:
+            f.write(good[0] + bad + good[2])
+        t = CandidateTSV(q)
+        with pytest.raises(NscError):
+            t.decode()
+    with pytest.raises(NscError):
+        CandidateTSV(str(tmp_path / "missing.tsv"))
