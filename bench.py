@@ -43,6 +43,10 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_CAND = {26: 2 * 62_384_240, 119: 2 * 65_241_200}      # SURVEY.md Appendix A (dense conv+fc MACs x2)
 # dense MACs of the dominant kernel family (the eight 64->64 convolutions), per candidate
 CONV_STACK_MACS = 5_898_240 * 2 + 16_384_000 * 2 + 2_949_120 + 8_192_000 + 1_474_560 + 4_096_000
+# MACs the tensor path actually issues for that family per candidate: kernel rows in the H padding are skipped
+# (13/15, 19/25, 11/15, 7/15, 13/25 of the taps), times 3 products in split mode
+CONV_STACK_EXEC_MACS = 2 * (5_898_240 * 13 // 15 + 16_384_000 * 19 // 25) + 2_949_120 * 11 // 15 + 8_192_000 * 19 // 25 + \
+    1_474_560 * 7 // 15 + 4_096_000 * 13 // 25
 CKPT = os.path.join(ROOT, "tests", "golden", "std_v010.pth")
 
 
@@ -277,6 +281,10 @@ def main():
                 "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                 "kernel_share_of_step": conv_ms / total_ms if total_ms else None,
                 "algorithmic_flops_per_candidate": 2 * CONV_STACK_MACS,
+                "executed_tensor_tflops": cands * 2 * CONV_STACK_EXEC_MACS * (3 if eng.precision == 0 else 1) /
+                                          (conv_ms / 1000.0) / 1e12 if eng.precision != 2 else None,
+                "executed_frac_of_peak": (cands * 2 * CONV_STACK_EXEC_MACS * (3 if eng.precision == 0 else 1) /
+                                          (conv_ms / 1000.0) / 1e12 / pk["bf16_sustained"]) if eng.precision != 2 else None,
                 "whole_net_frac": (value / world) * FLOPS_PER_CAND[C] / 1e12 / pk["bf16_sustained"],
                 "per_kernel_ms": {k_: round(v[0] / args.steps, 4) for k_, v in prof.items()}}
 
@@ -287,7 +295,7 @@ def main():
                "sample": "oracle/torch_port.py (PyTorch CPU operators, fp32): " + sample}
 
     if rank == 0:
-        prec_names = {0: "split-bf16 (3xbf16 MMA, fp32 accumulate)", 1: "bf16", 2: "f32"}
+        prec_names = {0: "split-f16 (fp16 hi+lo operands, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 1: "f16", 2: "f32"}
         print(json.dumps({
             "metric": "NeuSomaticNet candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,

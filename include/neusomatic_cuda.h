@@ -38,9 +38,11 @@ extern "C" {
 #define NSC_E_NOMEM 4
 
 /* arithmetic of the convolution stack (nsc_model_set_precision) */
-#define NSC_PREC_SPLIT_BF16 0 /* tcgen05 implicit GEMM, hi+lo bf16 operands, 3 MMAs, fp32 accumulate:
-                                 the parity mode (default)                                   */
-#define NSC_PREC_BF16 1       /* tcgen05, single-pass bf16 operands: fast, FAILS the parity bar */
+#define NSC_PREC_SPLIT16 0    /* tcgen05 implicit GEMM, 16-bit hi+lo operands (fp16), 3 MMAs per MAC, fp32
+                                 accumulate: the parity mode (default)                        */
+#define NSC_PREC_SINGLE16 1   /* tcgen05, single-pass 16-bit operands: fast, FAILS the parity bar */
+#define NSC_PREC_SPLIT_BF16 NSC_PREC_SPLIT16   /* historical names */
+#define NSC_PREC_BF16 NSC_PREC_SINGLE16
 #define NSC_PREC_FP32 2       /* fp32 FFMA kernels (CUDA cores): bit-stable reference path    */
 
 typedef struct nsc_model nsc_model;

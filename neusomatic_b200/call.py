@@ -114,6 +114,40 @@ def shard_ranges(n, world_size):
     return out
 
 
+def call_sharded(cand, score_fn, rank=None, world_size=None, group=None):
+    """Multi-GPU replacement of nn.DataParallel in call.py:417-419: every rank scores a contiguous range of
+    the candidate stream (``shard_ranges``) with ``score_fn(Candidates) -> (final_preds, none_preds)`` and the
+    dictionaries are merged on rank 0 in candidate order (later duplicates of a tag win, as in call.py:96-114).
+    There is no collective on the data path; the only exchange is the host-side gather of the results.
+    Returns (final_preds, none_preds) on rank 0 and (None, None) elsewhere."""
+    import torch.distributed as dist
+    from .synth import Candidates
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_ranges(len(cand), world_size)[rank]
+    part = Candidates(cand.matrices[lo:hi], cand.center[lo:hi], cand.tumor_cov[lo:hi], cand.normal_cov[lo:hi],
+                      None if cand.anns is None else cand.anns[lo:hi], cand.tags[lo:hi])
+    if getattr(cand, "anns255", None) is not None:
+        part.anns255 = cand.anns255[lo:hi]
+    mine = score_fn(part)
+    if world_size == 1:
+        return mine
+    gathered = [None] * world_size if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0, group=group)
+    if rank != 0:
+        return None, None
+    final_preds, none_preds = {}, {}
+    for f, n in gathered:                    # rank order == candidate order
+        for k, v in f.items():
+            none_preds.pop(k, None)
+            final_preds[k] = v
+        for k, v in n.items():
+            final_preds.pop(k, None)
+            none_preds[k] = v
+    return final_preds, none_preds
+
+
 class CandidateScorer:
     """Scores compact candidates (uint8 [N,5,32,23] + center/coverages [+ annotations]) held in
     host memory through ``nsc_score_host_u8``: the B200 replacement of the
