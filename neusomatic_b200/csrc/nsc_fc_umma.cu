@@ -101,7 +101,7 @@ fc_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constan
           const uint32_t buf = it & 1;
           if (it >= 2) mbar_wait(a_empty + 8 * buf, ((it >> 1) - 1) & 1);
           mbar_arrive_expect_tx(a_full + 8 * buf, kFcABytes);
-          tma_load_5d(smem_u32(a_buf + buf * kFcABytes), ph >= 5 ? &tmap_lo : &tmap_hi, a_full + 8 * buf, 0, 0, 0, ph % 5, t * 16);
+          tma_load_5d(smem_u32(a_buf + buf * kFcABytes), (args.split && ph < 5) ? &tmap_lo : &tmap_hi, a_full + 8 * buf, 0, 0, 0, ph % 5, t * 16);
         }
     }
   } else if (warp == 2) {
@@ -109,9 +109,11 @@ fc_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constan
       uint32_t it = 0;
       for (int t = blockIdx.x; t < args.n_tiles; t += gridDim.x)
         for (int ph = 0; ph < nph; ++ph) {
-          const int nsel = (args.split && ph < 5) ? 2 : 1;
+          // small terms first (the tensor core's fp32 accumulation truncates): x_lo*w_hi phases, then x_hi with w_lo, w_hi
+          const int nsel = (args.split && ph >= 5) ? 2 : 1;
           for (int w = 0; w < 4; ++w)
-            for (int sel = 0; sel < nsel; ++sel, ++it) {
+            for (int si = 0; si < nsel; ++si, ++it) {
+              const int sel = nsel == 2 ? 1 - si : 0;
               const uint32_t st = it % kFcWStages;
               if (it >= kFcWStages) mbar_wait(w_empty + 8 * st, ((it / kFcWStages) - 1) & 1);
               mbar_arrive_expect_tx(w_full + 8 * st, kFcWBytes);
@@ -134,9 +136,9 @@ fc_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constan
           mbar_wait(a_full + 8 * buf, (a_it >> 1) & 1);
           tc_fence_after_sync();
           const uint32_t a_base = smem_u32(a_buf + buf * kFcABytes);
-          const int nsel = (args.split && ph < 5) ? 2 : 1;
+          const int nsel = (args.split && ph >= 5) ? 2 : 1;
           for (int w = 0; w < 4; ++w)
-            for (int sel = 0; sel < nsel; ++sel, ++w_it) {
+            for (int si = 0; si < nsel; ++si, ++w_it) {
               const uint32_t st = w_it % kFcWStages;
               mbar_wait(w_full + 8 * st, (w_it / kFcWStages) & 1);
               tc_fence_after_sync();

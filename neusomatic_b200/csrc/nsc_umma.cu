@@ -18,8 +18,9 @@
 // instruction (measured: N = 64 issues every ~54 cycles instead of 32; N >= 128 runs at full rate).
 // Kernel rows that fall into the H padding are never issued.
 //
-// Precision: split fp16.  x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, three fp16 MMAs into one fp32
-// accumulator (single-pass bf16 / tf32 / fp16 miss the parity tolerances;
+// Precision: split fp16.  x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi (small terms first: the tensor core's
+// fp32 accumulation truncates, so the corrections are added while the accumulator is still small), three
+// fp16 MMAs into one fp32 accumulator (single-pass bf16 / tf32 / fp16 miss the parity tolerances;
 // split-fp16 sits at the fp32 noise floor).  A unit runs in 2*NK phases (x_hi | x_lo) x (32-channel
 // slices) so that only a 50 KB A buffer is live per phase; two buffers double-buffer the TMA loads.
 //
@@ -172,7 +173,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const uint32_t buf = it & 1;
             if (it >= 2) mbar_wait(a_empty + 8 * buf, ((it >> 1) - 1) & 1);
             mbar_arrive_expect_tx(a_full + 8 * buf, Cfg::A_BYTES);
-            tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), (ph >= NK) ? &tmap_lo : &tmap_hi, a_full + 8 * buf,
+            tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), (args.split && ph < NK) ? &tmap_lo : &tmap_hi, a_full + 8 * buf,
                         (ph % NK) * 32, 0, sub * Cfg::TW - Cfg::HALO, 0, grp);
           }
     }
@@ -183,9 +184,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
       for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
         for (int sub = 0; sub < Cfg::SUBS; ++sub)
           for (int ph = 0; ph < nph; ++ph) {
-            const int nsel = (args.split && ph < NK) ? 2 : 1;
-            for (int sel = 0; sel < nsel; ++sel)
+            const int nsel = (args.split && ph >= NK) ? 2 : 1;
+            for (int si = 0; si < nsel; ++si)
               for (int dx = 0; dx < KW; ++dx, ++it) {
+                const int sel = nsel == 2 ? 1 - si : 0;       // x_hi phases: w_lo stages first, then w_hi
                 const uint32_t st = it % WS;
                 if (it >= WS) mbar_wait(w_empty + 8 * st, ((it / WS) - 1) & 1);
                 mbar_arrive_expect_tx(w_full + 8 * st, Cfg::W_STAGE_BYTES);
@@ -218,8 +220,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             t_a += clock64() - t_c;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(a_buf + buf * Cfg::A_BYTES);
-            const int nsel = (args.split && ph < NK) ? 2 : 1;
-            for (int sel = 0; sel < nsel; ++sel)
+            const int nsel = (args.split && ph >= NK) ? 2 : 1;
+            for (int si = 0; si < nsel; ++si)
               for (int dx = 0; dx < KW; ++dx, ++w_it) {
                 const uint32_t st = w_it % WS;
                 t_c = clock64();
