@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ensemble", action="store_true", help="BASELINE configs[3]: C=119 ensemble model (not the default metric config)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,18 +188,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    C = 26
-    sd, meta = load_checkpoint(CKPT)
+    C = 119 if args.ensemble else 26
+    sd, meta = load_checkpoint(os.path.join(ROOT, "tests", "golden", "ens_v010.pth") if args.ensemble else CKPT)
     eng = Engine(sd, C, device=local_rank, precision=args.precision)
     B = args.batch
 
     # synthetic S1 candidates, seed = 1234 + rank; a 4096-candidate pool tiled to B
-    pool = synth.uniform_pileups(4096, seed=1234 + rank)
+    from neusomatic_b200 import anns_to_255
+    pool = synth.uniform_pileups(4096, seed=1234 + rank, ensemble=args.ensemble)
     reps = (B + 4095) // 4096
     mat_h = torch.from_numpy(np.tile(pool.matrices, (reps, 1, 1, 1))[:B]).pin_memory()
     meta_h = torch.from_numpy(np.tile(pool.meta, (reps, 1))[:B].copy()).pin_memory()
+    ann_h = torch.from_numpy(np.tile(anns_to_255(pool.anns), (reps, 1))[:B].copy()).pin_memory() if args.ensemble else None
     mat_d, meta_d = mat_h.to(dev), meta_h.to(dev)
-    x_d = eng.assemble(mat_d, meta_d, None, float(meta["coverage_thr"]))        # fp32 [B,26,5,32] in HBM
+    ann_d = ann_h.to(dev) if args.ensemble else None
+    x_d = eng.assemble(mat_d, meta_d, ann_d, float(meta["coverage_thr"]))        # fp32 [B,C,5,32] in HBM
     torch.cuda.synchronize()
 
     def barrier():
@@ -245,7 +249,7 @@ def main():
         res = {}
         for name in ("f32", "u8"):
             fn = (lambda: eng.score_host_f32(x_h, out=host_out)) if name == "f32" else \
-                 (lambda: eng.score_host_u8(mat_h, meta_h, None, float(meta["coverage_thr"]), out=host_out))
+                 (lambda: eng.score_host_u8(mat_h, meta_h, ann_h, float(meta["coverage_thr"]), out=host_out))
             fn()
             barrier()
             t0 = time.perf_counter()
@@ -257,10 +261,10 @@ def main():
                 dist.all_reduce(el, op=dist.ReduceOp.MAX)
             res[name] = world * B * k / float(el.item())
         d2h = B * 19 * 4
-        e2e = {"value": res["u8"], "unit": "candidates/s", "h2d_bytes_per_step": B * (3680 + 12),
+        e2e = {"value": res["u8"], "unit": "candidates/s", "h2d_bytes_per_step": B * (3680 + 12 + (372 if args.ensemble else 0)),
                "d2h_bytes_per_step": d2h, "api": "nsc_score_host_u8 (pinned uint8 [B,5,32,23] + int32 [B,3] in, host results out)"}
         e2e_u8 = {"value": res["f32"], "unit": "candidates/s", "h2d_bytes_per_step": B * C * 160 * 4,
-                  "d2h_bytes_per_step": d2h, "api": "nsc_score_host_f32 (pinned fp32 [B,26,5,32] in, host results out)"}
+                  "d2h_bytes_per_step": d2h, "api": "nsc_score_host_f32 (pinned fp32 [B,C,5,32] in, host results out)"}
 
     # ---- roofline of the dominant kernel family (the eight 64->64 convolutions) -------------------
     pk = peaks()
@@ -301,8 +305,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": prec_names.get(eng.precision, str(eng.precision)), "data": "synthetic",
-            "config": {"workload": "synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, "
-                                   "v0.1.0 standalone checkpoint, S1 uniform pileups",
+            "config": {"workload": ("synthetic ensemble call (BASELINE.json configs[3]): C=119, 119x5x32 matrices, v0.1.0 ensemble "
+                                    "checkpoint, S1 uniform pileups") if args.ensemble else
+                                   ("synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, "
+                                    "v0.1.0 standalone checkpoint, S1 uniform pileups"),
                        "batch_per_gpu": B, "candidates_per_step": world * B,
                        "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
                        "sharding": "contiguous candidate ranges per rank, no collective on the data path"},

@@ -98,6 +98,8 @@ struct UmmaConvArgs {
 
 // ---- fp16 hi/lo helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);   // fp16 range guard: saturate instead of producing inf / NaN
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -486,7 +488,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 // fp32 NCHW [B,C,5,32] -> packed hi/lo [groups][5][32][8][Cpad] (channels >= C zero); block = (group, h, 32-channel slice)
 __global__ void __launch_bounds__(256)
 pack_nchw_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B, int C, int Cpad) {
-  __shared__ float t[8][32][33];
+  constexpr int PS = 32 * 33 + 1;          // candidate-plane stride: odd multiple keeps the transposed reads conflict free
+  __shared__ float t[8 * PS];
   const int nslice = Cpad / 32;
   const int slice = blockIdx.x % nslice, gh = blockIdx.x / nslice;
   const int grp = gh / kH, h = gh % kH;
@@ -494,14 +497,14 @@ pack_nchw_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16
     const int w = i & 31, c = (i >> 5) & 31, g = i >> 10;
     const int64_t b = (int64_t)grp * 8 + g;
     const int cc = slice * 32 + c;
-    t[g][c][w] = (b < B && cc < C) ? in[((b * C + cc) * kH + h) * 32 + w] : 0.f;
+    t[g * PS + c * 33 + w] = (b < B && cc < C) ? __ldg(in + ((b * C + cc) * kH + h) * 32 + w) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 8 * 4; i += 256) {
     const int c8 = i & 3, g = (i >> 2) & 7, w = i >> 5;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = t[g][c8 * 8 + j][w];
+    for (int j = 0; j < 8; ++j) v[j] = t[g * PS + (c8 * 8 + j) * 33 + w];
     const size_t off = ((((size_t)grp * kH + h) * 32 + w) * 8 + g) * Cpad + slice * 32 + c8 * 8;
     uint4 a, b;
     split8(v, a, b);
