@@ -46,22 +46,31 @@ constexpr int kEpiThreads = 256;
 constexpr int kStageBytes = 32768;      // epilogue staging: hi plane + lo plane of one [128 x 64] row tile
 constexpr int kStashBytes = 20480;      // boundary columns carried between the two column blocks (W = 32)
 
-template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_>
+template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_, int KC_ = 32, int GP_ = 1>
 struct ConvCfg {
   static constexpr int KH = KH_, KW = KW_, DIL = DIL_, W = W_, NK = NK_, POOL = POOL_;
   static constexpr bool NCHW = NCHW_;
+  static constexpr int KC = KC_;                         // input channels per phase / weight stage (32 or 16)
+  static constexpr int GP = GP_;                         // candidate groups per unit (2 for the W = 8 layers: M stays 128)
+  static constexpr int RB = KC * 2;                      // bytes per operand row
+  static constexpr int ATOM = 8 * RB;                    // 8-row swizzle atom = SBO of the UMMA descriptors
+  static constexpr int NKK = KC / 16;                    // MMA K-steps per stage
+  static constexpr uint32_t SWZ = KC == 32 ? kSwizzle64 : kSwizzle32;
   static constexpr int PW = DIL * (KW - 1) / 2, PH = DIL * (KH - 1) / 2;
   static constexpr int TW = (W >= 16) ? 16 : 8;          // output columns per unit
-  static constexpr int M = TW * 8;                       // UMMA M: 128 (64 for the W = 8 layers)
+  static constexpr int RPW = 8 * GP;                     // operand rows per column: GP groups x 8 candidates
+  static constexpr int M = TW * RPW;                     // UMMA M (128; 64 only for W = 8 with GP = 1)
   static constexpr int HALO = (W >= 16) ? 2 : 4;         // neighbour / zero columns staged each side
   static constexpr int WB = TW + 2 * HALO;               // columns in the TMA box
-  static constexpr int A_BYTES = kH * WB * 8 * 64;       // one phase: 32 channels = 64-byte rows
-  static constexpr int W_STAGE_BYTES = KH * 4096;        // [KH][64 cout][32 cin] fp16, swizzle-64B
+  static constexpr int A_BYTES = kH * WB * RPW * RB;     // one phase
+  static constexpr int W_STAGE_BYTES = KH * 64 * RB;     // [KH][64 cout][KC cin] fp16, swizzled K-major
   static constexpr int WS = (61440 / W_STAGE_BYTES) < 8 ? (61440 / W_STAGE_BYTES) : 8;   // weight ring depth
   static constexpr int SUBS = W / TW;
   static constexpr int WOUT = POOL == 2 ? W / 2 : W;
   static constexpr bool STASH = (SUBS == 2) && (POOL != 0);
   static_assert(PW <= HALO, "halo too small");
+  static_assert(KC == 32 || KC == 16, "KC");
+  static_assert(!(STASH && GP != 1), "column-block stash assumes one group per unit");
   static constexpr size_t SMEM = 1024 + 2 * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
                                  (STASH ? kStashBytes : 0) + 256;
 };
@@ -175,8 +184,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const uint32_t buf = it & 1;
             if (it >= 2) mbar_wait(a_empty + 8 * buf, ((it >> 1) - 1) & 1);
             mbar_arrive_expect_tx(a_full + 8 * buf, Cfg::A_BYTES);
+            // tensor-map dims: (channel, candidate, group-in-unit, column, group*5 + row)
             tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), (args.split && ph < NK) ? &tmap_lo : &tmap_hi, a_full + 8 * buf,
-                        (ph % NK) * 32, 0, sub * Cfg::TW - Cfg::HALO, 0, grp);
+                        (ph % NK) * Cfg::KC, 0, 0, sub * Cfg::TW - Cfg::HALO, grp * Cfg::GP * kH);
           }
     }
   } else if (warp == 2) {
@@ -245,7 +255,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     }
 #pragma unroll
                     for (int h_in = 0; h_in < kH; ++h_in) {
-                      const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * 8) * 64;
+                      const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
 #pragma unroll
                       for (int dy = 0; dy < KH; ++dy) {
                         const int h_out = h_in - dy * DIL + Cfg::PH;
@@ -253,9 +263,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                         const int slot = acc_slot<DIL>(h_out);
                         if ((int)((shared_slots >> slot) & 1u) != pass) continue;
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                          const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, 512, kSwizzle64);
-                          const uint64_t bdesc = make_smem_desc(w_base + dy * 4096 + kk * 32, 16, 512, kSwizzle64);
+                        for (int kk = 0; kk < Cfg::NKK; ++kk) {
+                          const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
+                          const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
                           umma_f16(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
                           touched |= 1u << h_out;
                         }
@@ -273,15 +283,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                       if (h_out >= 0 && h_out < kH) { dy_lo = dy < dy_lo ? dy : dy_lo; dy_hi = dy; }
                     }
                     if (dy_hi < 0) continue;
-                    const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * 8) * 64;
+                    const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                      const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, 512, kSwizzle64);
+                    for (int kk = 0; kk < Cfg::NKK; ++kk) {
+                      const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
                       for (int dy = dy_lo, n = 0; dy <= dy_hi; dy += n) {
                         const int rem = dy_hi - dy + 1;
                         n = rem == 5 ? 3 : (rem < 4 ? rem : 4);   // N = 64 n <= 256; 5 rows as 192 + 128
                         const int h_out = h_in - dy * DIL + Cfg::PH;
-                        const uint64_t bdesc = make_smem_desc(w_base + dy * 4096 + kk * 32, 16, 512, kSwizzle64);
+                        const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
                         umma_f16(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
                       }
                     }
@@ -317,16 +327,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     uint32_t u_it = 0;
     long long t_epi = 0, t_full = 0;
     uint2 res_h[ITEMS][2], res_l[ITEMS][2];     // residual operands of the NEXT row to be processed
+    // element offset of operand row rr (column wl, group-in-unit, candidate) of image row h in a packed tensor of width Wt
+    auto row_off = [&](int grp_, int h_, int Wt, int col, int rr) -> size_t {
+      const int mg = rr % Cfg::RPW;
+      return ((((size_t)(grp_ * Cfg::GP + (mg >> 3)) * kH + h_) * Wt + col) * 8 + (mg & 7)) * 64;
+    };
     auto load_res = [&](int grp_, int sub_, uint32_t u_, int idx_) {
       const int slot_ = (u_ & 1) ? idx_ : (idx_ < 2 ? 3 + idx_ : idx_ - 2);
       const int h_ = slot_row<DIL>(slot_);
-      const size_t tile_ = ((((size_t)grp_ * kH + h_) * W + sub_ * Cfg::TW) * 8) * 64;
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {
         const int i = et + k * kEpiThreads, rr = i >> 3, ch = i & 7;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const size_t go = tile_ + rr * 64 + hh * 32 + ch * 4;
+          const size_t go = row_off(grp_, h_, W, sub_ * Cfg::TW + rr / Cfg::RPW, rr) + hh * 32 + ch * 4;
           res_h[k][hh] = *reinterpret_cast<const uint2*>(args.res_hi + go);
           res_l[k][hh] = *reinterpret_cast<const uint2*>(args.res_lo + go);
         }
@@ -376,7 +390,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             }
           }
           epi_bar();
-          const size_t in_tile = ((((size_t)grp * kH + h) * W + w0) * 8) * 64;   // element offset of the tile
           // ---- phase B1: residual add (coalesced items; the operands were prefetched one row ahead)
           if (args.res_hi != nullptr) {
 #pragma unroll
@@ -398,11 +411,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 #pragma unroll
           for (int k = 0; k < ITEMS; ++k) {
             const int i = et + k * kEpiThreads, rr = i >> 3, ch = i & 7;
-            const int wl = rr >> 3, g = rr & 7;
+            const int wl = rr / Cfg::RPW, mg = rr % Cfg::RPW, g = mg & 7;
+            const int ga = grp * Cfg::GP + (mg >> 3);       // actual candidate group of this row
             const float* p0 = stg + rr * 64 + ((ch ^ (rr & 7)) << 2);
             float4 m0 = *reinterpret_cast<const float4*>(p0), m1 = *reinterpret_cast<const float4*>(p0 + 32);
             if (Cfg::POOL == 0) {
-              const size_t o = in_tile + rr * 64 + ch * 4;
+              const size_t o = row_off(grp, h, W, w0 + wl, rr) + ch * 4;
               uint2 hi, lo;
               split2(m0.x, m0.y, hi.x, lo.x); split2(m0.z, m0.w, hi.y, lo.y);
               *reinterpret_cast<uint2*>(args.out_hi + o) = hi;
@@ -425,7 +439,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             };
             auto emit = [&](const float4& b0, const float4& b1, int wo) {
               if (Cfg::NCHW) {
-                const int64_t b = (int64_t)grp * 8 + g;
+                const int64_t b = (int64_t)ga * 8 + g;
                 if (b < args.B) {
                   float* o = args.out_nchw + ((b * 64 + ch * 4) * kH + h) * Cfg::WOUT + wo;
                   const int cs = kH * Cfg::WOUT;
@@ -434,7 +448,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                   o[0] = b1.x; o[cs] = b1.y; o[2 * cs] = b1.z; o[3 * cs] = b1.w;
                 }
               } else {
-                const size_t o = (((((size_t)grp * kH + h) * Cfg::WOUT + wo) * 8 + g) * 64) + ch * 4;
+                const size_t o = (((((size_t)ga * kH + h) * Cfg::WOUT + wo) * 8 + g) * 64) + ch * 4;
                 uint2 hi, lo;
                 split2(b0.x, b0.y, hi.x, lo.x); split2(b0.z, b0.w, hi.y, lo.y);
                 *reinterpret_cast<uint2*>(args.out_hi + o) = hi;
@@ -448,15 +462,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             if (do_emit) {
               float4 b0 = m0, b1 = m1;
               if (wl > 0) {
-                max4(b0, *reinterpret_cast<const float4*>(p0 - 8 * 64));
-                max4(b1, *reinterpret_cast<const float4*>(p0 - 8 * 64 + 32));
+                max4(b0, *reinterpret_cast<const float4*>(p0 - Cfg::RPW * 64));
+                max4(b1, *reinterpret_cast<const float4*>(p0 - Cfg::RPW * 64 + 32));
               } else if (Cfg::STASH && sub == 1) {
                 max4(b0, *reinterpret_cast<const float4*>(s1));
                 max4(b1, *reinterpret_cast<const float4*>(s1 + 32));
               }
               if (wl < Cfg::TW - 1) {
-                max4(b0, *reinterpret_cast<const float4*>(p0 + 8 * 64));
-                max4(b1, *reinterpret_cast<const float4*>(p0 + 8 * 64 + 32));
+                max4(b0, *reinterpret_cast<const float4*>(p0 + Cfg::RPW * 64));
+                max4(b1, *reinterpret_cast<const float4*>(p0 + Cfg::RPW * 64 + 32));
               }
               emit(b0, b1, (w0 + wl) / ST);
             }
@@ -536,7 +550,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int Cpad, int box_w) {
+// Packed activation tensor act[group][5][W][8][Cpad] seen as (channel, candidate, group-in-unit, column, group*5 + row):
+// the group stride is exactly 5 row strides, so the two groups of a unit are one extra dimension of stride 5 rows.
+static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int Cpad, int box_w, int KC, int GP) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult q;
@@ -544,20 +560,23 @@ static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available"); return NSC_E_CUDA; }
   }
   const cuuint64_t row = (cuuint64_t)Cpad * 2;
-  cuuint64_t dims[5] = {(cuuint64_t)Cpad, 8, (cuuint64_t)W, (cuuint64_t)kH, (cuuint64_t)groups};
-  cuuint64_t strides[4] = {row, 8 * row, (cuuint64_t)W * 8 * row, (cuuint64_t)kH * W * 8 * row};
-  cuuint32_t box[5] = {32, 8, (cuuint32_t)box_w, (cuuint32_t)kH, 1};
+  const cuuint64_t img_row = (cuuint64_t)W * 8 * row;
+  cuuint64_t dims[5] = {(cuuint64_t)Cpad, 8, (cuuint64_t)GP, (cuuint64_t)W, (cuuint64_t)(groups * kH - kH * (GP - 1))};
+  cuuint64_t strides[4] = {row, kH * img_row, 8 * row, img_row};
+  cuuint32_t box[5] = {(cuuint32_t)KC, 8, (cuuint32_t)GP, (cuuint32_t)box_w, (cuuint32_t)kH};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return NSC_E_CUDA; }
   return NSC_OK;
 }
 
 // Folded weights [64][Cin][KH][KW] -> stages ((sel*NK + kc)*KW + dx) of [KH][64 cout][32 cin] fp16 in the
 // swizzle-64B K-major shared-memory image the UMMA B descriptor reads (sel 0 = hi, 1 = lo part).
-static std::vector<uint8_t> pack_conv_weights(const std::vector<float>& w, int Cin, int KH, int KW, int NK, float* max_abs) {
-  const size_t stage = (size_t)KH * 4096;
+static std::vector<uint8_t> pack_conv_weights(const std::vector<float>& w, int Cin, int KH, int KW, int NK, int KC,
+                                              float* max_abs) {
+  const size_t stage = (size_t)KH * 64 * KC * 2;
   std::vector<uint8_t> out(2 * (size_t)NK * KW * stage, 0);
   for (int co = 0; co < 64; ++co)
     for (int ci = 0; ci < Cin; ++ci)
@@ -567,8 +586,9 @@ static std::vector<uint8_t> pack_conv_weights(const std::vector<float>& w, int C
           *max_abs = std::max(*max_abs, fabsf(v));
           const __half hi = __float2half_rn(v);
           const __half lo = __float2half_rn(v - __half2float(hi));
-          const int kc = ci / 32, k = ci % 32;
-          const uint32_t off = ptx::swz_offset<64>((uint32_t)(dy * 64 + co), (uint32_t)(k / 8)) + (k % 8) * 2;
+          const int kc = ci / KC, k = ci % KC;
+          const uint32_t r = (uint32_t)(dy * 64 + co), c = (uint32_t)(k / 8);
+          const uint32_t off = (KC == 32 ? ptx::swz_offset<64>(r, c) : ptx::swz_offset<32>(r, c)) + (k % 8) * 2;
           memcpy(out.data() + (size_t)((0 * NK + kc) * KW + dx) * stage + off, &hi, 2);
           memcpy(out.data() + (size_t)((1 * NK + kc) * KW + dx) * stage + off, &lo, 2);
         }
@@ -591,7 +611,7 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
   if ((rc = fold_conv_bn(m, "conv1", "bn1", bn_eps, &f)) != NSC_OK) return rc;
   u.nk1 = (m->C + 31) / 32;
   if (u.nk1 == 3) u.nk1 = 4;
-  if ((rc = upload_bytes(&u.wpk1, pack_conv_weights(f.w, m->C, 1, 3, u.nk1, &max_abs))) != NSC_OK) return rc;
+  if ((rc = upload_bytes(&u.wpk1, pack_conv_weights(f.w, m->C, 1, 3, u.nk1, 32, &max_abs))) != NSC_OK) return rc;
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j) {
       char conv[64], bn[64];
@@ -599,7 +619,8 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
       snprintf(bn, sizeof bn, "res_layers.%d.bn_r%d", i, j + 1);
       const int k = j == 0 ? kBlocks[i].k1 : kBlocks[i].k2;
       if ((rc = fold_conv_bn(m, conv, bn, bn_eps, &f)) != NSC_OK) return rc;
-      if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 2, &max_abs))) != NSC_OK) return rc;
+      const int kc = i == 3 ? 16 : 32;     // the W = 8 layers run two groups per unit on 16-channel phases
+      if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 64 / kc, kc, &max_abs))) != NSC_OK) return rc;
     }
   u.weights_fit_fp16 = max_abs < 6.0e4f;
   return fc_umma_upload_weights(m);
@@ -646,11 +667,11 @@ template <class Cfg>
 static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[2], const uint8_t* wpk, const float* bias,
                             uint16_t* const out[2], float* out_nchw, uint16_t* const res[2], int64_t n, int relu,
                             cudaStream_t s) {
-  const int64_t groups = (n + 7) / 8;
+  const int64_t groups = ((n + 7) / 8 + Cfg::GP - 1) / Cfg::GP;      // units of GP candidate groups
   CUtensorMap th, tl;
   int rc;
-  if ((rc = make_act_tmap(&th, in[0], m->umma.cap / 8, Cfg::W, Cfg::NK * 32, Cfg::WB)) != NSC_OK) return rc;
-  if ((rc = make_act_tmap(&tl, in[1], m->umma.cap / 8, Cfg::W, Cfg::NK * 32, Cfg::WB)) != NSC_OK) return rc;
+  if ((rc = make_act_tmap(&th, in[0], m->umma.cap / 8, Cfg::W, Cfg::NK * Cfg::KC, Cfg::WB, Cfg::KC, Cfg::GP)) != NSC_OK) return rc;
+  if ((rc = make_act_tmap(&tl, in[1], m->umma.cap / 8, Cfg::W, Cfg::NK * Cfg::KC, Cfg::WB, Cfg::KC, Cfg::GP)) != NSC_OK) return rc;
   UmmaConvArgs a;
   a.wpk = wpk;
   a.bias = bias;
@@ -767,8 +788,8 @@ static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 3, X, 8, n, s));
   // block 3 (3x3 d4, 5x5 d2, pool stride 2) -> fp32 [B,1280] for fc1
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 2, 0, false>>(m, 8, X, u.wpk[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 2, 2, false>>(m, 9, Y, u.wpk[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s)));
+  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 4, 0, false, 16, 2>>(m, 8, X, u.wpk[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s)));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 4, 2, false, 16, 2>>(m, 9, Y, u.wpk[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s)));
   NSC_RUN(dbg_unpack(m, 4, N, 4, n, s));
   NSC_RUN(fc_umma_forward(m, N, n, o, s));
 #undef NSC_RUN
