@@ -65,13 +65,14 @@ struct ConvCfg {
   static constexpr int A_BYTES = kH * WB * RPW * RB;     // one phase
   static constexpr int W_STAGE_BYTES = KH * 64 * RB;     // [KH][64 cout][KC cin] fp16, swizzled K-major
   static constexpr int WS = (61440 / W_STAGE_BYTES) < 8 ? (61440 / W_STAGE_BYTES) : 8;   // weight ring depth
+  static constexpr int NA = (3 * A_BYTES + WS * W_STAGE_BYTES + kStageBytes + 24576 <= 232448) ? 3 : 2;   // A ring depth
   static constexpr int SUBS = W / TW;
   static constexpr int WOUT = POOL == 2 ? W / 2 : W;
   static constexpr bool STASH = (SUBS == 2) && (POOL != 0);
   static_assert(PW <= HALO, "halo too small");
   static_assert(KC == 32 || KC == 16, "KC");
   static_assert(!(STASH && GP != 1), "column-block stash assumes one group per unit");
-  static constexpr size_t SMEM = 1024 + 2 * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
+  static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
                                  (STASH ? kStashBytes : 0) + 256;
 };
 
@@ -142,22 +143,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   constexpr int KH = Cfg::KH, KW = Cfg::KW, DIL = Cfg::DIL, W = Cfg::W, NK = Cfg::NK, WS = Cfg::WS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_buf = smem;                                         // 2 x A_BYTES
-  uint8_t* w_buf = a_buf + 2 * Cfg::A_BYTES;                     // WS x W_STAGE_BYTES
+  uint8_t* a_buf = smem;                                         // NA x A_BYTES
+  uint8_t* w_buf = a_buf + Cfg::NA * Cfg::A_BYTES;               // WS x W_STAGE_BYTES
   uint8_t* st_hi = w_buf + WS * Cfg::W_STAGE_BYTES;              // 16 KB: [128 rows][128 B], chunk-swizzled
   uint8_t* st_lo = st_hi + 16384;
   uint8_t* stash = st_lo + 16384;                                // [hi|lo][2 cols][5][8 g][8 chunks][16 B]
-  __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4];
+  __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[64];
-  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[2]);
-  const uint32_t w_full = smem_u32(&bars[4]), w_empty = smem_u32(&bars[12]);
-  const uint32_t acc_full = smem_u32(&bars[20]), shared_free = smem_u32(&bars[21]), all_free = smem_u32(&bars[22]);
+  const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[3]);
+  const uint32_t w_full = smem_u32(&bars[6]), w_empty = smem_u32(&bars[14]);
+  const uint32_t acc_full = smem_u32(&bars[22]), shared_free = smem_u32(&bars[23]), all_free = smem_u32(&bars[24]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < 64) bias_s[tid] = args.bias[tid];
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < Cfg::NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < WS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     mbar_init(acc_full, 1);
     mbar_init(shared_free, kEpiThreads);
@@ -181,8 +182,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
       for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
         for (int sub = 0; sub < Cfg::SUBS; ++sub)
           for (int ph = 0; ph < nph; ++ph, ++it) {
-            const uint32_t buf = it & 1;
-            if (it >= 2) mbar_wait(a_empty + 8 * buf, ((it >> 1) - 1) & 1);
+            const uint32_t buf = it % Cfg::NA;
+            if (it >= Cfg::NA) mbar_wait(a_empty + 8 * buf, ((it / Cfg::NA) - 1) & 1);
             mbar_arrive_expect_tx(a_full + 8 * buf, Cfg::A_BYTES);
             // tensor-map dims: (channel, candidate, group-in-unit, column, group*5 + row)
             tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), (args.split && ph < NK) ? &tmap_lo : &tmap_hi, a_full + 8 * buf,
@@ -226,9 +227,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           uint32_t touched = 0;
           bool first_stage = true;
           for (int ph = 0; ph < nph; ++ph, ++a_it) {
-            const uint32_t buf = a_it & 1;
+            const uint32_t buf = a_it % Cfg::NA;
             t_c = clock64();
-            mbar_wait(a_full + 8 * buf, (a_it >> 1) & 1);
+            mbar_wait(a_full + 8 * buf, (a_it / Cfg::NA) & 1);
             t_a += clock64() - t_c;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(a_buf + buf * Cfg::A_BYTES);
