@@ -248,3 +248,52 @@ def test_call_tsv_end_to_end(tmp_path, golden):
         for k in d2:
             assert d1[k][0] == d2[k][0] and [float(v) for v in d1[k][5]] == [float(v) for v in d2[k][5]]
     sc.engine.close()
+
+
+def test_c_abi_error_paths():
+    """Errors are reported through return codes + nsc_last_error (Python raises), never silently."""
+    import ctypes as C
+    from neusomatic_b200 import _lib, Engine
+    from neusomatic_b200._lib import NscError
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.nsc_model_create(C.byref(h), 0, 0) != 0 and b"num_channels" in lib.nsc_last_error()
+    assert lib.nsc_model_create(C.byref(h), 99, 26) != 0
+    _lib.check(lib.nsc_model_create(C.byref(h), 0, 26))
+    w = np.zeros(10, np.float32)
+    assert lib.nsc_model_set_param(h, b"conv9.weight", w.ctypes.data, 10) != 0 and b"unknown parameter" in lib.nsc_last_error()
+    assert lib.nsc_model_set_param(h, b"conv1.bias", w.ctypes.data, 10) != 0 and b"expected 64" in lib.nsc_last_error()
+    assert lib.nsc_model_finalize(h, 1e-5) != 0 and b"missing parameter" in lib.nsc_last_error()
+    x = torch.zeros(1, 26, 5, 32, device="cuda")
+    o = torch.zeros(9, device="cuda")
+    rc = lib.nsc_forward_f32(h, x.data_ptr(), 1, o.data_ptr(), o.data_ptr(), o.data_ptr(), None, None, None, None, None)
+    assert rc != 0 and b"finalize" in lib.nsc_last_error()
+    lib.nsc_model_destroy(h)
+    sd = synth.random_state_dict(26, seed=1)
+    eng = Engine(sd, 26)
+    with pytest.raises(ValueError):
+        eng.forward_f32(torch.zeros(2, 25, 5, 32, device="cuda"))
+    with pytest.raises(NscError):
+        eng.set_precision(7)
+    with pytest.raises(NscError):      # ensemble-only argument missing is caught on the ensemble model
+        Engine(synth.random_state_dict(119, seed=1), 119).score_host_u8(np.zeros((1, 5, 32, 23), np.uint8),
+                                                                         np.zeros((1, 3), np.int32), None, 100.0)
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", MODES)
+def test_large_batch_crosses_default_chunk(precision):
+    """More candidates than one pass of the layer kernels (32768): results independent of the chunking."""
+    from neusomatic_b200 import Engine
+    cand = synth.structured_pileups(2048, seed=21)
+    sd = synth.random_state_dict(26, seed=5)
+    x = oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)
+    eng = Engine(sd, 26, precision=precision)
+    xs = torch.from_numpy(x).cuda()
+    big = xs.repeat(17, 1, 1, 1)[:33000].contiguous()
+    o_big = [t.cpu().numpy() for t in eng.forward_f32(big)[:3]]
+    o_small = [t.cpu().numpy() for t in eng.forward_f32(xs)[:3]]
+    for a, b in zip(o_big, o_small):
+        np.testing.assert_array_equal(a[:2048], b)
+        np.testing.assert_array_equal(a[32768:33000], b[32768 - 16 * 2048:33000 - 16 * 2048])
+    eng.close()
