@@ -64,7 +64,9 @@ __device__ __forceinline__ void fc_head_finish(const float* o /*9*/, int64_t b, 
 __global__ void __launch_bounds__(kFcThreads, 1)
 fc_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo, const FcArgs args) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an offset on the __shared__ array itself (keeps the shared address space: LDS/STS,
+  // not generic LD/ST, for every access derived from it)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_buf = smem;
   uint8_t* w_buf = a_buf + 2 * kFcABytes;
   float* hw_s = reinterpret_cast<float*>(w_buf + kFcWStages * kFcWBytes);   // [9][240]

@@ -142,7 +142,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                  const UmmaConvArgs args) {
   constexpr int KH = Cfg::KH, KW = Cfg::KW, DIL = Cfg::DIL, W = Cfg::W, NK = Cfg::NK, WS = Cfg::WS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an offset on the __shared__ array itself (keeps the shared address space: LDS/STS,
+  // not generic LD/ST, for every access derived from it)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_buf = smem;                                         // NA x A_BYTES
   uint8_t* w_buf = a_buf + Cfg::NA * Cfg::A_BYTES;               // WS x W_STAGE_BYTES
   uint8_t* st_hi = w_buf + WS * Cfg::W_STAGE_BYTES;              // 16 KB: [128 rows][128 B], chunk-swizzled
@@ -323,6 +325,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     const bool active = (Cfg::M == 128) || lane < 16;
     constexpr int ITEMS = Cfg::M * 8 / kEpiThreads;
     constexpr int ST = Cfg::POOL == 2 ? 2 : 1;
+    float bias_r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias_r[j] = bias_s[half * 32 + j];
     float* stg = reinterpret_cast<float*>(st_hi);           // 32 KB fp32 staging tile
     float* stash_f = reinterpret_cast<float*>(stash);       // [2 cols][5][8 g][64 ch] fp32
     uint32_t u_it = 0;
@@ -382,10 +387,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               float4 v;
-              v.x = __uint_as_float(r[c * 4 + 0]) + bias_s[half * 32 + c * 4 + 0];
-              v.y = __uint_as_float(r[c * 4 + 1]) + bias_s[half * 32 + c * 4 + 1];
-              v.z = __uint_as_float(r[c * 4 + 2]) + bias_s[half * 32 + c * 4 + 2];
-              v.w = __uint_as_float(r[c * 4 + 3]) + bias_s[half * 32 + c * 4 + 3];
+              v.x = __uint_as_float(r[c * 4 + 0]) + bias_r[c * 4 + 0];
+              v.y = __uint_as_float(r[c * 4 + 1]) + bias_r[c * 4 + 1];
+              v.z = __uint_as_float(r[c * 4 + 2]) + bias_r[c * 4 + 2];
+              v.w = __uint_as_float(r[c * 4 + 3]) + bias_r[c * 4 + 3];
               if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               *reinterpret_cast<float4*>(stg + row * 64 + ((half * 8 + (c ^ (row & 7))) << 2)) = v;
             }
