@@ -83,3 +83,30 @@ def test_torch_port_matches_reference(golden):
     np.testing.assert_allclose(o1.numpy(), g["o1"], atol=1e-5)
     np.testing.assert_allclose(o2.numpy(), g["o2"], atol=1e-5)
     np.testing.assert_allclose(o3.numpy(), g["o3"], atol=1e-5)
+
+
+def test_train_port_matches_reference_train_step():
+    """oracle/train_port.py against two optimisation steps of the unmodified reference (train.py:436-441)."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    from neusomatic_b200 import synth
+    from oracle import train_port
+    g = dict(np.load(os.path.join(GOLDEN, "train_std.npz")))
+    p = {k: torch.from_numpy(v) for k, v in synth.random_state_dict(26, seed=11).items()}
+    x = torch.from_numpy(oracle.assemble_channels(g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], None, 100))
+    labels, len_labels = torch.from_numpy(g["labels"]).long(), torch.from_numpy(g["len_labels"]).long()
+    centers = torch.from_numpy(g["center"]).float()
+    mom = {}
+    for step in range(2):
+        loss, parts, grads = train_port.grads(p, x, labels, centers, len_labels, torch.from_numpy(g["w_type"]),
+                                              torch.from_numpy(g["w_len"]))
+        np.testing.assert_allclose([loss.item()] + [t.item() for t in parts], g["loss%d" % step], rtol=2e-5)
+        if step == 0:
+            for k in g:
+                if k.startswith("grad."):
+                    np.testing.assert_allclose(grads[k[5:]].numpy(), g[k], rtol=1e-3, atol=1e-4 * float(np.abs(g[k]).max()))
+        train_port.sgd_step(p, grads, mom, 0.01, 0.9)
+    for k in g:
+        if k.startswith("final."):
+            np.testing.assert_allclose(p[k[6:]].numpy(), g[k], rtol=1e-4, atol=1e-5)
