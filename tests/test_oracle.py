@@ -105,7 +105,7 @@ def test_train_port_matches_reference_train_step():
         if step == 0:
             for k in g:
                 if k.startswith("grad."):
-                    np.testing.assert_allclose(grads[k[5:]].numpy(), g[k], rtol=1e-3, atol=1e-4 * float(np.abs(g[k]).max()))
+                    np.testing.assert_allclose(grads[k[5:]].numpy(), g[k], rtol=1e-3, atol=max(1e-4 * float(np.abs(g[k]).max()), 1e-6))   # conv biases in front of a BN have ~0 gradient
         train_port.sgd_step(p, grads, mom, 0.01, 0.9)
     for k in g:
         if k.startswith("final."):
