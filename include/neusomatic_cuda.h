@@ -158,6 +158,31 @@ const char* nsc_model_kernel_name(const nsc_model* m);
 
 int nsc_model_destroy(nsc_model* m);
 
+/* ---- training step (fp32 CUDA-core kernels) -----------------------------------------
+ * One optimisation step of train.py:379-383,416-441: training-mode forward (BatchNorm2d batch statistics and
+ * running-stat update), loss = CrossEntropyLoss(w_type)(o1,y) + SmoothL1Loss()(o2[:,0],center) +
+ * CrossEntropyLoss(w_len)(o3,y_len), loss.backward(), optim.SGD(lr, momentum).step().
+ * Parameters / gradients / momentum are CALLER-OWNED flat fp32 device vectors in nn.Module.named_parameters()
+ * order (network.py:41-64; nsc_trainer_param_slice gives each tensor's offset), `running` is a flat fp32 device
+ * vector [9 BatchNorm layers][mean 64 | var 64] in module order (bn1, res_layers.0.bn_r1, .bn_r2, ...).
+ * A data-parallel driver all-reduces `grads` (one NCCL call on the flat vector) between the two calls. */
+typedef struct nsc_trainer nsc_trainer;
+int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t max_batch);
+int64_t nsc_trainer_num_params(const nsc_trainer* t);
+int nsc_trainer_param_slice(const nsc_trainer* t, const char* name, int64_t* offset, int64_t* numel);
+/* x_dev [B,C,5,32] fp32; type_labels / len_labels [B] int32; centers [B] fp32 (var_pos_s[:,1]); w_type_dev /
+ * w_len_dev [4] fp32 class weights (train.py:364-381); grads [num_params] is overwritten; losses_dev [4] =
+ * (total, CE type, SmoothL1, CE length) or NULL.  2 <= B <= max_batch.  Work is enqueued on `stream`. */
+int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* running, const float* x_dev,
+                               const int32_t* type_labels, const float* centers, const int32_t* len_labels,
+                               const float* w_type_dev, const float* w_len_dev, int64_t B, float bn_momentum,
+                               float* grads, float* losses_dev, void* stream);
+/* optim.SGD: buf = momentum * buf + grad_scale * grad ; p -= lr * buf   (grad_scale = 1 / world size after a
+ * sum all-reduce; momentum buffers start at zero). */
+int nsc_sgd_momentum_update(float* params, float* momentum_buf, const float* grads, int64_t n, float lr,
+                            float momentum, float grad_scale, void* stream);
+int nsc_trainer_destroy(nsc_trainer* t);
+
 /* ---- candidate TSV decoder (host side; no GPU involved) -------------------------------------------------
  * Replaces extract_zlib / candidate_loader_tsv / extract_info_tsv (dataloader.py:38-123) and the tag parsing
  * of NeuSomaticDataset.__getitem__ (dataloader.py:267-274) for inference: mmaps a candidates_*.tsv

@@ -41,6 +41,12 @@ SIGNATURES = {
     "nsc_model_launch_count": (_i64, [_vp]),
     "nsc_model_kernel_name": (C.c_char_p, [_vp]),
     "nsc_model_destroy": (_i32, [_vp]),
+    "nsc_trainer_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i64]),
+    "nsc_trainer_num_params": (_i64, [_vp]),
+    "nsc_trainer_param_slice": (_i32, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "nsc_train_forward_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp]),
+    "nsc_sgd_momentum_update": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
+    "nsc_trainer_destroy": (_i32, [_vp]),
     "nsc_tsv_open": (_i32, [C.POINTER(_vp), C.c_char_p]),
     "nsc_tsv_count": (_i64, [_vp]),
     "nsc_tsv_decode": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32]),

@@ -140,6 +140,8 @@ int fp32_upload_weights(nsc_model* m, float bn_eps);
 void fp32_free_weights(nsc_model* m);
 int fp32_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
 int fp32_conv1(nsc_model* m, const float* x, float* out, int64_t n, cudaStream_t s);
+int fp32_conv_generic(nsc_model* m, int k, int dil, int W, const float* in, const float* wt, const float* bias,
+                      const float* resid, float* out, int64_t n, int Cin, cudaStream_t s);
 int fp32_fc_heads(nsc_model* m, const float* x2, int64_t n, const Outputs& o, cudaStream_t s);
 // nsc_umma.cu
 int umma_upload_weights(nsc_model* m, float bn_eps);

@@ -280,6 +280,22 @@ int fp32_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o
   return fp32_fc_heads(m, Bf, n, o, s);
 }
 
+// Raw convolution (bias only, optional residual add) for the training path (nsc_train.cu): every
+// (kernel size, dilation, width) combination of the network, forward or as data-gradient with flipped weights.
+int fp32_conv_generic(nsc_model* m, int k, int dil, int W, const float* in, const float* wt, const float* bias,
+                      const float* resid, float* out, int64_t n, int Cin, cudaStream_t s) {
+  const int slot = 15;
+  if (k == 1 && W == 32) return launch_conv<1, 3, 1, 32>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 3 && dil == 1 && W == 32) return launch_conv<3, 3, 1, 32>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 5 && dil == 1 && W == 32) return launch_conv<5, 5, 1, 32>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 3 && dil == 2 && W == 16) return launch_conv<3, 3, 2, 16>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 5 && dil == 1 && W == 16) return launch_conv<5, 5, 1, 16>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 3 && dil == 4 && W == 8) return launch_conv<3, 3, 4, 8>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  if (k == 5 && dil == 2 && W == 8) return launch_conv<5, 5, 2, 8>(m, slot, in, wt, bias, resid, out, n, Cin, 0, 0, s);
+  set_error("unsupported convolution (k=%d, dil=%d, W=%d)", k, dil, W);
+  return NSC_E_INVALID;
+}
+
 int fp32_conv1(nsc_model* m, const float* x, float* out, int64_t n, cudaStream_t s) {
   return launch_conv<1, 3, 1, 32>(m, 1, x, m->w32.conv1_w, m->w32.conv1_b, nullptr, out, n, m->C, 1, 1, s);
 }
