@@ -50,7 +50,7 @@ struct nsc_trainer {
 
 namespace nsc {
 
-constexpr int kWgSplits = 32;
+constexpr int kWgSplits = 96;   // batch splits of the weight-gradient kernel (grid = kernel rows x splits)
 
 // ---------------------------------------------------------------------------------------------------------
 // kernels
@@ -67,6 +67,46 @@ __global__ void repack_w_kernel(const float* __restrict__ w, float* __restrict__
 }
 
 // per-channel batch statistics: mean, 1/sqrt(var_biased + eps); running stats updated with momentum (unbiased var)
+constexpr int kRedSplits = 8;    // blocks per channel in the per-channel reductions
+
+// partial per-channel sums over a slice of the batch: part[c][split] = (sum u, sum u^2)
+__global__ void __launch_bounds__(256)
+bn_stats_partial_kernel(const float* __restrict__ u, int N, int HW, double* __restrict__ part) {
+  const int c = blockIdx.x, sp = blockIdx.y;
+  double s = 0.0, ss = 0.0;
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < total; i += 256 * kRedSplits) {
+    const double v = u[((i / HW) * 64 + c) * HW + (i % HW)];
+    s += v;
+    ss += v * v;
+  }
+  __shared__ double sh[2][256];
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[(c * kRedSplits + sp) * 2] = sh[0][0]; part[(c * kRedSplits + sp) * 2 + 1] = sh[1][0]; }
+}
+
+__global__ void bn_stats_final_kernel(const double* __restrict__ part, int64_t total, float eps, float momentum,
+                                      float* __restrict__ stats, float* __restrict__ running) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  double s = 0.0, ss = 0.0;
+  for (int sp = 0; sp < kRedSplits; ++sp) { s += part[(c * kRedSplits + sp) * 2]; ss += part[(c * kRedSplits + sp) * 2 + 1]; }
+  const double mean = s / (double)total;
+  double var = ss / (double)total - mean * mean;
+  if (var < 0) var = 0;
+  stats[c] = (float)mean;
+  stats[64 + c] = (float)(1.0 / sqrt(var + (double)eps));
+  const double unbiased = total > 1 ? var * (double)total / (double)(total - 1) : var;
+  running[c] = (float)((1.0 - momentum) * running[c] + momentum * mean);
+  running[64 + c] = (float)((1.0 - momentum) * running[64 + c] + momentum * unbiased);
+}
+
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ u, int N, int HW, float eps, float momentum, float* __restrict__ stats /*mean|invstd*/,
                 float* __restrict__ running /*mean 64 | var 64*/) {
@@ -156,12 +196,12 @@ __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __res
 // Also used (u == nullptr) as a plain per-channel sum of dy (convolution bias gradient).
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ dy,
-                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][2]*/) {
-  const int c = blockIdx.x;
+                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][2]*/) {
+  const int c = blockIdx.x, sp = blockIdx.y;
   const float mean = u ? stats[c] : 0.f, invstd = u ? stats[64 + c] : 0.f;
   double s = 0.0, sx = 0.0;
   const int64_t total = (int64_t)N * HW;
-  for (int64_t i = threadIdx.x; i < total; i += 256) {
+  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < total; i += 256 * kRedSplits) {
     const int64_t idx = ((i / HW) * 64 + c) * HW + (i % HW);
     float g = dy[idx];
     if (mask_src != nullptr && !(mask_src[idx] > 0.f)) g = 0.f;
@@ -176,7 +216,17 @@ bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stat
     if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { sums[c * 2] = sh[0][0]; sums[c * 2 + 1] = sh[1][0]; }
+  if (threadIdx.x == 0) { sums[(c * kRedSplits + sp) * 2] = sh[0][0]; sums[(c * kRedSplits + sp) * 2 + 1] = sh[1][0]; }
+}
+
+// [64][splits][2] -> [64][2]
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums) {
+  const int c = threadIdx.x;
+  if (c >= 64) return;
+  double a = 0.0, b = 0.0;
+  for (int sp = 0; sp < kRedSplits; ++sp) { a += part[(c * kRedSplits + sp) * 2]; b += part[(c * kRedSplits + sp) * 2 + 1]; }
+  sums[c * 2] = a;
+  sums[c * 2 + 1] = b;
 }
 
 // du = gamma * invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M); also writes dgamma, dbeta
@@ -199,23 +249,24 @@ __global__ void store_channel_sums_kernel(const double* __restrict__ sums, float
 }
 
 // weight gradient partial sums: part[split][tap][ci][co] += x[b, ci, h + dy*d - ph, w + dx*d - pw] * du[b, co, h, w]
-template <int W>
+// One block = (kernel row dy, batch split): the sample is staged once in shared memory and serves the KW taps of the row.
+template <int W, int KW>
 __global__ void __launch_bounds__(256)
-wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ part, int N, int Cin, int KH, int KW,
-             int dil) {
-  const int tap = blockIdx.x, split = blockIdx.y;
-  const int dy = tap / KW, dx = tap % KW;
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ part, int N, int Cin, int KH, int dil) {
+  const int dy = blockIdx.x, split = blockIdx.y;
   const int ph = dil * (KH - 1) / 2, pw = dil * (KW - 1) / 2;
-  const int oy = dy * dil - ph, ox = dx * dil - pw;
+  const int oy = dy * dil - ph;
   extern __shared__ float sm[];
-  float* xs = sm;                     // [Cin][5][W]
+  float* xs = sm;                     // [64][5][W]  (channels >= Cin zero)
   float* ds = sm + 64 * kH * W;       // [64][5][W]
   const int tid = threadIdx.x, cig = tid & 15, cog = tid >> 4;   // 4 input channels x 4 output channels per thread
-  float acc[4][4];
+  float acc[KW][4][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int t = 0; t < KW; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
   const int per = (N + gridDim.y - 1) / gridDim.y;
   const int b0 = split * per, b1 = min(N, b0 + per);
   for (int b = b0; b < b1; ++b) {
@@ -229,25 +280,33 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* _
     for (int h = 0; h < kH; ++h) {
       const int hh = h + oy;
       if (hh < 0 || hh >= kH) continue;
-      const int w_lo = max(0, -ox), w_hi = min(W, W - ox);
-      for (int w = w_lo; w < w_hi; ++w) {
-        float xv[4], dv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i] = xs[((cig * 4 + i) * kH + hh) * W + w + ox];
+      for (int w = 0; w < W; ++w) {
+        float dv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) dv[j] = ds[((cog * 4 + j) * kH + h) * W + w];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int t = 0; t < KW; ++t) {
+          const int ww = w + t * dil - pw;
+          if (ww < 0 || ww >= W) continue;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], dv[j], acc[i][j]);
+          for (int i = 0; i < 4; ++i) {
+            const float xv = xs[((cig * 4 + i) * kH + hh) * W + ww];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(xv, dv[j], acc[t][i][j]);
+          }
+        }
       }
     }
   }
-  float* p = part + ((size_t)split * gridDim.x + tap) * 64 * 64;
+  const int T = KH * KW;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int t = 0; t < KW; ++t) {
+    float* p = part + ((size_t)split * T + dy * KW + t) * 64 * 64;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p[(cig * 4 + i) * 64 + cog * 4 + j] = acc[i][j];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[(cig * 4 + i) * 64 + cog * 4 + j] = acc[t][i][j];
+  }
 }
 
 // dW[co][ci][tap] = sum over splits of part[split][tap][ci][co]
@@ -397,15 +456,18 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
 static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s) {
   const int T = L.k_h * L.k_w;
   const size_t smem = (size_t)2 * 64 * kH * L.W * sizeof(float);
-  dim3 grid(T, kWgSplits);
-#define NSC_WG(WW)                                                                                            \
-  do {                                                                                                        \
-    NSC_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_kernel<WW><<<grid, 256, smem, s>>>(xin, du, t->wpart, N, L.cin, L.k_h, L.k_w, L.dil);                 \
+  dim3 grid(L.k_h, kWgSplits);
+#define NSC_WG(WW, KK)                                                                                              \
+  do {                                                                                                              \
+    NSC_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<WW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wgrad_kernel<WW, KK><<<grid, 256, smem, s>>>(xin, du, t->wpart, N, L.cin, L.k_h, L.dil);                           \
   } while (0)
-  if (L.W == 32) NSC_WG(32);
-  else if (L.W == 16) NSC_WG(16);
-  else NSC_WG(8);
+  if (L.W == 32 && L.k_w == 3) NSC_WG(32, 3);
+  else if (L.W == 32) NSC_WG(32, 5);
+  else if (L.W == 16 && L.k_w == 3) NSC_WG(16, 3);
+  else if (L.W == 16) NSC_WG(16, 5);
+  else if (L.k_w == 3) NSC_WG(8, 3);
+  else NSC_WG(8, 5);
 #undef NSC_WG
   NSC_CUDA_TRY(cudaGetLastError());
   wgrad_reduce_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(t->wpart, dw, L.cin, T, kWgSplits);
@@ -474,7 +536,7 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   e = e ? e : alloc(&t->logits, (size_t)max_batch * 9 * 4); e = e ? e : alloc(&t->dlogits, (size_t)max_batch * 9 * 4);
   e = e ? e : alloc(&t->gA, full); e = e ? e : alloc(&t->gB, full); e = e ? e : alloc(&t->gC, full);
   e = e ? e : alloc(&t->stats, 9 * 128 * 4);
-  e = e ? e : cudaMalloc((void**)&t->red, 256 * sizeof(double));
+  e = e ? e : cudaMalloc((void**)&t->red, (256 + 64 * kRedSplits * 2) * sizeof(double));
   e = e ? e : alloc(&t->wf, (size_t)25 * 128 * 64 * 4); e = e ? e : alloc(&t->wb, (size_t)25 * 64 * 64 * 4);
   e = e ? e : alloc(&t->wpart, (size_t)kWgSplits * 25 * 64 * 64 * 4);
   e = e ? e : alloc(&t->head_w, 9 * kFcHidden * 4); e = e ? e : alloc(&t->head_g, 9 * kFcHidden * 4);
@@ -519,7 +581,9 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     int r = fp32_conv_generic(&t->dummy, L.k_h == 1 ? 1 : L.k_h, L.dil, L.W, in, t->wf, params + L.b_off, nullptr, u, N, L.cin, s);
     if (r != NSC_OK) return r;
     const int HW = kH * L.W;
-    bn_stats_kernel<<<64, 256, 0, s>>>(u, N, HW, eps, bn_momentum, t->stats + li * 128, running + li * 128);
+    bn_stats_partial_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, N, HW, t->red + 256);
+    NSC_LAUNCH_OK();
+    bn_stats_final_kernel<<<1, 64, 0, s>>>(t->red + 256, (int64_t)N * HW, eps, bn_momentum, t->stats + li * 128, running + li * 128);
     NSC_LAUNCH_OK();
     const int64_t total = (int64_t)N * 64 * HW;
     bn_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, params + L.be_off, resid, out, total, HW, relu);
@@ -582,12 +646,16 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const TLayer& L = t->L[li];
     const int HW = kH * L.W;
     const int64_t total = (int64_t)N * 64 * HW;
-    bn_bwd_reduce_kernel<<<64, 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 16);
+    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 256);
+    NSC_LAUNCH_OK();
+    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16);
     NSC_LAUNCH_OK();
     bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
                                                         grads + L.g_off, grads + L.be_off, total, HW, 1.0 / ((double)N * HW));
     NSC_LAUNCH_OK();
-    bn_bwd_reduce_kernel<<<64, 256, 0, s>>>(nullptr, nullptr, du_buf, nullptr, N, HW, t->red + 16);     // conv bias gradient
+    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(nullptr, nullptr, du_buf, nullptr, N, HW, t->red + 256);   // conv bias gradient
+    NSC_LAUNCH_OK();
+    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16);
     NSC_LAUNCH_OK();
     store_channel_sums_kernel<<<1, 64, 0, s>>>(t->red + 16, grads + L.b_off);
     NSC_LAUNCH_OK();
