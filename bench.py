@@ -155,6 +155,49 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def run_train(args, rank, local_rank, world, dev):
+    """BASELINE.json configs[4] (not the headline metric): one train.py optimisation step per bench step on a synthetic
+    batch per GPU; gradients summed over ranks with one NCCL all-reduce of the flat 873 385-float vector."""
+    import torch.distributed as dist
+    from neusomatic_b200 import synth
+    from neusomatic_b200.train import Trainer
+    from oracle import nsnet_oracle as oracle     # input assembly of the synthetic batch only (outside the timed region)
+    B = min(args.batch, 1024)
+    cand = synth.structured_pileups(B, seed=100 + rank)
+    x = torch.from_numpy(oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)).to(dev)
+    vt = torch.tensor([synth.VARTYPE_CLASSES.index(t.split(".")[4]) for t in cand.tags], dtype=torch.int32, device=dev)
+    ln = torch.tensor([min(int(t.split(".")[6]), 3) for t in cand.tags], dtype=torch.int32, device=dev)
+    ce = torch.from_numpy(cand.center).float().to(dev)
+    w1 = torch.tensor([0.2, 0.21, 0.13, 0.16], device=dev)
+    w3 = torch.tensor([0.12, 0.2, 0.23, 0.24], device=dev)
+    tr = Trainer(synth.random_state_dict(26, seed=11), 26, device=local_rank, max_batch=B)
+    for _ in range(args.warmup):
+        tr.step(x, vt, ce, ln, w1, w3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = tr.step(x, vt, ce, ln, w1, w3)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "NeuSomaticNet train samples/sec (fwd+bwd+SGD)", "value": world * B * args.steps / (ms / 1000.0),
+                          "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "train.py step (BASELINE.json configs[4]): C=26, SGD lr 0.01 momentum 0.9, "
+                                                 "BatchNorm batch statistics per GPU, one NCCL all-reduce of 873385 floats per step",
+                                     "batch_per_gpu": B}, "loss": float(losses[0])}), flush=True)
+    tr.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +209,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--train", action="store_true", help="BASELINE configs[4]: train.py step (fwd+bwd+SGD), data-parallel with one NCCL all-reduce")
     ap.add_argument("--ensemble", action="store_true", help="BASELINE configs[3]: C=119 ensemble model (not the default metric config)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -187,6 +231,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.train:
+        run_train(args, rank, local_rank, world, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     C = 119 if args.ensemble else 26
     sd, meta = load_checkpoint(os.path.join(ROOT, "tests", "golden", "ens_v010.pth") if args.ensemble else CKPT)
