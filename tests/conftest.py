@@ -22,7 +22,7 @@ def load_golden(name):
     return g, ck
 
 
-@pytest.fixture(scope="session", params=["std_v010", "ens_v010", "std_v014"])
+@pytest.fixture(scope="session", params=["std_v010", "ens_v010", "std_v014", "ens_v014", "std_wex"])
 def golden(request):
     g, ck = load_golden(request.param)
     return request.param, g, ck

@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-What it does, per model (standalone v0.1.0, ensemble v0.1.0, standalone v0.1.4):
+What it does, per model (standalone v0.1.0, ensemble v0.1.0, standalone v0.1.4, ensemble v0.1.4, standalone WEX):
   1. generates seeded structured candidates (neusomatic_b200.synth.structured_pileups),
   2. writes them as a candidate TSV + .idx in the reference's on-disk format
      (generate_dataset.py:1569-1583),
@@ -46,6 +46,8 @@ MODELS = {
     "std_v010": ("NeuSomatic_v0.1.0_standalone_Dream3_70purity.pth", False, 192, 2024),
     "ens_v010": ("NeuSomatic_v0.1.0_ensemble_Dream3_70purity.pth", True, 96, 2025),
     "std_v014": ("NeuSomatic_v0.1.4_standalone_SEQC-WGS-Spike.pth", False, 192, 2026),
+    "ens_v014": ("NeuSomatic_v0.1.4_ensemble_SEQC-WGS-GT50-SpikeWGS10.pth", True, 96, 2027),
+    "std_wex": ("NeuSomatic_v0.1.0_standalone_WEX_100purity.pth", False, 128, 2028),
 }
 
 

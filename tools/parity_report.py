@@ -8,7 +8,7 @@ from oracle import nsnet_oracle as oracle
 from neusomatic_b200 import Engine
 from neusomatic_b200.call import load_checkpoint
 
-for name in ("std_v010", "ens_v010", "std_v014"):
+for name in ("std_v010", "ens_v010", "std_v014", "ens_v014", "std_wex"):
     g, ck = load_golden(name)
     x = oracle.assemble_channels(g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], g.get("anns"),
                                  int(ck["coverage_thr"]))
