@@ -47,6 +47,7 @@ CONV_STACK_MACS = 5_898_240 * 2 + 16_384_000 * 2 + 2_949_120 + 8_192_000 + 1_474
 # (13/15, 19/25, 11/15, 7/15, 13/25 of the taps), times 3 products in split mode
 CONV_STACK_EXEC_MACS = 2 * (5_898_240 * 13 // 15 + 16_384_000 * 19 // 25) + 2_949_120 * 11 // 15 + 8_192_000 * 19 // 25 + \
     1_474_560 * 7 // 15 + 4_096_000 * 13 // 25
+MMA_SLOTS = {0: 3, 1: 1, 3: 2}    # fp16-equivalent tcgen05 issue slots per MAC by NSC_PREC_* mode
 CKPT = os.path.join(ROOT, "tests", "golden", "std_v010.pth")
 
 
@@ -335,9 +336,11 @@ def main():
                 "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                 "kernel_share_of_step": conv_ms / total_ms if total_ms else None,
                 "algorithmic_flops_per_candidate": 2 * CONV_STACK_MACS,
-                "executed_tensor_tflops": cands * 2 * CONV_STACK_EXEC_MACS * (3 if eng.precision == 0 else 1) /
+                # tensor-pipe occupancy in fp16-instruction equivalents: 3 per MAC (split-f16), 2 per MAC (split8: one fp16
+                # + two fp8 products, an fp8 instruction covers twice the K of an fp16 one in the same issue slot)
+                "executed_tensor_tflops": cands * 2 * CONV_STACK_EXEC_MACS * MMA_SLOTS.get(eng.precision, 1) /
                                           (conv_ms / 1000.0) / 1e12 if eng.precision != 2 else None,
-                "executed_frac_of_peak": (cands * 2 * CONV_STACK_EXEC_MACS * (3 if eng.precision == 0 else 1) /
+                "executed_frac_of_peak": (cands * 2 * CONV_STACK_EXEC_MACS * MMA_SLOTS.get(eng.precision, 1) /
                                           (conv_ms / 1000.0) / 1e12 / pk["bf16_sustained"]) if eng.precision != 2 else None,
                 "whole_net_frac": (value / world) * FLOPS_PER_CAND[C] / 1e12 / pk["bf16_sustained"],
                 "per_kernel_ms": {k_: round(v[0] / args.steps, 4) for k_, v in prof.items()}}
@@ -349,7 +352,8 @@ def main():
                "sample": "oracle/torch_port.py (PyTorch CPU operators, fp32): " + sample}
 
     if rank == 0:
-        prec_names = {0: "split-f16 (fp16 hi+lo operands, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 1: "f16", 2: "f32"}
+        prec_names = {0: "split-f16 (fp16 hi+lo operands, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 1: "f16", 2: "f32",
+                      3: "f16 + fp8 corrections (fp16 main product, two e4m3 correction products scaled by 2^15, fp32 accumulate)"}
         print(json.dumps({
             "metric": "NeuSomaticNet candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,

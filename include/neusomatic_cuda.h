@@ -44,6 +44,8 @@ extern "C" {
 #define NSC_PREC_SPLIT_BF16 NSC_PREC_SPLIT16   /* historical names */
 #define NSC_PREC_BF16 NSC_PREC_SINGLE16
 #define NSC_PREC_FP32 2       /* fp32 FFMA kernels (CUDA cores): bit-stable reference path    */
+#define NSC_PREC_SPLIT8 3     /* tcgen05: fp16 main product + the two correction products on the fp8 (e4m3) path
+                                 with power-of-two scaling, 2 instruction slots per MAC; meets the parity bar */
 
 typedef struct nsc_model nsc_model;
 

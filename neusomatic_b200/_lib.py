@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libneusomatic_cuda.so")
 PREC_SPLIT_BF16 = 0
 PREC_BF16 = 1
 PREC_FP32 = 2
+PREC_SPLIT8 = 3
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
 _OUT7 = [_vp] * 7   # type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax

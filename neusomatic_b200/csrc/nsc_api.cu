@@ -181,6 +181,7 @@ static int forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs&
       return fp32_forward_chunk(m, x, n, o, s);
     case NSC_PREC_SPLIT_BF16:
     case NSC_PREC_BF16:
+    case NSC_PREC_SPLIT8:
       return umma_forward_chunk(m, x, n, o, s);
     default:
       set_error("unknown precision mode %d", m->precision);
@@ -288,7 +289,8 @@ int nsc_model_finalize(nsc_model* m, float bn_eps) {
 
 int nsc_model_set_precision(nsc_model* m, int precision) {
   if (!m) { set_error("model is NULL"); return NSC_E_INVALID; }
-  if (precision != NSC_PREC_FP32 && precision != NSC_PREC_SPLIT_BF16 && precision != NSC_PREC_BF16) {
+  if (precision != NSC_PREC_FP32 && precision != NSC_PREC_SPLIT_BF16 && precision != NSC_PREC_BF16 &&
+      precision != NSC_PREC_SPLIT8) {
     set_error("unknown precision mode %d", precision);
     return NSC_E_INVALID;
   }

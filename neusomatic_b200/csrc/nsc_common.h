@@ -77,13 +77,15 @@ struct UmmaState {
   uint8_t* w1pk = nullptr;              // fc1: [2][20] tiles of [240][64] fp16, swizzle-128B (nsc_fc_umma.cu)
   uint8_t* wpk1 = nullptr;              // conv1: swizzled fp16 hi/lo weight stages (nsc_umma.cu)
   uint8_t* wpk[4][2] = {};              // res_layers[i].conv_r{1,2}
+  uint8_t* wpk8[4][2] = {};             // the same layers for NSC_PREC_SPLIT8 (fp8 correction stages + fp16 stages)
   int nk1 = 1;                          // 32-channel input slices of conv1 (C = 26 -> 1, C = 119 -> 4)
   uint16_t* xin[2] = {};                // packed network input (hi, lo): [cap/8][5][32][8][32*nk1]
-  uint16_t* buf[3][2] = {};             // 3 packed activation tensors x (hi, lo): [cap/8][5][32][8][64]
+  uint16_t* buf[3][3] = {};             // 3 packed activation tensors x (hi, lo, c8): [cap/8][5][32][8][64] (c8: 128 B rows)
   float* fc_in = nullptr;               // fp32 [cap,1280] input of fc1
   int64_t cap = 0;
   int num_sms = 148;
   bool weights_fit_fp16 = true;
+  bool weights_fit_fp8 = true;
 };
 
 }  // namespace nsc

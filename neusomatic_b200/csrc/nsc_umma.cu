@@ -24,15 +24,25 @@
 // split-fp16 sits at the fp32 noise floor).  A unit runs in 2*NK phases (x_hi | x_lo) x (32-channel
 // slices) so that only a 50 KB A buffer is live per phase; two buffers double-buffer the TMA loads.
 //
+// NSC_PREC_SPLIT8 (ConvCfg::S8): the two correction products run on the fp8 tensor path instead, at twice the
+// MAC rate per instruction:   x*w ~= [ e4m3(x_lo * 2^12) * e4m3(w * 2^3) + e4m3(x) * e4m3(w_lo * 2^15) ] * 2^-15 + x_hi*w_hi.
+// The fp8 products accumulate first (kind::f8f6f4, K = 32 per instruction), then the first kind::f16 MMA on each
+// accumulator rescales it with scale_input_d = 15 (D = A*B + D * 2^-15) and the fp16 products follow: 2 instruction
+// slots per MAC instead of 3.  The activations of such a layer are stored as x16 (fp16), c8 = [e4m3(x) | e4m3(x_lo*2^12)]
+// (one 128-byte row per position) and, for tensors that are also a residual input, the exact fp16 lo part.
+// CPU emulation (tools/emulate_fp8_corrections.py): max |dlogit| 5.5e-4, |dprob| 1.2e-4, |dpos| 1.5e-4 over the golden sets.
+//
 // Overlap: the five accumulators of consecutive units live at TMEM columns [0,320) and [192,512)
 // alternately, so only two of them are shared; the epilogue (8 warps) drains those two first and the
 // MMA issuer starts the next unit on the three free accumulators meanwhile.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "nsc_common.h"
 #include "umma.cuh"
@@ -46,15 +56,18 @@ constexpr int kEpiThreads = 256;
 constexpr int kStageBytes = 32768;      // epilogue staging: hi plane + lo plane of one [128 x 64] row tile
 constexpr int kStashBytes = 20480;      // boundary columns carried between the two column blocks (W = 32)
 
-template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_, int KC_ = 32, int GP_ = 1>
+template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_, int KC_ = 32, int GP_ = 1, bool S8_ = false>
 struct ConvCfg {
+  static constexpr bool S8 = S8_;                        // fp8 correction products (64 input channels only)
   static constexpr int KH = KH_, KW = KW_, DIL = DIL_, W = W_, NK = NK_, POOL = POOL_;
   static constexpr bool NCHW = NCHW_;
   static constexpr int KC = KC_;                         // input channels per phase / weight stage (32 or 16)
   static constexpr int GP = GP_;                         // candidate groups per unit (2 for the W = 8 layers: M stays 128)
   static constexpr int RB = KC * 2;                      // bytes per operand row
   static constexpr int ATOM = 8 * RB;                    // 8-row swizzle atom = SBO of the UMMA descriptors
-  static constexpr int NKK = KC / 16;                    // MMA K-steps per stage
+  static constexpr int NKK = KC / 16;                    // MMA K-steps per stage (32 operand bytes each, either kind)
+  static constexpr int NPH8 = S8 ? 2 * (64 / RB) : 0;    // fp8 phases per unit: (x_lo8 | x8) x slices of RB channels
+  static constexpr int NPH = S8 ? NPH8 + NK : 2 * NK;    // phases per unit
   static constexpr uint32_t SWZ = KC == 32 ? kSwizzle64 : kSwizzle32;
   static constexpr int PW = DIL * (KW - 1) / 2, PH = DIL * (KH - 1) / 2;
   static constexpr int TW = (W >= 16) ? 16 : 8;          // output columns per unit
@@ -71,6 +84,7 @@ struct ConvCfg {
   static constexpr bool STASH = (SUBS == 2) && (POOL != 0);
   static_assert(PW <= HALO, "halo too small");
   static_assert(KC == 32 || KC == 16, "KC");
+  static_assert(!S8 || NK * KC == 64, "the fp8 correction layout assumes 64 input channels");
   static_assert(!(STASH && GP != 1), "column-block stash assumes one group per unit");
   static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
                                  (STASH ? kStashBytes : 0) + 256;
@@ -91,11 +105,39 @@ __host__ __device__ __forceinline__ constexpr int slot_row(int s) {
   return 0;
 }
 
+// Input rows whose reachable output rows (h_out = h_in - dy*DIL + PH) are pairwise disjoint and together all five
+// (bit h_in set), found greedily; 0 if the greedy choice does not cover everything.
+template <int KH, int DIL>
+__host__ __device__ constexpr uint32_t cover_set() {
+  constexpr int PH = DIL * (KH - 1) / 2;
+  uint32_t covered = 0, chosen = 0;
+  for (int iter = 0; iter < kH; ++iter) {
+    int best = -1, best_n = 0;
+    for (int h_in = 0; h_in < kH; ++h_in) {
+      uint32_t m = 0;
+      int n = 0;
+      for (int dy = 0; dy < KH; ++dy) {
+        const int h_out = h_in - dy * DIL + PH;
+        if (h_out >= 0 && h_out < kH) { m |= 1u << h_out; ++n; }
+      }
+      if ((m & covered) == 0 && n > best_n) { best = h_in; best_n = n; }
+    }
+    if (best < 0) break;
+    for (int dy = 0; dy < KH; ++dy) {
+      const int h_out = best - dy * DIL + PH;
+      if (h_out >= 0 && h_out < kH) covered |= 1u << h_out;
+    }
+    chosen |= 1u << best;
+  }
+  return covered == 0x1fu ? chosen : 0u;
+}
+
 struct UmmaConvArgs {
   const uint8_t* wpk;        // packed weights of this layer (pack_conv_weights)
   const float* bias;         // [64] folded BN bias
   uint16_t* out_hi;          // packed [groups][5][WOUT][8][64] (hi / lo)
-  uint16_t* out_lo;
+  uint16_t* out_lo;          // exact fp16 lo part (nullptr: not needed by the consumer)
+  uint8_t* out_c8;           // packed [groups][5][WOUT][8][128]: e4m3(x) | e4m3(x_lo * 2^12) for an S8 consumer (or nullptr)
   float* out_nchw;           // fp32 [B,64,5,WOUT] (NCHW configs)
   const uint16_t* res_hi;    // residual input, packed, width W (or nullptr)
   const uint16_t* res_lo;
@@ -104,6 +146,7 @@ struct UmmaConvArgs {
   int relu;
   int split;                 // 1: hi/lo split operands (3 products); 0: single-pass fp16
   long long* stats;          // optional [grid][8] cycle counters (NSC_UMMA_STATS=1)
+  int dbg_skip;              // timing experiments only (NSC_UMMA_SKIP): 1 = no fp8 MMAs, 2 = no fp16 MMAs, 4 = no epilogue body
 };
 
 // ---- fp16 hi/lo helpers --------------------------------------------------------------------------------
@@ -134,6 +177,47 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   split2(v[4], v[5], hi.z, lo.z);
   split2(v[6], v[7], hi.w, lo.w);
 }
+// four values -> four e4m3 bytes (first value in the lowest byte), round to nearest, saturating
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+constexpr float kXlo8Scale = 4096.f;   // 2^12 on the activation lo part, 2^3 on w, 2^15 on w_lo: every fp8 product carries 2^15
+// One output item: channels [4 ch, 4 ch + 4) (v0) and [32 + 4 ch, ...) (v1) of packed position row `prow`
+__device__ __forceinline__ void store_item(uint16_t* out_hi, uint16_t* out_lo, uint8_t* out_c8, size_t prow, int ch,
+                                           const float4& v0, const float4& v1) {
+  const size_t o = prow * 64 + ch * 4;
+  uint2 h0, l0, h1, l1;
+  split2(v0.x, v0.y, h0.x, l0.x); split2(v0.z, v0.w, h0.y, l0.y);
+  split2(v1.x, v1.y, h1.x, l1.x); split2(v1.z, v1.w, h1.y, l1.y);
+  *reinterpret_cast<uint2*>(out_hi + o) = h0;
+  *reinterpret_cast<uint2*>(out_hi + o + 32) = h1;
+  if (out_lo != nullptr) {
+    *reinterpret_cast<uint2*>(out_lo + o) = l0;
+    *reinterpret_cast<uint2*>(out_lo + o + 32) = l1;
+  }
+  if (out_c8 != nullptr) {
+    uint8_t* c = out_c8 + prow * 128 + ch * 4;
+    *reinterpret_cast<uint32_t*>(c) = e4m3x4(v0.x, v0.y, v0.z, v0.w);
+    *reinterpret_cast<uint32_t*>(c + 32) = e4m3x4(v1.x, v1.y, v1.z, v1.w);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h0.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h0.y));
+    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&h1.x)), f = __half22float2(*reinterpret_cast<const __half2*>(&h1.y));
+    *reinterpret_cast<uint32_t*>(c + 64) = e4m3x4((v0.x - a.x) * kXlo8Scale, (v0.y - a.y) * kXlo8Scale, (v0.z - b.x) * kXlo8Scale, (v0.w - b.y) * kXlo8Scale);
+    *reinterpret_cast<uint32_t*>(c + 96) = e4m3x4((v1.x - e.x) * kXlo8Scale, (v1.y - e.y) * kXlo8Scale, (v1.z - f.x) * kXlo8Scale, (v1.w - f.y) * kXlo8Scale);
+  }
+}
+// 32-byte global vectors (LDG/STG.256 on sm_100)
+__device__ __forceinline__ void ldg_v8(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 template <class Cfg>
@@ -152,7 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   uint8_t* stash = st_lo + 16384;                                // [hi|lo][2 cols][5][8 g][8 chunks][16 B]
   __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[64];
+  __shared__ __align__(16) float bias_s[64];
   const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[3]);
   const uint32_t w_full = smem_u32(&bars[6]), w_empty = smem_u32(&bars[14]);
   const uint32_t acc_full = smem_u32(&bars[22]), shared_free = smem_u32(&bars[23]), all_free = smem_u32(&bars[24]);
@@ -175,7 +259,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const int nph = args.split ? 2 * NK : NK;     // phases per unit: (hi | lo) x NK channel slices
+  // phases per unit: (lo | hi) x NK channel slices, or for S8 (x_lo8 | x8) x byte slices then NK fp16 slices
+  const int nph = Cfg::S8 ? Cfg::NPH : (args.split ? 2 * NK : NK);
 
   if (warp == 0) {
     // ===== A producer: one TMA box per phase =====
@@ -186,10 +271,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           for (int ph = 0; ph < nph; ++ph, ++it) {
             const uint32_t buf = it % Cfg::NA;
             if (it >= Cfg::NA) mbar_wait(a_empty + 8 * buf, ((it / Cfg::NA) - 1) & 1);
+            if (args.dbg_skip & 8) { mbar_arrive(a_full + 8 * buf); continue; }
             mbar_arrive_expect_tx(a_full + 8 * buf, Cfg::A_BYTES);
             // tensor-map dims: (channel, candidate, group-in-unit, column, group*5 + row)
-            tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), (args.split && ph < NK) ? &tmap_lo : &tmap_hi, a_full + 8 * buf,
-                        (ph % NK) * Cfg::KC, 0, 0, sub * Cfg::TW - Cfg::HALO, grp * Cfg::GP * kH);
+            const void* tm;
+            int c0;
+            if (Cfg::S8) {
+              // tmap_lo = the c8 tensor (bytes 0-63: e4m3(x), 64-127: e4m3(x_lo * 2^12)); the x_lo8 slices come first
+              constexpr int HP = Cfg::NPH8 / 2;
+              tm = ph < Cfg::NPH8 ? &tmap_lo : &tmap_hi;
+              c0 = ph < HP ? 64 + ph * Cfg::RB : ph < Cfg::NPH8 ? (ph - HP) * Cfg::RB : (ph - Cfg::NPH8) * Cfg::KC;
+            } else {
+              tm = (args.split && ph < NK) ? &tmap_lo : &tmap_hi;
+              c0 = (ph % NK) * Cfg::KC;
+            }
+            tma_load_5d(smem_u32(a_buf + buf * Cfg::A_BYTES), tm, a_full + 8 * buf, c0, 0, 0, sub * Cfg::TW - Cfg::HALO,
+                        grp * Cfg::GP * kH);
           }
     }
   } else if (warp == 2) {
@@ -199,16 +296,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
       for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
         for (int sub = 0; sub < Cfg::SUBS; ++sub)
           for (int ph = 0; ph < nph; ++ph) {
-            const int nsel = (args.split && ph >= NK) ? 2 : 1;
+            const int nsel = (!Cfg::S8 && args.split && ph >= NK) ? 2 : 1;
             for (int si = 0; si < nsel; ++si)
               for (int dx = 0; dx < KW; ++dx, ++it) {
                 const int sel = nsel == 2 ? 1 - si : 0;       // x_hi phases: w_lo stages first, then w_hi
+                // S8: the stages are packed in the order they are consumed (pack_conv_weights_s8)
+                const size_t stage_idx = Cfg::S8 ? (size_t)(ph * KW + dx) : (size_t)((sel * NK + (ph % NK)) * KW + dx);
                 const uint32_t st = it % WS;
                 if (it >= WS) mbar_wait(w_empty + 8 * st, ((it / WS) - 1) & 1);
+                if (args.dbg_skip & 16) { mbar_arrive(w_full + 8 * st); continue; }
                 mbar_arrive_expect_tx(w_full + 8 * st, Cfg::W_STAGE_BYTES);
-                bulk_g2s(smem_u32(w_buf + st * Cfg::W_STAGE_BYTES),
-                         args.wpk + (size_t)((sel * NK + (ph % NK)) * KW + dx) * Cfg::W_STAGE_BYTES, Cfg::W_STAGE_BYTES,
-                         w_full + 8 * st);
+                bulk_g2s(smem_u32(w_buf + st * Cfg::W_STAGE_BYTES), args.wpk + stage_idx * Cfg::W_STAGE_BYTES,
+                         Cfg::W_STAGE_BYTES, w_full + 8 * st);
               }
           }
     }
@@ -218,24 +317,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
       uint32_t a_it = 0, w_it = 0, u_it = 0;
       long long t_acc = 0, t_a = 0, t_w = 0, t_c;
       const long long t_begin = clock64();
-      for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
-        for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
-          const uint32_t acc0 = tmem + (u_it & 1) * 192;          // accumulator window of this unit
-          const uint32_t shared_slots = (u_it & 1) ? 0x03u : 0x18u;   // slots shared with the previous unit
+      // one unit; the parity of the unit (which accumulator window, which slots are shared with the previous unit)
+      // is a compile-time tag: every tcgen05.mma below is then unconditional (a predicated-off MMA still costs its
+      // issue slot, measured)
+      auto run_unit = [&](auto par_tag) {
+          constexpr uint32_t PAR = decltype(par_tag)::value ? 1u : 0u;
+          const uint32_t acc0 = tmem + PAR * 192;                 // accumulator window of this unit
+          constexpr uint32_t shared_slots = PAR ? 0x03u : 0x18u;  // slots shared with the previous unit
           t_c = clock64();
           if (u_it >= 2) mbar_wait(all_free + 8 * (u_it & 1), ((u_it >> 1) - 1) & 1);   // unit u-2 fully drained
           t_acc += clock64() - t_c;
           tc_fence_after_sync();
           uint32_t touched = 0;
           bool first_stage = true;
-          for (int ph = 0; ph < nph; ++ph, ++a_it) {
+          // one phase; F8 is a compile-time tag so that the fp8 and fp16 phases are separate instruction streams (a
+          // runtime flag made ptxas emit every MMA twice, predicated, and the nullified twin still costs an issue slot)
+          auto run_phase = [&](const int ph, auto f8_tag) {
+            constexpr bool f8 = decltype(f8_tag)::value;
             const uint32_t buf = a_it % Cfg::NA;
             t_c = clock64();
             mbar_wait(a_full + 8 * buf, (a_it / Cfg::NA) & 1);
             t_a += clock64() - t_c;
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(a_buf + buf * Cfg::A_BYTES);
-            const int nsel = (args.split && ph >= NK) ? 2 : 1;
+            const int nsel = (!Cfg::S8 && args.split && ph >= NK) ? 2 : 1;
             for (int si = 0; si < nsel; ++si)
               for (int dx = 0; dx < KW; ++dx, ++w_it) {
                 const uint32_t st = w_it % WS;
@@ -245,10 +350,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 tc_fence_after_sync();
                 const uint32_t w_base = smem_u32(w_buf + st * Cfg::W_STAGE_BYTES);
                 const int wl0 = dx * DIL - Cfg::PW + Cfg::HALO;   // first box column of this kernel column
-                if (first_stage) {
+                if (args.dbg_skip & (f8 ? 1 : 2)) {
+                } else if (first_stage) {
                   // first touch of every accumulator: single-tap MMAs with explicit accumulate flags; the
                   // accumulators not shared with the previous unit go first, the two shared ones after the
                   // epilogue has drained them
+#pragma unroll
                   for (int pass = 0; pass < 2; ++pass) {
                     if (pass == 1 && u_it > 0) {
                       t_c = clock64();
@@ -269,8 +376,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                         for (int kk = 0; kk < Cfg::NKK; ++kk) {
                           const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
                           const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                          umma_f16(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
+                          if (f8) umma_f8(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
+                          else umma_f16(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
                           touched |= 1u << h_out;
+                        }
+                      }
+                    }
+                  }
+                } else if (Cfg::S8 && !f8 && ph == Cfg::NPH8 && dx == 0) {
+                  // first fp16 stage: the first fp16 MMA on each accumulator rescales the fp8 sums (D = A*B + D * 2^-15).
+                  // The input rows of cover_set() reach disjoint sets of output rows that together are all five, so
+                  // their first K-step carries the scale on whole concatenated instructions; everything else is plain.
+                  constexpr uint32_t COVER = cover_set<KH, DIL>();
+                  static_assert(COVER != 0, "no disjoint cover of the output rows");
+#pragma unroll
+                  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                    for (int h_in = 0; h_in < kH; ++h_in) {
+                      if ((int)((COVER >> h_in) & 1u) == pass) continue;     // pass 0: the cover rows, pass 1: the rest
+                      int dy_lo = KH, dy_hi = -1;
+#pragma unroll
+                      for (int dy = 0; dy < KH; ++dy) {
+                        const int h_out = h_in - dy * DIL + Cfg::PH;
+                        if (h_out >= 0 && h_out < kH) { dy_lo = dy < dy_lo ? dy : dy_lo; dy_hi = dy; }
+                      }
+                      if (dy_hi < 0) continue;
+                      const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
+#pragma unroll
+                      for (int kk = 0; kk < Cfg::NKK; ++kk) {
+                        const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
+                        for (int dy = dy_lo, n = 0; dy <= dy_hi; dy += n) {
+                          const int rem = dy_hi - dy + 1;
+                          n = rem == 5 ? 3 : (rem < 4 ? rem : 4);
+                          const int h_out = h_in - dy * DIL + Cfg::PH;
+                          const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
+                          const uint32_t d = acc0 + acc_slot<DIL>(h_out) * 64;
+                          if (pass == 0 && kk == 0) umma_f16_scaled<15>(d, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0));
+                          else umma_f16(d, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
                         }
                       }
                     }
@@ -295,7 +437,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                         n = rem == 5 ? 3 : (rem < 4 ? rem : 4);   // N = 64 n <= 256; 5 rows as 192 + 128
                         const int h_out = h_in - dy * DIL + Cfg::PH;
                         const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                        umma_f16(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
+                        if (f8) umma_f8(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
+                        else umma_f16(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
                       }
                     }
                   }
@@ -304,8 +447,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 first_stage = false;
               }
             umma_commit(a_empty + 8 * buf);
+            ++a_it;
+          };
+          if (Cfg::S8) {
+            for (int ph = 0; ph < Cfg::NPH8; ++ph) run_phase(ph, std::true_type{});
+            for (int ph = Cfg::NPH8; ph < Cfg::NPH; ++ph) run_phase(ph, std::false_type{});
+          } else {
+            for (int ph = 0; ph < nph; ++ph) run_phase(ph, std::false_type{});
           }
           umma_commit(acc_full);
+      };
+      for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
+        for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
+          if (u_it & 1) run_unit(std::true_type{});
+          else run_unit(std::false_type{});
         }
       if (args.stats) {
         long long* st = args.stats + (size_t)blockIdx.x * 8;
@@ -372,6 +527,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         mbar_arrive(shared_free);
 #pragma unroll 1
         for (int idx = 0; idx < kH; ++idx) {
+          if (args.dbg_skip & 4) { if (idx == kH - 1) { tc_fence_before_sync(); mbar_arrive(all_free + 8 * (u_it & 1)); } continue; }
           const int slot = (u_it & 1) ? idx : (idx < 2 ? 3 + idx : idx - 2);
           const int h = slot_row<DIL>(slot);
           if (idx == 1) {
@@ -422,14 +578,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const float* p0 = stg + rr * 64 + ((ch ^ (rr & 7)) << 2);
             float4 m0 = *reinterpret_cast<const float4*>(p0), m1 = *reinterpret_cast<const float4*>(p0 + 32);
             if (Cfg::POOL == 0) {
-              const size_t o = row_off(grp, h, W, w0 + wl, rr) + ch * 4;
-              uint2 hi, lo;
-              split2(m0.x, m0.y, hi.x, lo.x); split2(m0.z, m0.w, hi.y, lo.y);
-              *reinterpret_cast<uint2*>(args.out_hi + o) = hi;
-              *reinterpret_cast<uint2*>(args.out_lo + o) = lo;
-              split2(m1.x, m1.y, hi.x, lo.x); split2(m1.z, m1.w, hi.y, lo.y);
-              *reinterpret_cast<uint2*>(args.out_hi + o + 32) = hi;
-              *reinterpret_cast<uint2*>(args.out_lo + o + 32) = lo;
+              store_item(args.out_hi, args.out_lo, args.out_c8, row_off(grp, h, W, w0 + wl, rr) / 64, ch, m0, m1);
               continue;
             }
             // stash slots: 0 = column TW-2, 1 = column TW-1 of the first column block
@@ -454,14 +603,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                   o[0] = b1.x; o[cs] = b1.y; o[2 * cs] = b1.z; o[3 * cs] = b1.w;
                 }
               } else {
-                const size_t o = (((((size_t)ga * kH + h) * Cfg::WOUT + wo) * 8 + g) * 64) + ch * 4;
-                uint2 hi, lo;
-                split2(b0.x, b0.y, hi.x, lo.x); split2(b0.z, b0.w, hi.y, lo.y);
-                *reinterpret_cast<uint2*>(args.out_hi + o) = hi;
-                *reinterpret_cast<uint2*>(args.out_lo + o) = lo;
-                split2(b1.x, b1.y, hi.x, lo.x); split2(b1.z, b1.w, hi.y, lo.y);
-                *reinterpret_cast<uint2*>(args.out_hi + o + 32) = hi;
-                *reinterpret_cast<uint2*>(args.out_lo + o + 32) = lo;
+                store_item(args.out_hi, args.out_lo, args.out_c8, ((((size_t)ga * kH + h) * Cfg::WOUT + wo) * 8 + g), ch, b0, b1);
               }
             };
             const bool do_emit = (ST == 1) ? !(Cfg::STASH && sub == 0 && wl == Cfg::TW - 1) : ((wl & 1) == 0);
@@ -558,21 +700,25 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // Packed activation tensor act[group][5][W][8][Cpad] seen as (channel, candidate, group-in-unit, column, group*5 + row):
 // the group stride is exactly 5 row strides, so the two groups of a unit are one extra dimension of stride 5 rows.
-static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int Cpad, int box_w, int KC, int GP) {
+// elem_bytes = 2: fp16 tensor with Cpad channels per row, box of KC channels.  elem_bytes = 1: the c8 tensor
+// (Cpad = 128 bytes per row), box of KC bytes.  The swizzle mode follows the box row bytes (64 or 32).
+static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int Cpad, int box_w, int KC, int GP,
+                         int elem_bytes = 2) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult q;
     NSC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &q));
     if (!encode) { set_error("cuTensorMapEncodeTiled is not available"); return NSC_E_CUDA; }
   }
-  const cuuint64_t row = (cuuint64_t)Cpad * 2;
+  const cuuint64_t row = (cuuint64_t)Cpad * elem_bytes;
   const cuuint64_t img_row = (cuuint64_t)W * 8 * row;
   cuuint64_t dims[5] = {(cuuint64_t)Cpad, 8, (cuuint64_t)GP, (cuuint64_t)W, (cuuint64_t)(groups * kH - kH * (GP - 1))};
   cuuint64_t strides[4] = {row, kH * img_row, 8 * row, img_row};
   cuuint32_t box[5] = {(cuuint32_t)KC, 8, (cuuint32_t)GP, (cuuint32_t)box_w, (cuuint32_t)kH};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = encode(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, base, dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      KC * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return NSC_E_CUDA; }
   return NSC_OK;
@@ -597,6 +743,33 @@ static std::vector<uint8_t> pack_conv_weights(const std::vector<float>& w, int C
           const uint32_t off = (KC == 32 ? ptx::swz_offset<64>(r, c) : ptx::swz_offset<32>(r, c)) + (k % 8) * 2;
           memcpy(out.data() + (size_t)((0 * NK + kc) * KW + dx) * stage + off, &hi, 2);
           memcpy(out.data() + (size_t)((1 * NK + kc) * KW + dx) * stage + off, &lo, 2);
+        }
+  return out;
+}
+
+// NSC_PREC_SPLIT8 stages of a 64 -> 64 convolution, in the order the kernel consumes them (phase-major, then kernel
+// column): [x_lo8 phases: e4m3(w * 2^3)] [x8 phases: e4m3((w - fp16(w)) * 2^15)] [x16 phases: fp16(w)], every stage
+// [KH][64 cout][RB bytes of cin] in the swizzled K-major shared-memory image (RB = 2 KC: 64 or 32).
+static std::vector<uint8_t> pack_conv_weights_s8(const std::vector<float>& w, int KH, int KW, int KC) {
+  const int RB = 2 * KC, NS8 = 64 / RB, NK = 64 / KC;
+  const size_t stage = (size_t)KH * 64 * RB;
+  std::vector<uint8_t> out((size_t)(2 * NS8 + NK) * KW * stage, 0);
+  auto swz = [&](uint32_t r, uint32_t chunk) { return RB == 64 ? ptx::swz_offset<64>(r, chunk) : ptx::swz_offset<32>(r, chunk); };
+  for (int co = 0; co < 64; ++co)
+    for (int ci = 0; ci < 64; ++ci)
+      for (int dy = 0; dy < KH; ++dy)
+        for (int dx = 0; dx < KW; ++dx) {
+          const float v = w[(((size_t)co * 64 + ci) * KH + dy) * KW + dx];
+          const __half hi = __float2half_rn(v);
+          const float lo = v - __half2float(hi);
+          const uint32_t r = (uint32_t)(dy * 64 + co);
+          const __nv_fp8_storage_t w8 = __nv_cvt_float_to_fp8(v * 8.f, __NV_SATFINITE, __NV_E4M3);
+          const __nv_fp8_storage_t wl8 = __nv_cvt_float_to_fp8(lo * 32768.f, __NV_SATFINITE, __NV_E4M3);
+          const int p8 = ci / RB, k8 = ci % RB;
+          out[(size_t)((0 * NS8 + p8) * KW + dx) * stage + swz(r, k8 / 16) + k8 % 16] = w8;
+          out[(size_t)((1 * NS8 + p8) * KW + dx) * stage + swz(r, k8 / 16) + k8 % 16] = wl8;
+          const int p16 = ci / KC, k16 = ci % KC;
+          memcpy(out.data() + (size_t)((2 * NS8 + p16) * KW + dx) * stage + swz(r, k16 / 8) + (k16 % 8) * 2, &hi, 2);
         }
   return out;
 }
@@ -627,8 +800,10 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
       if ((rc = fold_conv_bn(m, conv, bn, bn_eps, &f)) != NSC_OK) return rc;
       const int kc = i == 3 ? 16 : 32;     // the W = 8 layers run two groups per unit on 16-channel phases
       if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 64 / kc, kc, &max_abs))) != NSC_OK) return rc;
+      if ((rc = upload_bytes(&u.wpk8[i][j], pack_conv_weights_s8(f.w, k, k, kc))) != NSC_OK) return rc;
     }
   u.weights_fit_fp16 = max_abs < 6.0e4f;
+  u.weights_fit_fp8 = max_abs <= 28.f;     // e4m3(w * 2^3) and e4m3(w_lo * 2^15) stay below 448
   return fc_umma_upload_weights(m);
 }
 
@@ -637,9 +812,9 @@ void umma_free(nsc_model* m) {
   cudaFree(u.wpk1); u.wpk1 = nullptr;
   cudaFree(u.w1pk); u.w1pk = nullptr;
   for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 2; ++j) { cudaFree(u.wpk[i][j]); u.wpk[i][j] = nullptr; }
+    for (int j = 0; j < 2; ++j) { cudaFree(u.wpk[i][j]); u.wpk[i][j] = nullptr; cudaFree(u.wpk8[i][j]); u.wpk8[i][j] = nullptr; }
   for (int i = 0; i < 3; ++i)
-    for (int p = 0; p < 2; ++p) { cudaFree(u.buf[i][p]); u.buf[i][p] = nullptr; }
+    for (int p = 0; p < 3; ++p) { cudaFree(u.buf[i][p]); u.buf[i][p] = nullptr; }
   for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
   cudaFree(u.fc_in); u.fc_in = nullptr;
   u.cap = 0;
@@ -657,7 +832,7 @@ static int umma_ensure_workspace(nsc_model* m) {
   cap = (cap + 7) / 8 * 8;
   const size_t bytes = (size_t)cap * kH * 32 * 64 * sizeof(uint16_t);
   for (int i = 0; i < 3; ++i)
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 3; ++p) {   // x16 | exact lo16 | c8 (128 bytes per position: the same size)
       NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[i][p], bytes));
       NSC_CUDA_TRY(cudaMemset(u.buf[i][p], 0, bytes));
     }
@@ -669,20 +844,25 @@ static int umma_ensure_workspace(nsc_model* m) {
   return NSC_OK;
 }
 
+enum : int { kOutLo = 1, kOutC8 = 2, kOutHiLo = kOutLo };   // which companions of the fp16 hi tensor a layer writes
+
 template <class Cfg>
-static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[2], const uint8_t* wpk, const float* bias,
-                            uint16_t* const out[2], float* out_nchw, uint16_t* const res[2], int64_t n, int relu,
-                            cudaStream_t s) {
+static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const uint8_t* wpk, const float* bias,
+                            uint16_t* const out[3], float* out_nchw, uint16_t* const res[2], int64_t n, int relu,
+                            cudaStream_t s, int out_fmt = kOutHiLo) {
   const int64_t groups = ((n + 7) / 8 + Cfg::GP - 1) / Cfg::GP;      // units of GP candidate groups
   CUtensorMap th, tl;
   int rc;
   if ((rc = make_act_tmap(&th, in[0], m->umma.cap / 8, Cfg::W, Cfg::NK * Cfg::KC, Cfg::WB, Cfg::KC, Cfg::GP)) != NSC_OK) return rc;
-  if ((rc = make_act_tmap(&tl, in[1], m->umma.cap / 8, Cfg::W, Cfg::NK * Cfg::KC, Cfg::WB, Cfg::KC, Cfg::GP)) != NSC_OK) return rc;
+  if (Cfg::S8) rc = make_act_tmap(&tl, in[2], m->umma.cap / 8, Cfg::W, 128, Cfg::WB, Cfg::RB, Cfg::GP, 1);
+  else rc = make_act_tmap(&tl, in[1], m->umma.cap / 8, Cfg::W, Cfg::NK * Cfg::KC, Cfg::WB, Cfg::KC, Cfg::GP);
+  if (rc != NSC_OK) return rc;
   UmmaConvArgs a;
   a.wpk = wpk;
   a.bias = bias;
   a.out_hi = out ? out[0] : nullptr;
-  a.out_lo = out ? out[1] : nullptr;
+  a.out_lo = (out && (out_fmt & kOutLo)) ? out[1] : nullptr;
+  a.out_c8 = (out && (out_fmt & kOutC8)) ? reinterpret_cast<uint8_t*>(out[2]) : nullptr;
   a.out_nchw = out_nchw;
   a.res_hi = res ? res[0] : nullptr;
   a.res_lo = res ? res[1] : nullptr;
@@ -691,6 +871,8 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[2], const
   a.relu = relu;
   a.split = m->precision == NSC_PREC_BF16 ? 0 : 1;
   a.stats = nullptr;
+  static const int dbg_skip = getenv("NSC_UMMA_SKIP") ? atoi(getenv("NSC_UMMA_SKIP")) : 0;
+  a.dbg_skip = dbg_skip;
   static const bool want_stats = getenv("NSC_UMMA_STATS") != nullptr;
   static long long* stats_dev = nullptr;
   if (want_stats) {
@@ -765,7 +947,8 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
   return umma_run(m, n, o, s);
 }
 
-static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
+template <bool S8>
+static int umma_run_t(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
   int rc;
   UmmaState& u = m->umma;
   const Fp32Weights& w = m->w32;
@@ -773,33 +956,48 @@ static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
   uint16_t** X = u.buf[0];   // block input (and residual)
   uint16_t** Y = u.buf[1];   // relu(bn(conv_r1))
   uint16_t** N = u.buf[2];   // pooled block output
-  // conv1 + BN + ReLU + pool1 (network.py:44-47,67)
-  if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s)));
-  else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s)));
-  else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s)));
+  // what the consumers of a tensor need besides its fp16 hi part: a block input is a residual (exact lo) and, for
+  // NSC_PREC_SPLIT8, an fp8 correction operand (c8); conv_r1's output only feeds conv_r2
+  constexpr int oX = S8 ? (kOutLo | kOutC8) : kOutHiLo, oY = S8 ? kOutC8 : kOutHiLo;
+  uint8_t* const (*wp)[2] = S8 ? u.wpk8 : u.wpk;
+  // conv1 + BN + ReLU + pool1 (network.py:44-47,67): split-fp16 in every tensor mode (its input is the packed hi/lo image)
+  if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
+  else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
+  else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
   NSC_RUN(dbg_unpack(m, 0, X, 32, n, s));
   // block 0 (3x3 d1, 5x5 d1, pool stride 1)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false>>(m, 2, X, u.wpk[0][0], w.res_b[0][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 1, false>>(m, 3, Y, u.wpk[0][1], w.res_b[0][1], N, nullptr, X, n, 0, s)));
+  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false, 32, 1, S8>>(m, 2, X, wp[0][0], w.res_b[0][0], Y, nullptr, nullptr, n, 1, s, oY)));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 1, false, 32, 1, S8>>(m, 3, Y, wp[0][1], w.res_b[0][1], N, nullptr, X, n, 0, s, oX)));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 1, X, 32, n, s));
   // block 1 (3x3 d1, 5x5 d1, pool stride 2)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false>>(m, 4, X, u.wpk[1][0], w.res_b[1][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 2, false>>(m, 5, Y, u.wpk[1][1], w.res_b[1][1], N, nullptr, X, n, 0, s)));
+  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false, 32, 1, S8>>(m, 4, X, wp[1][0], w.res_b[1][0], Y, nullptr, nullptr, n, 1, s, oY)));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 2, false, 32, 1, S8>>(m, 5, Y, wp[1][1], w.res_b[1][1], N, nullptr, X, n, 0, s, oX)));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 2, X, 16, n, s));
   // block 2 (3x3 d2, 5x5 d1, pool stride 2)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 2, 16, 2, 0, false>>(m, 6, X, u.wpk[2][0], w.res_b[2][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 16, 2, 2, false>>(m, 7, Y, u.wpk[2][1], w.res_b[2][1], N, nullptr, X, n, 0, s)));
+  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 2, 16, 2, 0, false, 32, 1, S8>>(m, 6, X, wp[2][0], w.res_b[2][0], Y, nullptr, nullptr, n, 1, s, oY)));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 16, 2, 2, false, 32, 1, S8>>(m, 7, Y, wp[2][1], w.res_b[2][1], N, nullptr, X, n, 0, s, oX)));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 3, X, 8, n, s));
-  // block 3 (3x3 d4, 5x5 d2, pool stride 2) -> fp32 [B,1280] for fc1
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 4, 0, false, 16, 2>>(m, 8, X, u.wpk[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 4, 2, false, 16, 2>>(m, 9, Y, u.wpk[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s)));
+  // block 3 (3x3 d4, 5x5 d2, pool stride 2) -> packed hi/lo [B][5][4][64] for fc1
+  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 4, 0, false, 16, 2, S8>>(m, 8, X, wp[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s, oY)));
+  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 4, 2, false, 16, 2, S8>>(m, 9, Y, wp[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s, kOutHiLo)));
   NSC_RUN(dbg_unpack(m, 4, N, 4, n, s));
   NSC_RUN(fc_umma_forward(m, N, n, o, s));
 #undef NSC_RUN
   return NSC_OK;
+}
+
+static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
+  if (m->precision == NSC_PREC_SPLIT8) {
+    if (!m->umma.weights_fit_fp8) {
+      set_error("folded convolution weights exceed the range of the fp8 correction terms (|w| > 28); use NSC_PREC_SPLIT16");
+      return NSC_E_STATE;
+    }
+    return umma_run_t<true>(m, n, o, s);
+  }
+  return umma_run_t<false>(m, n, o, s);
 }
 
 }  // namespace nsc

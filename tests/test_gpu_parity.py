@@ -15,7 +15,7 @@ from neusomatic_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL_PROB, TOL_POS = 2e-3, 1e-3
-MODES = [0, 2]      # NSC_PREC_* modes that must meet the parity bar: split-bf16 tensor path, fp32 path
+MODES = [0, 2, 3]   # NSC_PREC_* modes that must meet the parity bar: split-fp16 tensor path, fp32 path, fp8-correction tensor path
 
 
 def _engine(ck, C, precision):

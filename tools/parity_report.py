@@ -13,7 +13,7 @@ for name in ("std_v010", "ens_v010", "std_v014", "ens_v014", "std_wex"):
     x = oracle.assemble_channels(g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], g.get("anns"),
                                  int(ck["coverage_thr"]))
     sd, meta = load_checkpoint(ck)
-    for prec in (0, 1, 2):
+    for prec in (0, 3, 1, 2):
         eng = Engine(sd, x.shape[1], precision=prec)
         o1, o2, o3 = [t.cpu().numpy() for t in eng.forward_f32(torch.from_numpy(x).cuda())[:3]]
         p1, p3 = oracle.softmax(o1), oracle.softmax(o3)
