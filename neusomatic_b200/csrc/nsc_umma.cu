@@ -480,9 +480,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     const bool active = (Cfg::M == 128) || lane < 16;
     constexpr int ITEMS = Cfg::M * 8 / kEpiThreads;
     constexpr int ST = Cfg::POOL == 2 ? 2 : 1;
-    float bias_r[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bias_r[j] = bias_s[half * 32 + j];
     float* stg = reinterpret_cast<float*>(st_hi);           // 32 KB fp32 staging tile
     float* stash_f = reinterpret_cast<float*>(stash);       // [2 cols][5][8 g][64 ch] fp32
     uint32_t u_it = 0;
@@ -542,11 +539,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           if (active) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              float4 v;
-              v.x = __uint_as_float(r[c * 4 + 0]) + bias_r[c * 4 + 0];
-              v.y = __uint_as_float(r[c * 4 + 1]) + bias_r[c * 4 + 1];
-              v.z = __uint_as_float(r[c * 4 + 2]) + bias_r[c * 4 + 2];
-              v.w = __uint_as_float(r[c * 4 + 3]) + bias_r[c * 4 + 3];
+              float4 v = *reinterpret_cast<const float4*>(bias_s + half * 32 + c * 4);   // broadcast read
+              v.x += __uint_as_float(r[c * 4 + 0]);
+              v.y += __uint_as_float(r[c * 4 + 1]);
+              v.z += __uint_as_float(r[c * 4 + 2]);
+              v.w += __uint_as_float(r[c * 4 + 3]);
               if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               *reinterpret_cast<float4*>(stg + row * 64 + ((half * 8 + (c ^ (row & 7))) << 2)) = v;
             }
@@ -608,18 +605,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             };
             const bool do_emit = (ST == 1) ? !(Cfg::STASH && sub == 0 && wl == Cfg::TW - 1) : ((wl & 1) == 0);
             if (do_emit) {
+              // neighbours: the left one comes from the staging tile, from the stash (first column of the second column
+              // block) or is -inf; the right one from the tile or -inf.  Addresses are clamped so that all four loads are
+              // unconditional and in flight together.
+              const float4 ninf = make_float4(__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
+              const float* pl = (wl > 0) ? p0 - Cfg::RPW * 64 : ((Cfg::STASH && sub == 1) ? s1 : p0);
+              const float* pr = (wl < Cfg::TW - 1) ? p0 + Cfg::RPW * 64 : p0;
+              float4 l0 = *reinterpret_cast<const float4*>(pl), l1 = *reinterpret_cast<const float4*>(pl + 32);
+              float4 r0 = *reinterpret_cast<const float4*>(pr), r1 = *reinterpret_cast<const float4*>(pr + 32);
+              if (wl == 0 && !(Cfg::STASH && sub == 1)) { l0 = ninf; l1 = ninf; }
               float4 b0 = m0, b1 = m1;
-              if (wl > 0) {
-                max4(b0, *reinterpret_cast<const float4*>(p0 - Cfg::RPW * 64));
-                max4(b1, *reinterpret_cast<const float4*>(p0 - Cfg::RPW * 64 + 32));
-              } else if (Cfg::STASH && sub == 1) {
-                max4(b0, *reinterpret_cast<const float4*>(s1));
-                max4(b1, *reinterpret_cast<const float4*>(s1 + 32));
-              }
-              if (wl < Cfg::TW - 1) {
-                max4(b0, *reinterpret_cast<const float4*>(p0 + Cfg::RPW * 64));
-                max4(b1, *reinterpret_cast<const float4*>(p0 + Cfg::RPW * 64 + 32));
-              }
+              max4(b0, l0); max4(b1, l1);
+              max4(b0, r0); max4(b1, r1);
               emit(b0, b1, (w0 + wl) / ST);
             }
             // stride-1 pool across the column-block boundary: the last column of block 0 is emitted by block 1
