@@ -39,13 +39,14 @@ extern "C" {
 
 /* arithmetic of the convolution stack (nsc_model_set_precision) */
 #define NSC_PREC_SPLIT16 0    /* tcgen05 implicit GEMM, 16-bit hi+lo operands (fp16), 3 MMAs per MAC, fp32
-                                 accumulate: the parity mode (default)                        */
+                                 accumulate: meets the parity bar                              */
 #define NSC_PREC_SINGLE16 1   /* tcgen05, single-pass 16-bit operands: fast, FAILS the parity bar */
 #define NSC_PREC_SPLIT_BF16 NSC_PREC_SPLIT16   /* historical names */
 #define NSC_PREC_BF16 NSC_PREC_SINGLE16
 #define NSC_PREC_FP32 2       /* fp32 FFMA kernels (CUDA cores): bit-stable reference path    */
 #define NSC_PREC_SPLIT8 3     /* tcgen05: fp16 main product + the two correction products on the fp8 (e4m3) path
-                                 with power-of-two scaling, 2 instruction slots per MAC; meets the parity bar */
+                                 with power-of-two scaling, 2 instruction slots per MAC; meets the parity bar.
+                                 DEFAULT (a checkpoint with |folded w| > 28 falls back to SPLIT16)           */
 
 typedef struct nsc_model nsc_model;
 

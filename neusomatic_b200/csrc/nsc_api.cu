@@ -282,6 +282,9 @@ int nsc_model_finalize(nsc_model* m, float bn_eps) {
   int rc = fp32_upload_weights(m, bn_eps);
   if (rc != NSC_OK) return rc;
   if ((rc = umma_upload_weights(m, bn_eps)) != NSC_OK) return rc;
+  // the default mode needs |folded w| <= 28 for its fp8 correction terms; a checkpoint outside that range silently gets
+  // the all-fp16 split instead (an explicit request for SPLIT8 fails loudly at the first forward)
+  if (m->precision == NSC_PREC_SPLIT8 && !m->precision_explicit && !m->umma.weights_fit_fp8) m->precision = NSC_PREC_SPLIT16;
   NSC_CUDA_TRY(cudaDeviceSynchronize());
   m->finalized = true;
   return NSC_OK;
@@ -295,6 +298,7 @@ int nsc_model_set_precision(nsc_model* m, int precision) {
     return NSC_E_INVALID;
   }
   m->precision = precision;
+  m->precision_explicit = true;
   return NSC_OK;
 }
 

@@ -93,7 +93,8 @@ struct UmmaState {
 struct nsc_model {
   int device = 0;
   int C = 26;
-  int precision = NSC_PREC_SPLIT_BF16;
+  int precision = NSC_PREC_SPLIT8;                     // library default; falls back to SPLIT16 at finalize if |w| > 28
+  bool precision_explicit = false;                     // set through nsc_model_set_precision
   bool finalized = false;
   bool normalize_channels = false;                     // checkpoint["normalize_channels"]
   std::map<std::string, std::vector<float>> params;   // host copy of the state_dict

@@ -297,3 +297,29 @@ def test_large_batch_crosses_default_chunk(precision):
         np.testing.assert_array_equal(a[:2048], b)
         np.testing.assert_array_equal(a[32768:33000], b[32768 - 16 * 2048:33000 - 16 * 2048])
     eng.close()
+
+
+def test_default_mode_is_split8_with_fp16_fallback_for_large_weights():
+    """The library default is NSC_PREC_SPLIT8; a checkpoint whose folded weights leave the range of the fp8 correction
+    terms (|w| > 28) silently gets NSC_PREC_SPLIT16, and an explicit request for SPLIT8 on it fails loudly."""
+    from neusomatic_b200 import Engine
+    from neusomatic_b200._lib import NscError
+    cand = synth.structured_pileups(64, seed=3)
+    x = oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)
+    sd = synth.random_state_dict(26, seed=2)
+    eng = Engine(sd, 26)
+    assert eng.precision == 3
+    eng.close()
+    big = {k: np.array(v, copy=True) for k, v in sd.items()}
+    big["res_layers.1.conv_r2.weight"][3, 5, 2, 2] = 300.0
+    eng = Engine(big, 26)
+    assert eng.precision == 0
+    p = oracle.normalize_state_dict(big)
+    (r1, r2, r3), _ = oracle.forward(p, x, return_internals=True)
+    o1, o2, o3 = [t.cpu().numpy() for t in eng.forward_f32(torch.from_numpy(x).cuda())[:3]]
+    assert np.abs(oracle.softmax(o1) - oracle.softmax(r1)).max() <= TOL_PROB and np.abs(o2 - r2).max() <= TOL_POS * max(1.0, np.abs(r2).max())
+    eng.close()
+    eng = Engine(big, 26, precision=3)
+    with pytest.raises(NscError):
+        eng.forward_f32(torch.from_numpy(x).cuda())
+    eng.close()
