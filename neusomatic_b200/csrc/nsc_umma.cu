@@ -86,8 +86,12 @@ struct ConvCfg {
   static_assert(KC == 32 || KC == 16, "KC");
   static_assert(!S8 || NK * KC == 64, "the fp8 correction layout assumes 64 input channels");
   static_assert(!(STASH && GP != 1), "column-block stash assumes one group per unit");
+  // layers without pooling convert in registers and leave through TMA tensor stores from two double-buffered
+  // [128 rows][128 B] swizzle-128B tiles (x16 and c8 / lo16): no item phase, no LSU stores
+  static constexpr bool TMAOUT = (POOL == 0) && (GP == 1) && (TW == 16);
   static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
-                                 (STASH ? kStashBytes : 0) + 256;
+                                 (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + 256;
+  static_assert(SMEM <= 232448 - 1024, "shared memory budget");
 };
 
 // accumulator slot (64 TMEM columns each) of output row h: rows of one dilation chain are adjacent and
@@ -218,11 +222,21 @@ __device__ __forceinline__ void stg_v8(void* p, const uint32_t* r) {
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// TMA tensor store shared -> global (2-D, bulk-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src_smem), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
 template <class Cfg>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+                 const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1,
                  const UmmaConvArgs args) {
   constexpr int KH = Cfg::KH, KW = Cfg::KW, DIL = Cfg::DIL, W = Cfg::W, NK = Cfg::NK, WS = Cfg::WS;
   extern __shared__ uint8_t smem_raw[];
@@ -253,6 +267,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     fence_barrier_init();
     tma_prefetch_desc(&tmap_hi);
     tma_prefetch_desc(&tmap_lo);
+    if (Cfg::TMAOUT) { tma_prefetch_desc(&tmap_o0); tma_prefetch_desc(&tmap_o1); }
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_slot), 512);
   tc_fence_before_sync();
@@ -482,7 +497,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     constexpr int ST = Cfg::POOL == 2 ? 2 : 1;
     float* stg = reinterpret_cast<float*>(st_hi);           // 32 KB fp32 staging tile
     float* stash_f = reinterpret_cast<float*>(stash);       // [2 cols][5][8 g][64 ch] fp32
-    uint32_t u_it = 0;
+    uint32_t u_it = 0, rowc = 0;
     long long t_epi = 0, t_full = 0;
     uint2 res_h[ITEMS][2], res_l[ITEMS][2];     // residual operands of the NEXT row to be processed
     // element offset of operand row rr (column wl, group-in-unit, candidate) of image row h in a packed tensor of width Wt
@@ -535,6 +550,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             tmem_ld_wait();
           }
           if (idx == kH - 1) { tc_fence_before_sync(); mbar_arrive(all_free + 8 * (u_it & 1)); }
+          if (Cfg::TMAOUT) {
+            // ---- no pooling: convert this thread's row (32 channels) in registers, write it into the swizzle-128B output
+            // tiles of this image row (tile 0 = x16, tile 1 = c8 or the fp16 lo part) and let one thread hand them to TMA
+            uint8_t* t0 = st_hi + (rowc & 1) * kStageBytes;
+            uint8_t* t1 = t0 + 16384;
+            const uint32_t sw = row & 7, rbase = row * 128;
+            uint32_t e8[8], el8[8];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {          // 8 channels = one 16-byte chunk of the x16 row
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j] = __uint_as_float(r[c * 8 + j]) + bias_s[half * 32 + c * 8 + j];
+                if (args.relu) v[j] = fmaxf(v[j], 0.f);
+              }
+              uint4 hq, lq;
+              split8(v, hq, lq);
+              *reinterpret_cast<uint4*>(t0 + rbase + (((half * 4 + c) ^ sw) << 4)) = hq;
+              if (args.out_c8 == nullptr) {
+                *reinterpret_cast<uint4*>(t1 + rbase + (((half * 4 + c) ^ sw) << 4)) = lq;
+              } else {
+                float hf[8];
+                const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&hq.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&hq.y));
+                const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hq.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&hq.w));
+                hf[0] = a0.x; hf[1] = a0.y; hf[2] = a1.x; hf[3] = a1.y; hf[4] = a2.x; hf[5] = a2.y; hf[6] = a3.x; hf[7] = a3.y;
+                e8[2 * c] = e4m3x4(v[0], v[1], v[2], v[3]);
+                e8[2 * c + 1] = e4m3x4(v[4], v[5], v[6], v[7]);
+                el8[2 * c] = e4m3x4((v[0] - hf[0]) * kXlo8Scale, (v[1] - hf[1]) * kXlo8Scale, (v[2] - hf[2]) * kXlo8Scale, (v[3] - hf[3]) * kXlo8Scale);
+                el8[2 * c + 1] = e4m3x4((v[4] - hf[4]) * kXlo8Scale, (v[5] - hf[5]) * kXlo8Scale, (v[6] - hf[6]) * kXlo8Scale, (v[7] - hf[7]) * kXlo8Scale);
+              }
+            }
+            if (args.out_c8 != nullptr) {          // c8 row: bytes [half*32, +32) = e4m3(x), bytes [64 + half*32, +32) = e4m3(x_lo * 2^12)
+              *reinterpret_cast<uint4*>(t1 + rbase + (((half * 2 + 0) ^ sw) << 4)) = make_uint4(e8[0], e8[1], e8[2], e8[3]);
+              *reinterpret_cast<uint4*>(t1 + rbase + (((half * 2 + 1) ^ sw) << 4)) = make_uint4(e8[4], e8[5], e8[6], e8[7]);
+              *reinterpret_cast<uint4*>(t1 + rbase + (((4 + half * 2 + 0) ^ sw) << 4)) = make_uint4(el8[0], el8[1], el8[2], el8[3]);
+              *reinterpret_cast<uint4*>(t1 + rbase + (((4 + half * 2 + 1) ^ sw) << 4)) = make_uint4(el8[4], el8[5], el8[6], el8[7]);
+            }
+            fence_proxy_async_smem();
+            // the stores of the previous image row must have finished reading their tiles before anyone passes the barrier:
+            // those are the tiles the next row writes
+            if (et == 0) bulk_wait_group_read0();
+            epi_bar();
+            if (et == 0) {
+              const int prow0 = ((grp * kH + h) * W + w0) * 8;
+              tma_store_2d(&tmap_o0, smem_u32(t0), 0, prow0);
+              tma_store_2d(&tmap_o1, smem_u32(t1), 0, prow0);
+              bulk_commit_group();
+            }
+            ++rowc;
+            continue;
+          }
           // ---- phase A: this thread's row, 32 channels
           if (active) {
 #pragma unroll
@@ -631,6 +697,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
         t_epi += clock64() - t_c;
       }
+    if (Cfg::TMAOUT && et == 0) bulk_wait_group0();     // the output tiles must outlive the last TMA stores
     if (args.stats && et == 0) {
       long long* st = args.stats + (size_t)blockIdx.x * 8;
       st[5] = t_epi; st[6] = t_full;
@@ -718,6 +785,26 @@ static int make_act_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int
                       KC * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return NSC_E_CUDA; }
+  return NSC_OK;
+}
+
+// Packed output tensor seen as [rows][128 bytes] (x16 / lo16: 64 fp16 per position, c8: 128 bytes per position): box of
+// 128 position rows = the 16 columns x 8 candidates of one unit and image row, swizzle-128B in shared memory
+static int make_out_tmap(CUtensorMap* tm, void* base, int64_t rows, int elem_bytes) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    NSC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &q));
+    if (!encode) { set_error("cuTensorMapEncodeTiled is not available"); return NSC_E_CUDA; }
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)(128 / elem_bytes), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides,
+                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return NSC_E_CUDA; }
   return NSC_OK;
 }
 
@@ -877,6 +964,14 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
     NSC_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, 148 * 8 * sizeof(long long), s));
     a.stats = stats_dev;
   }
+  CUtensorMap to0 = th, to1 = th;   // placeholders for the layers that store through the LSU
+  if (Cfg::TMAOUT) {
+    const int64_t rows = m->umma.cap * kH * Cfg::W;
+    if ((rc = make_out_tmap(&to0, a.out_hi, rows, 2)) != NSC_OK) return rc;
+    if (a.out_c8 != nullptr) rc = make_out_tmap(&to1, a.out_c8, rows, 1);
+    else rc = make_out_tmap(&to1, a.out_lo, rows, 2);
+    if (rc != NSC_OK) return rc;
+  }
   auto kern = conv_umma_kernel<Cfg>;
   static bool attr_set = false;   // one static per template instantiation
   if (!attr_set) {
@@ -886,7 +981,7 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
   const int grid = (int)std::min<int64_t>(groups, m->umma.num_sms);
   {
     ProfScope prof(m, slot, s);
-    kern<<<grid, kUmmaThreads, Cfg::SMEM, s>>>(th, tl, a);
+    kern<<<grid, kUmmaThreads, Cfg::SMEM, s>>>(th, tl, to0, to1, a);
   }
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches++;
