@@ -415,10 +415,13 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
   cudaEvent_t* in_free = &m->hevent[2];
   cudaEvent_t* out_ready = &m->hevent[4];
   cudaEvent_t* out_free = &m->hevent[6];
-  int64_t it = 0;
-  for (int64_t i = 0; i < B; i += cap, ++it) {
+  // the first slice is small: its host-to-device copy is the only one no kernel overlaps
+  const int64_t first = std::min<int64_t>(cap, 4096);
+  int64_t it = 0, n_prev = 0;
+  for (int64_t i = 0; i < B; i += n_prev, ++it) {
     const int slot = (int)(it & 1);
-    const int64_t n = std::min<int64_t>(cap, B - i);
+    const int64_t n = std::min<int64_t>(it == 0 ? first : cap, B - i);
+    n_prev = n;
     char* din = (char*)m->hstage_in[slot];
     char* dmeta = din + ((in_per * cap + 255) / 256) * 256;
     char* dann = dmeta + ((meta_per * cap + 255) / 256) * 256;
