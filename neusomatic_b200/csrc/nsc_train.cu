@@ -249,16 +249,20 @@ __global__ void store_channel_sums_kernel(const double* __restrict__ sums, float
 }
 
 // weight gradient partial sums: part[split][tap][ci][co] += x[b, ci, h + dy*d - ph, w + dx*d - pw] * du[b, co, h, w]
-// One block = (kernel row dy, batch split): the sample is staged once in shared memory and serves the KW taps of the row.
+// One block = (kernel row dy, batch split): the sample is staged once in shared memory, position-major ([5*W][64 + 4 pad]
+// for both tensors), so a thread's 4 input channels / 4 output channels of one position are ONE 16-byte load each:
+// 1 + KW loads per 16 KW FMAs.  The summation order (sample, row, column) is fixed: results are deterministic.
+constexpr int kWgLd = 68;   // floats per staged position (64 channels + 4: keeps 16-byte alignment, spreads the banks)
 template <int W, int KW>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ part, int N, int Cin, int KH, int dil) {
   const int dy = blockIdx.x, split = blockIdx.y;
   const int ph = dil * (KH - 1) / 2, pw = dil * (KW - 1) / 2;
   const int oy = dy * dil - ph;
-  extern __shared__ float sm[];
-  float* xs = sm;                     // [64][5][W]  (channels >= Cin zero)
-  float* ds = sm + 64 * kH * W;       // [64][5][W]
+  constexpr int P = kH * W;
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;                     // [5*W][68]  (channels >= Cin zero)
+  float* ds = sm + P * kWgLd;         // [5*W][68]
   const int tid = threadIdx.x, cig = tid & 15, cog = tid >> 4;   // 4 input channels x 4 output channels per thread
   float acc[KW][4][4];
 #pragma unroll
@@ -271,29 +275,33 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* _
   const int b0 = split * per, b1 = min(N, b0 + per);
   for (int b = b0; b < b1; ++b) {
     __syncthreads();
-    for (int i = tid; i < 64 * kH * W; i += 256) {
-      const int ci = i / (kH * W);
-      xs[i] = ci < Cin ? x[((size_t)b * Cin + ci) * (kH * W) + i % (kH * W)] : 0.f;
-      ds[i] = du[(size_t)b * 64 * (kH * W) + i];
+    for (int i = tid; i < 64 * P; i += 256) {
+      const int c = i / P, pos = i - c * P;
+      xs[pos * kWgLd + c] = c < Cin ? x[((size_t)b * Cin + c) * P + pos] : 0.f;
+      ds[pos * kWgLd + c] = du[(size_t)b * 64 * P + i];
     }
     __syncthreads();
     for (int h = 0; h < kH; ++h) {
       const int hh = h + oy;
       if (hh < 0 || hh >= kH) continue;
+      const float* xrow = xs + (hh * W) * kWgLd + cig * 4;
+      const float* drow = ds + (h * W) * kWgLd + cog * 4;
+#pragma unroll 4
       for (int w = 0; w < W; ++w) {
-        float dv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dv[j] = ds[((cog * 4 + j) * kH + h) * W + w];
+        const float4 dv = *reinterpret_cast<const float4*>(drow + w * kWgLd);
 #pragma unroll
         for (int t = 0; t < KW; ++t) {
           const int ww = w + t * dil - pw;
           if (ww < 0 || ww >= W) continue;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float xv = xs[((cig * 4 + i) * kH + hh) * W + ww];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(xv, dv[j], acc[t][i][j]);
-          }
+          const float4 xv = *reinterpret_cast<const float4*>(xrow + ww * kWgLd);
+          acc[t][0][0] = fmaf(xv.x, dv.x, acc[t][0][0]); acc[t][0][1] = fmaf(xv.x, dv.y, acc[t][0][1]);
+          acc[t][0][2] = fmaf(xv.x, dv.z, acc[t][0][2]); acc[t][0][3] = fmaf(xv.x, dv.w, acc[t][0][3]);
+          acc[t][1][0] = fmaf(xv.y, dv.x, acc[t][1][0]); acc[t][1][1] = fmaf(xv.y, dv.y, acc[t][1][1]);
+          acc[t][1][2] = fmaf(xv.y, dv.z, acc[t][1][2]); acc[t][1][3] = fmaf(xv.y, dv.w, acc[t][1][3]);
+          acc[t][2][0] = fmaf(xv.z, dv.x, acc[t][2][0]); acc[t][2][1] = fmaf(xv.z, dv.y, acc[t][2][1]);
+          acc[t][2][2] = fmaf(xv.z, dv.z, acc[t][2][2]); acc[t][2][3] = fmaf(xv.z, dv.w, acc[t][2][3]);
+          acc[t][3][0] = fmaf(xv.w, dv.x, acc[t][3][0]); acc[t][3][1] = fmaf(xv.w, dv.y, acc[t][3][1]);
+          acc[t][3][2] = fmaf(xv.w, dv.z, acc[t][3][2]); acc[t][3][3] = fmaf(xv.w, dv.w, acc[t][3][3]);
         }
       }
     }
@@ -455,7 +463,7 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
 
 static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s) {
   const int T = L.k_h * L.k_w;
-  const size_t smem = (size_t)2 * 64 * kH * L.W * sizeof(float);
+  const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
 #define NSC_WG(WW, KK)                                                                                              \
   do {                                                                                                              \
