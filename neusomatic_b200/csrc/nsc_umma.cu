@@ -233,6 +233,48 @@ __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
+// One weight stage's MMAs for the input rows in `rows`: for every input row the kernel rows whose output row is in range
+// form a chain of adjacent accumulator slots; the chain is clipped to slots [slot_lo, slot_hi] and issued as N-concatenated
+// instructions of up to four taps.  MODE 0: accumulate; 1: the first K-step overwrites (first touch of the accumulators);
+// 2: the first K-step rescales the accumulator (D = A*B + D * 2^-15).  Everything but the operand bases is compile time.
+template <class Cfg, int MODE, bool F8>
+__device__ __forceinline__ void issue_rows(uint32_t acc0, uint32_t a_base, uint32_t w_base, int wl0, uint32_t rows, int slot_lo,
+                                           int slot_hi) {
+  constexpr int KH = Cfg::KH, DIL = Cfg::DIL;
+#pragma unroll
+  for (int h_in = 0; h_in < kH; ++h_in) {
+    if (!((rows >> h_in) & 1u)) continue;
+    // kernel rows dy with output row h_out = h_in - dy*DIL + PH inside [0,5): a contiguous range, slots ascending with dy
+    int dy_lo = KH, dy_hi = -1;
+#pragma unroll
+    for (int dy = 0; dy < KH; ++dy) {
+      const int h_out = h_in - dy * DIL + Cfg::PH;
+      if (h_out < 0 || h_out >= kH) continue;
+      const int slot = acc_slot<DIL>(h_out);
+      if (slot < slot_lo || slot > slot_hi) continue;
+      dy_lo = dy < dy_lo ? dy : dy_lo;
+      dy_hi = dy;
+    }
+    if (dy_hi < 0) continue;
+    const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
+#pragma unroll
+    for (int kk = 0; kk < Cfg::NKK; ++kk) {
+      const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
+      for (int dy = dy_lo, n = 0; dy <= dy_hi; dy += n) {
+        const int rem = dy_hi - dy + 1;
+        n = rem == 5 ? 3 : (rem < 4 ? rem : 4);   // N = 64 n <= 256; 5 rows as 192 + 128
+        const int h_out = h_in - dy * DIL + Cfg::PH;
+        const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
+        const uint32_t d = acc0 + acc_slot<DIL>(h_out) * 64;
+        const uint32_t idesc = make_idesc_f16(Cfg::M, 64 * n, 0);
+        if (MODE == 2 && kk == 0) umma_f16_scaled<15>(d, adesc, bdesc, idesc);
+        else if (F8) umma_f8(d, adesc, bdesc, idesc, (MODE == 1 && kk == 0) ? 0u : 1u);
+        else umma_f16(d, adesc, bdesc, idesc, (MODE == 1 && kk == 0) ? 0u : 1u);
+      }
+    }
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
@@ -338,12 +380,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
       auto run_unit = [&](auto par_tag) {
           constexpr uint32_t PAR = decltype(par_tag)::value ? 1u : 0u;
           const uint32_t acc0 = tmem + PAR * 192;                 // accumulator window of this unit
-          constexpr uint32_t shared_slots = PAR ? 0x03u : 0x18u;  // slots shared with the previous unit
+          constexpr uint32_t COVER = cover_set<KH, DIL>();        // input rows with disjoint, complete output-row sets
+          static_assert(COVER != 0, "no disjoint cover of the output rows");
           t_c = clock64();
           if (u_it >= 2) mbar_wait(all_free + 8 * (u_it & 1), ((u_it >> 1) - 1) & 1);   // unit u-2 fully drained
           t_acc += clock64() - t_c;
           tc_fence_after_sync();
-          uint32_t touched = 0;
           bool first_stage = true;
           // one phase; F8 is a compile-time tag so that the fp8 and fp16 phases are separate instruction streams (a
           // runtime flag made ptxas emit every MMA twice, predicated, and the nullified twin still costs an issue slot)
@@ -367,96 +409,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 const int wl0 = dx * DIL - Cfg::PW + Cfg::HALO;   // first box column of this kernel column
                 if (args.dbg_skip & (f8 ? 1 : 2)) {
                 } else if (first_stage) {
-                  // first touch of every accumulator: single-tap MMAs with explicit accumulate flags; the
-                  // accumulators not shared with the previous unit go first, the two shared ones after the
-                  // epilogue has drained them
-#pragma unroll
-                  for (int pass = 0; pass < 2; ++pass) {
-                    if (pass == 1 && u_it > 0) {
-                      t_c = clock64();
-                      mbar_wait(shared_free, (u_it - 1) & 1);
-                      t_acc += clock64() - t_c;
-                      tc_fence_after_sync();
-                    }
-#pragma unroll
-                    for (int h_in = 0; h_in < kH; ++h_in) {
-                      const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
-#pragma unroll
-                      for (int dy = 0; dy < KH; ++dy) {
-                        const int h_out = h_in - dy * DIL + Cfg::PH;
-                        if (h_out < 0 || h_out >= kH) continue;
-                        const int slot = acc_slot<DIL>(h_out);
-                        if ((int)((shared_slots >> slot) & 1u) != pass) continue;
-#pragma unroll
-                        for (int kk = 0; kk < Cfg::NKK; ++kk) {
-                          const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                          const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                          if (f8) umma_f8(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
-                          else umma_f16(acc0 + slot * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64, 0), (touched >> h_out) & 1);
-                          touched |= 1u << h_out;
-                        }
-                      }
-                    }
+                  // first touch of every accumulator (accumulate flag off on the first K-step of the cover rows, whose
+                  // output-row sets are disjoint and complete); the accumulators not shared with the previous unit go
+                  // first, the two shared ones after the epilogue has drained them
+                  constexpr int NS_LO = PAR ? 2 : 0, NS_HI = PAR ? 4 : 2, SH_LO = PAR ? 0 : 3, SH_HI = PAR ? 1 : 4;
+                  issue_rows<Cfg, 1, f8>(acc0, a_base, w_base, wl0, COVER, NS_LO, NS_HI);
+                  issue_rows<Cfg, 0, f8>(acc0, a_base, w_base, wl0, 0x1fu & ~COVER, NS_LO, NS_HI);
+                  if (u_it > 0) {
+                    t_c = clock64();
+                    mbar_wait(shared_free, (u_it - 1) & 1);
+                    t_acc += clock64() - t_c;
+                    tc_fence_after_sync();
                   }
+                  issue_rows<Cfg, 1, f8>(acc0, a_base, w_base, wl0, COVER, SH_LO, SH_HI);
+                  issue_rows<Cfg, 0, f8>(acc0, a_base, w_base, wl0, 0x1fu & ~COVER, SH_LO, SH_HI);
                 } else if (Cfg::S8 && !f8 && ph == Cfg::NPH8 && dx == 0) {
-                  // first fp16 stage: the first fp16 MMA on each accumulator rescales the fp8 sums (D = A*B + D * 2^-15).
-                  // The input rows of cover_set() reach disjoint sets of output rows that together are all five, so
-                  // their first K-step carries the scale on whole concatenated instructions; everything else is plain.
-                  constexpr uint32_t COVER = cover_set<KH, DIL>();
-                  static_assert(COVER != 0, "no disjoint cover of the output rows");
-#pragma unroll
-                  for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-                    for (int h_in = 0; h_in < kH; ++h_in) {
-                      if ((int)((COVER >> h_in) & 1u) == pass) continue;     // pass 0: the cover rows, pass 1: the rest
-                      int dy_lo = KH, dy_hi = -1;
-#pragma unroll
-                      for (int dy = 0; dy < KH; ++dy) {
-                        const int h_out = h_in - dy * DIL + Cfg::PH;
-                        if (h_out >= 0 && h_out < kH) { dy_lo = dy < dy_lo ? dy : dy_lo; dy_hi = dy; }
-                      }
-                      if (dy_hi < 0) continue;
-                      const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
-#pragma unroll
-                      for (int kk = 0; kk < Cfg::NKK; ++kk) {
-                        const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                        for (int dy = dy_lo, n = 0; dy <= dy_hi; dy += n) {
-                          const int rem = dy_hi - dy + 1;
-                          n = rem == 5 ? 3 : (rem < 4 ? rem : 4);
-                          const int h_out = h_in - dy * DIL + Cfg::PH;
-                          const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                          const uint32_t d = acc0 + acc_slot<DIL>(h_out) * 64;
-                          if (pass == 0 && kk == 0) umma_f16_scaled<15>(d, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0));
-                          else umma_f16(d, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
-                        }
-                      }
-                    }
-                  }
+                  // first fp16 stage: the first fp16 MMA on each accumulator rescales the fp8 sums (D = A*B + D * 2^-15):
+                  // again the first K-step of the cover rows, on whole concatenated instructions
+                  issue_rows<Cfg, 2, false>(acc0, a_base, w_base, wl0, COVER, 0, 4);
+                  issue_rows<Cfg, 0, false>(acc0, a_base, w_base, wl0, 0x1fu & ~COVER, 0, 4);
                 } else {
-#pragma unroll
-                  for (int h_in = 0; h_in < kH; ++h_in) {
-                    // kernel rows dy with output row h_out = h_in - dy*DIL + PH inside [0,5): a contiguous range
-                    int dy_lo = KH, dy_hi = -1;
-#pragma unroll
-                    for (int dy = 0; dy < KH; ++dy) {
-                      const int h_out = h_in - dy * DIL + Cfg::PH;
-                      if (h_out >= 0 && h_out < kH) { dy_lo = dy < dy_lo ? dy : dy_lo; dy_hi = dy; }
-                    }
-                    if (dy_hi < 0) continue;
-                    const uint32_t a_row = a_base + (uint32_t)((h_in * Cfg::WB + wl0) * Cfg::RPW) * Cfg::RB;
-#pragma unroll
-                    for (int kk = 0; kk < Cfg::NKK; ++kk) {
-                      const uint64_t adesc = make_smem_desc(a_row + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                      for (int dy = dy_lo, n = 0; dy <= dy_hi; dy += n) {
-                        const int rem = dy_hi - dy + 1;
-                        n = rem == 5 ? 3 : (rem < 4 ? rem : 4);   // N = 64 n <= 256; 5 rows as 192 + 128
-                        const int h_out = h_in - dy * DIL + Cfg::PH;
-                        const uint64_t bdesc = make_smem_desc(w_base + dy * 64 * Cfg::RB + kk * 32, 16, Cfg::ATOM, Cfg::SWZ);
-                        if (f8) umma_f8(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
-                        else umma_f16(acc0 + acc_slot<DIL>(h_out) * 64, adesc, bdesc, make_idesc_f16(Cfg::M, 64 * n, 0), 1u);
-                      }
-                    }
-                  }
+                  issue_rows<Cfg, 0, f8>(acc0, a_base, w_base, wl0, 0x1fu, 0, 4);
                 }
                 umma_commit(w_empty + 8 * st);
                 first_stage = false;
