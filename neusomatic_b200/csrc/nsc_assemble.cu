@@ -66,13 +66,30 @@ assemble_pack_kernel(const uint8_t* __restrict__ mat, const int32_t* __restrict_
                      double thr, int C, int Cpad, int normalize, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B) {
   __shared__ uint32_t rows[8][184];      // the 8 candidates' row h: 32 x 23 bytes each
   __shared__ int mx_s[8];
+  // channels >= 24 (coverage, annotations, zero padding) do not depend on the position: their fp16 hi / lo halves are
+  // computed once per candidate and block and copied by every position
+  __shared__ __align__(16) uint16_t cst_hi[8][128], cst_lo[8][128];
   const int grp = blockIdx.x / kH, h = blockIdx.x % kH;
   const int tid = threadIdx.x, g = tid & 7, w = tid >> 3;
   const int64_t b = (int64_t)grp * 8 + g;
+  const int na = C - kBaseCh;
   if (tid < 8) mx_s[tid] = 0;
   for (int i = tid; i < 8 * 184; i += 256) {
     const int64_t bb = (int64_t)grp * 8 + i / 184;
     rows[i / 184][i % 184] = bb < B ? reinterpret_cast<const uint32_t*>(mat + (bb * kH + h) * (kW * kStoredCh))[i % 184] : 0u;
+  }
+  for (int i = tid; i < 8 * (Cpad - 24); i += 256) {
+    const int gg = i / (Cpad - 24), c = 24 + i % (Cpad - 24);
+    const int64_t bb = (int64_t)grp * 8 + gg;
+    float f = 0.f;
+    if (bb < B && c < C) {
+      if (c < kBaseCh) f = __fdiv_rn((float)(fmin((double)meta[bb * 3 + (c - 23)], thr) / thr * 255.0), 255.f);
+      else f = __fdiv_rn(anns255 ? anns255[bb * na + (c - kBaseCh)] : 0.f, 255.f);
+    }
+    const __half hh = __float2half_rn(f);
+    const __half ll = __float2half_rn(f - __half2float(hh));
+    cst_hi[gg][c] = *reinterpret_cast<const uint16_t*>(&hh);
+    cst_lo[gg][c] = *reinterpret_cast<const uint16_t*>(&ll);
   }
   __syncthreads();
   {   // np.max(matrix[:, :, 0]) per candidate (dataloader.py:390)
@@ -82,37 +99,29 @@ assemble_pack_kernel(const uint8_t* __restrict__ mat, const int32_t* __restrict_
     atomicMax(&mx_s[g], v);
   }
   __syncthreads();
-  const uint8_t* px = reinterpret_cast<const uint8_t*>(rows[g]) + w * kStoredCh;
-  const int mx = mx_s[g];
-  int center = 0;
-  float ch24 = 0.f, ch25 = 0.f;
-  if (b < B) {
-    center = meta[b * 3 + 0];
-    ch24 = __fdiv_rn((float)(fmin((double)meta[b * 3 + 1], thr) / thr * 255.0), 255.f);
-    ch25 = __fdiv_rn((float)(fmin((double)meta[b * 3 + 2], thr) / thr * 255.0), 255.f);
-  }
-  const int na = C - kBaseCh;
-  const size_t row_off = ((((size_t)grp * kH + h) * kW + w) * 8 + g) * Cpad;
-  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+  // The block's 256 positions (w, g) are 256 consecutive rows of Cpad channels in both output tensors.  Work items are
+  // (row, 8-channel chunk) with the chunk index fastest, so consecutive lanes write consecutive 16-byte pieces.
+  const size_t blk_off = (((size_t)grp * kH + h) * kW) * 8 * Cpad;
+  // channels 0..23: the stored bytes and the centre marker
+  for (int it = tid; it < 256 * 3; it += 256) {
+    const int row = it / 3, c0 = (it - row * 3) * 8;
+    const int gg = row & 7, ww = row >> 3;
+    const int64_t bb = (int64_t)grp * 8 + gg;
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(rows[gg]) + ww * kStoredCh;
+    const int center = bb < B ? meta[bb * 3 + 0] : -1;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       float f = 0.f;
-      if (b < B && c < C) {
+      if (bb < B) {
         if (c < kStoredCh) {
           f = (float)px[c];
           if (normalize && c >= 3) f = (float)((double)px[c] * ((double)px[(c & 1) ? 1 : 2] / 255.0));
           f = __fdiv_rn(f, 255.f);
           if (c < 3) f = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
-        } else if (c == 23) {
-          f = (w == center) ? __fdiv_rn((float)mx, 255.f) : 0.f;
-        } else if (c == 24) {
-          f = ch24;
-        } else if (c == 25) {
-          f = ch25;
         } else {
-          f = __fdiv_rn(anns255 ? anns255[b * na + (c - kBaseCh)] : 0.f, 255.f);
+          f = (ww == center) ? __fdiv_rn((float)mx_s[gg], 255.f) : 0.f;
         }
       }
       v[j] = f;
@@ -126,8 +135,15 @@ assemble_pack_kernel(const uint8_t* __restrict__ mat, const int32_t* __restrict_
       ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
       pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    *reinterpret_cast<uint4*>(hi + row_off + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    *reinterpret_cast<uint4*>(lo + row_off + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+  // channels 24..Cpad-1: position independent
+  const int nc = (Cpad - 24) / 8;
+  for (int it = tid; it < 256 * nc; it += 256) {
+    const int row = it / nc, c0 = 24 + (it - row * nc) * 8;
+    *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_hi[row & 7][c0]);
+    *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_lo[row & 7][c0]);
   }
 }
 
