@@ -59,24 +59,30 @@ assemble_kernel(const uint8_t* __restrict__ mat,     // [B,5,32,23]
 }
 
 // Same arithmetic, fused with the hi/lo fp16 split and the packed layout of the tensor path
-// (nsc_umma.cu): uint8 [B,5,32,23] -> act[group][h][w][g][Cpad] hi / lo.  One block per (group, h);
-// thread = (w, g) writes the Cpad channels of one position.
+// (nsc_umma.cu): uint8 [B,5,32,23] -> act[group][h][w][g][Cpad] hi / lo.  One block per group of 8 candidates: their
+// 8 x 3680 bytes are staged once, the per-candidate maximum and the position-independent channels are computed once,
+// then the five image rows are written: work items are (position row, 8-channel chunk) with the chunk fastest, so
+// consecutive lanes write consecutive 16-byte pieces of rows that are themselves consecutive in memory.
 __global__ void __launch_bounds__(256)
 assemble_pack_kernel(const uint8_t* __restrict__ mat, const int32_t* __restrict__ meta, const float* __restrict__ anns255,
                      double thr, int C, int Cpad, int normalize, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B) {
-  __shared__ uint32_t rows[8][184];      // the 8 candidates' row h: 32 x 23 bytes each
-  __shared__ int mx_s[8];
-  // channels >= 24 (coverage, annotations, zero padding) do not depend on the position: their fp16 hi / lo halves are
-  // computed once per candidate and block and copied by every position
+  constexpr int CAND_WORDS = kH * kW * kStoredCh / 4;   // 920
+  __shared__ uint32_t cand[8][CAND_WORDS];               // the 8 candidates' stored matrices
+  __shared__ int mx_s[8], center_s[8];
+  // channels >= 24 (coverage, annotations, zero padding) do not depend on the position
   __shared__ __align__(16) uint16_t cst_hi[8][128], cst_lo[8][128];
-  const int grp = blockIdx.x / kH, h = blockIdx.x % kH;
-  const int tid = threadIdx.x, g = tid & 7, w = tid >> 3;
-  const int64_t b = (int64_t)grp * 8 + g;
+  const int grp = blockIdx.x;
+  const int tid = threadIdx.x;
   const int na = C - kBaseCh;
-  if (tid < 8) mx_s[tid] = 0;
-  for (int i = tid; i < 8 * 184; i += 256) {
-    const int64_t bb = (int64_t)grp * 8 + i / 184;
-    rows[i / 184][i % 184] = bb < B ? reinterpret_cast<const uint32_t*>(mat + (bb * kH + h) * (kW * kStoredCh))[i % 184] : 0u;
+  if (tid < 8) {
+    const int64_t bb = (int64_t)grp * 8 + tid;
+    mx_s[tid] = 0;
+    center_s[tid] = bb < B ? meta[bb * 3 + 0] : -1;
+  }
+  for (int i = tid; i < 8 * CAND_WORDS; i += 256) {
+    const int gg = i / CAND_WORDS, k = i - gg * CAND_WORDS;
+    const int64_t bb = (int64_t)grp * 8 + gg;
+    cand[gg][k] = bb < B ? reinterpret_cast<const uint32_t*>(mat + bb * (kH * kW * kStoredCh))[k] : 0u;
   }
   for (int i = tid; i < 8 * (Cpad - 24); i += 256) {
     const int gg = i / (Cpad - 24), c = 24 + i % (Cpad - 24);
@@ -92,58 +98,61 @@ assemble_pack_kernel(const uint8_t* __restrict__ mat, const int32_t* __restrict_
     cst_lo[gg][c] = *reinterpret_cast<const uint16_t*>(&ll);
   }
   __syncthreads();
-  {   // np.max(matrix[:, :, 0]) per candidate (dataloader.py:390)
+  // np.max(matrix[:, :, 0]) per candidate (dataloader.py:390): 160 positions each, 32 threads per candidate
+  {
+    const int gg = tid >> 5, l = tid & 31;
+    const uint8_t* cb = reinterpret_cast<const uint8_t*>(cand[gg]);
     int v = 0;
-    if (b < B)
-      for (int hh = 0; hh < kH; ++hh) v = max(v, (int)mat[((b * kH + hh) * kW + w) * kStoredCh]);
-    atomicMax(&mx_s[g], v);
+    for (int p = l; p < kH * kW; p += 32) v = max(v, (int)cb[p * kStoredCh]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if (l == 0) mx_s[gg] = v;
   }
   __syncthreads();
-  // The block's 256 positions (w, g) are 256 consecutive rows of Cpad channels in both output tensors.  Work items are
-  // (row, 8-channel chunk) with the chunk index fastest, so consecutive lanes write consecutive 16-byte pieces.
-  const size_t blk_off = (((size_t)grp * kH + h) * kW) * 8 * Cpad;
-  // channels 0..23: the stored bytes and the centre marker
-  for (int it = tid; it < 256 * 3; it += 256) {
-    const int row = it / 3, c0 = (it - row * 3) * 8;
-    const int gg = row & 7, ww = row >> 3;
-    const int64_t bb = (int64_t)grp * 8 + gg;
-    const uint8_t* px = reinterpret_cast<const uint8_t*>(rows[gg]) + ww * kStoredCh;
-    const int center = bb < B ? meta[bb * 3 + 0] : -1;
-    float v[8];
+  for (int h = 0; h < kH; ++h) {
+    const size_t blk_off = (((size_t)grp * kH + h) * kW) * 8 * Cpad;
+    // channels 0..23: the stored bytes and the centre marker
+    for (int it = tid; it < 256 * 3; it += 256) {
+      const int row = it / 3, c0 = (it - row * 3) * 8;
+      const int gg = row & 7, ww = row >> 3;
+      const bool valid = (int64_t)grp * 8 + gg < B;
+      const uint8_t* px = reinterpret_cast<const uint8_t*>(cand[gg]) + (h * kW + ww) * kStoredCh;
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      float f = 0.f;
-      if (bb < B) {
-        if (c < kStoredCh) {
-          f = (float)px[c];
-          if (normalize && c >= 3) f = (float)((double)px[c] * ((double)px[(c & 1) ? 1 : 2] / 255.0));
-          f = __fdiv_rn(f, 255.f);
-          if (c < 3) f = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
-        } else {
-          f = (ww == center) ? __fdiv_rn((float)mx_s[gg], 255.f) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float f = 0.f;
+        if (valid) {
+          if (c < kStoredCh) {
+            f = (float)px[c];
+            if (normalize && c >= 3) f = (float)((double)px[c] * ((double)px[(c & 1) ? 1 : 2] / 255.0));
+            f = __fdiv_rn(f, 255.f);
+            if (c < 3) f = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
+          } else {
+            f = (ww == center_s[gg]) ? __fdiv_rn((float)mx_s[gg], 255.f) : 0.f;
+          }
         }
+        v[j] = f;
       }
-      v[j] = f;
-    }
-    uint32_t ph[4], pl[4];
+      uint32_t ph[4], pl[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-      ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
-      pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+      for (int j = 0; j < 4; ++j) {
+        const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
-    *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-  }
-  // channels 24..Cpad-1: position independent
-  const int nc = (Cpad - 24) / 8;
-  for (int it = tid; it < 256 * nc; it += 256) {
-    const int row = it / nc, c0 = 24 + (it - row * nc) * 8;
-    *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_hi[row & 7][c0]);
-    *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_lo[row & 7][c0]);
+    // channels 24..Cpad-1: position independent
+    const int nc = (Cpad - 24) / 8;
+    for (int it = tid; it < 256 * nc; it += 256) {
+      const int row = it / nc, c0 = 24 + (it - row * nc) * 8;
+      *reinterpret_cast<uint4*>(hi + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_hi[row & 7][c0]);
+      *reinterpret_cast<uint4*>(lo + blk_off + (size_t)row * Cpad + c0) = *reinterpret_cast<const uint4*>(&cst_lo[row & 7][c0]);
+    }
   }
 }
 
@@ -151,7 +160,7 @@ int assemble_pack(nsc_model* m, const uint8_t* mat, const int32_t* meta, const f
                   uint16_t* hi, uint16_t* lo, int Cpad, cudaStream_t s) {
   if (n == 0) return NSC_OK;
   ProfScope prof(m, 0, s);
-  assemble_pack_kernel<<<(unsigned)(((n + 7) / 8) * kH), 256, 0, s>>>(mat, meta, anns255, (double)coverage_thr, m->C, Cpad,
+  assemble_pack_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(mat, meta, anns255, (double)coverage_thr, m->C, Cpad,
                                                                      m->normalize_channels ? 1 : 0, hi, lo, (int)n);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches++;
