@@ -153,6 +153,11 @@ int umma_max_chunk(nsc_model* m);
 int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s);
 int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float coverage_thr,
                           int64_t n, const Outputs& o, cudaStream_t s);
+// training step on the tensor path (nsc_umma.cu): workspace of the trainer's private model handle, fp32 NCHW convolutions
+int umma_train_init(nsc_model* m, int64_t max_batch);
+void umma_train_free(nsc_model* m);
+int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
+                    const float* resid, float* out, int64_t n, cudaStream_t s);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);

@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "nsc_common.h"
 
 namespace nsc {
@@ -32,7 +35,9 @@ struct nsc_trainer {
   nsc::TLayer L[9];
   int64_t fc_off[8];            // fc1.w, fc1.b, fc2.w, fc2.b, fc3.w, fc3.b, fc4.w, fc4.b
   std::vector<std::pair<std::string, std::pair<int64_t, int64_t>>> slices;
-  nsc_model dummy;              // launch counter / profiler hooks of the shared conv launcher
+  nsc_model dummy;              // launch counter / profiler hooks of the shared conv launcher; tensor-path workspace
+  bool tensor_fwd = true;       // 64 -> 64 train-mode forward convolutions on the tensor path
+  bool tensor_bwd = true;       // their data gradients too (NSC_TRAIN_FP32=1: both off; NSC_TRAIN_TENSOR=fwd|bwd: one of them)
   // activations (fp32 NCHW)
   float *u0 = nullptr, *a0 = nullptr, *x[5] = {};            // x[i]: input of block i (x[4] = flatten input)
   float *u1[4] = {}, *a1[4] = {}, *u2[4] = {}, *z[4] = {};
@@ -503,6 +508,12 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   t->C = num_channels;
   t->max_batch = max_batch;
   t->dummy.device = device;
+  t->tensor_fwd = t->tensor_bwd = getenv("NSC_TRAIN_FP32") == nullptr;
+  if (const char* e = getenv("NSC_TRAIN_TENSOR")) { t->tensor_fwd = strstr(e, "fwd") != nullptr; t->tensor_bwd = strstr(e, "bwd") != nullptr; }
+  if (t->tensor_fwd || t->tensor_bwd) {
+    int rc = umma_train_init(&t->dummy, max_batch);
+    if (rc != NSC_OK) { delete t; return rc; }
+  }
   // parameter layout: nn.Module.named_parameters() order (network.py:41-64)
   int64_t off = 0;
   auto add = [&](const std::string& name, int64_t n) { t->slices.push_back({name, {off, n}}); const int64_t o = off; off += n; return o; };
@@ -584,9 +595,15 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   auto conv_bn = [&](int li, const float* in, float* u, float* out, int relu, const float* resid) -> int {
     const TLayer& L = t->L[li];
     const int T = L.k_h * L.k_w;
-    repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
-    NSC_LAUNCH_OK();
-    int r = fp32_conv_generic(&t->dummy, L.k_h == 1 ? 1 : L.k_h, L.dil, L.W, in, t->wf, params + L.b_off, nullptr, u, N, L.cin, s);
+    int r;
+    if (t->tensor_fwd && L.cin == 64) {
+      // train-mode forward convolution on the tensor path (split fp16, fp32 accumulate): u = conv(in, w) + b
+      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s);
+    } else {
+      repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
+      NSC_LAUNCH_OK();
+      r = fp32_conv_generic(&t->dummy, L.k_h == 1 ? 1 : L.k_h, L.dil, L.W, in, t->wf, params + L.b_off, nullptr, u, N, L.cin, s);
+    }
     if (r != NSC_OK) return r;
     const int HW = kH * L.W;
     bn_stats_partial_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, N, HW, t->red + 256);
@@ -672,6 +689,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   auto dgrad = [&](int li, const float* du, const float* resid, float* dx) -> int {
     const TLayer& L = t->L[li];
     const int T = L.k_h * L.k_w;
+    if (t->tensor_bwd)   // data gradient = the same convolution with swapped channels and flipped taps
+      return umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, du, params + L.w_off, 1, t->zeros, resid, dx, N, s);
     repack_w_kernel<<<grid_for((int64_t)64 * 64 * T), 256, 0, s>>>(params + L.w_off, t->wf, t->wb, 64, T);
     NSC_LAUNCH_OK();
     return fp32_conv_generic(&t->dummy, L.k_h, L.dil, L.W, du, t->wb, t->zeros, resid, dx, N, 64, s);
@@ -718,6 +737,7 @@ int nsc_trainer_destroy(nsc_trainer* t) {
   cudaFree(t->h); cudaFree(t->dh); cudaFree(t->logits); cudaFree(t->dlogits);
   cudaFree(t->gA); cudaFree(t->gB); cudaFree(t->gC); cudaFree(t->stats); cudaFree(t->red);
   cudaFree(t->wf); cudaFree(t->wb); cudaFree(t->wpart); cudaFree(t->head_w); cudaFree(t->head_g); cudaFree(t->zeros);
+  umma_train_free(&t->dummy);
   delete t;
   return NSC_OK;
 }

@@ -88,7 +88,7 @@ struct ConvCfg {
   static_assert(!(STASH && GP != 1), "column-block stash assumes one group per unit");
   // layers without pooling convert in registers and leave through TMA tensor stores from two double-buffered
   // [128 rows][128 B] swizzle-128B tiles (x16 and c8 / lo16): no item phase, no LSU stores
-  static constexpr bool TMAOUT = (POOL == 0) && (GP == 1) && (TW == 16);
+  static constexpr bool TMAOUT = (POOL == 0) && (GP == 1) && (TW == 16) && !NCHW;
   static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
                                  (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + 256;
   static_assert(SMEM <= 232448 - 1024, "shared memory budget");
@@ -143,6 +143,8 @@ struct UmmaConvArgs {
   uint16_t* out_lo;          // exact fp16 lo part (nullptr: not needed by the consumer)
   uint8_t* out_c8;           // packed [groups][5][WOUT][8][128]: e4m3(x) | e4m3(x_lo * 2^12) for an S8 consumer (or nullptr)
   float* out_nchw;           // fp32 [B,64,5,WOUT] (NCHW configs)
+  const float* out_scale;    // device scalar multiplied into the NCHW output before the addend (or nullptr = 1)
+  const float* res_nchw;     // fp32 [B,64,5,WOUT] added to the NCHW output (training: gradient of the skip connection) or nullptr
   const uint16_t* res_hi;    // residual input, packed, width W (or nullptr)
   const uint16_t* res_lo;
   int n_groups;
@@ -578,7 +580,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           if (active) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              float4 v = *reinterpret_cast<const float4*>(bias_s + half * 32 + c * 4);   // broadcast read
+              float4 v = Cfg::NCHW ? make_float4(0.f, 0.f, 0.f, 0.f)    // training: bias follows the output scale
+                                   : *reinterpret_cast<const float4*>(bias_s + half * 32 + c * 4);   // broadcast read
               v.x += __uint_as_float(r[c * 4 + 0]);
               v.y += __uint_as_float(r[c * 4 + 1]);
               v.z += __uint_as_float(r[c * 4 + 2]);
@@ -614,7 +617,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const float* p0 = stg + rr * 64 + ((ch ^ (rr & 7)) << 2);
             float4 m0 = *reinterpret_cast<const float4*>(p0), m1 = *reinterpret_cast<const float4*>(p0 + 32);
             if (Cfg::POOL == 0) {
-              store_item(args.out_hi, args.out_lo, args.out_c8, row_off(grp, h, W, w0 + wl, rr) / 64, ch, m0, m1);
+              if (Cfg::NCHW) {
+                // training: raw fp32 NCHW output (+ optional fp32 addend); 4-byte scattered stores, small tensors
+                const int64_t b = (int64_t)ga * 8 + g;
+                if (b < args.B) {
+                  const int64_t o = ((b * 64 + ch * 4) * kH + h) * W + (w0 + wl);
+                  const int cs = kH * W;
+                  const float vv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                  const float osc = args.out_scale != nullptr ? __ldg(args.out_scale) : 1.f;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const int cj = (j & 3) + (j >> 2) * 32;
+                    const int64_t oj = o + (int64_t)cj * cs;
+                    args.out_nchw[oj] = vv[j] * osc + bias_s[ch * 4 + cj] + (args.res_nchw != nullptr ? args.res_nchw[oj] : 0.f);
+                  }
+                }
+              } else {
+                store_item(args.out_hi, args.out_lo, args.out_c8, row_off(grp, h, W, w0 + wl, rr) / 64, ch, m0, m1);
+              }
               continue;
             }
             // stash slots: 0 = column TW-2, 1 = column TW-1 of the first column block
@@ -906,7 +926,8 @@ enum : int { kOutLo = 1, kOutC8 = 2, kOutHiLo = kOutLo };   // which companions 
 template <class Cfg>
 static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const uint8_t* wpk, const float* bias,
                             uint16_t* const out[3], float* out_nchw, uint16_t* const res[2], int64_t n, int relu,
-                            cudaStream_t s, int out_fmt = kOutHiLo) {
+                            cudaStream_t s, int out_fmt = kOutHiLo, const float* res_nchw = nullptr,
+                            const float* out_scale = nullptr) {
   const int64_t groups = ((n + 7) / 8 + Cfg::GP - 1) / Cfg::GP;      // units of GP candidate groups
   CUtensorMap th, tl;
   int rc;
@@ -921,6 +942,8 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
   a.out_lo = (out && (out_fmt & kOutLo)) ? out[1] : nullptr;
   a.out_c8 = (out && (out_fmt & kOutC8)) ? reinterpret_cast<uint8_t*>(out[2]) : nullptr;
   a.out_nchw = out_nchw;
+  a.res_nchw = res_nchw;
+  a.out_scale = out_scale;
   a.res_hi = res ? res[0] : nullptr;
   a.res_lo = res ? res[1] : nullptr;
   a.n_groups = (int)groups;
@@ -1063,6 +1086,132 @@ static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
     return umma_run_t<true>(m, n, o, s);
   }
   return umma_run_t<false>(m, n, o, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// training step: the train-mode forward convolutions and the data-gradient convolutions (train.py:416-441) on the same
+// tensor kernels.  Tensors of the optimisation step are fp32 NCHW; weights change every step, so they are packed on the
+// device: plain (forward) or with input / output channels swapped and the taps flipped (data gradient).
+// ---------------------------------------------------------------------------------------------
+// max |x| over a tensor as the bit pattern of a non-negative float (atomicMax on unsigned works for those)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < __int_as_float(0x7f800000)) atomicMax(out, __float_as_uint(m));
+}
+
+// Weights of the optimisation step are multiplied by 2^8 before the hi/lo split: a weight of 0.02 would leave its lo part
+// (1e-5) in the fp16 subnormal range, i.e. 1.5e-6 of relative error per product instead of 2^-22.
+constexpr float kTrainWScale = 256.f;
+// fp32 [B,64,5,W] -> packed hi/lo [Bpad/8][5][W][8][64]; candidates >= B are zero.  The values are multiplied by the power
+// of two that brings the tensor's maximum (absmax bits at scl[0]) to [8192, 16384) -- gradients are far below the fp16
+// normal range, and small activations would lose their lo part -- and the inverse (times the inverse of the weight
+// scale) is left at scl[1] for the epilogue of the convolution.
+__global__ void __launch_bounds__(256)
+pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B, int Bpad, int W,
+                   float* __restrict__ scl) {
+  float scale = 1.f;
+  {
+    const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scl)[0]);
+    if (m > 0.f) scale = exp2f(floorf(log2f(16384.f / m)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) scl[1] = 1.f / (scale * kTrainWScale);
+  }
+  const int64_t total = (int64_t)Bpad * kH * W * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t r = i / W;
+    const int c8 = (int)(r % 8);
+    r /= 8;
+    const int h = (int)(r % kH);
+    const int64_t b = r / kH;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = b < B ? __ldg(in + ((b * 64 + c8 * 8 + j) * kH + h) * W + w) * scale : 0.f;
+    uint4 a, l;
+    split8(v, a, l);
+    const size_t off = (((((size_t)(b >> 3)) * kH + h) * W + w) * 8 + (b & 7)) * 64 + c8 * 8;
+    *reinterpret_cast<uint4*>(hi + off) = a;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+// PyTorch weight [64][64][KH][KW] fp32 -> the split-fp16 stage images of pack_conv_weights (sel 0 = hi, 1 = lo).
+// flip: the data-gradient convolution, i.e. weight(out = ci, in = co, dy, dx) = w[co][ci][KH-1-dy][KW-1-dx]
+__global__ void pack_train_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int KH, int KW, int KC, int flip) {
+  const int NK = 64 / KC;
+  const size_t stage = (size_t)KH * 64 * KC * 2;
+  const int total = 64 * 64 * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int dx = i % KW, dy = (i / KW) % KH, ci = (i / (KW * KH)) % 64, co = i / (KW * KH * 64);
+    const float v = flip ? w[((ci * 64 + co) * KH + (KH - 1 - dy)) * KW + (KW - 1 - dx)] : w[i];
+    const float vs = fminf(fmaxf(v * kTrainWScale, -65504.f), 65504.f);
+    const __half hv = __float2half_rn(vs);
+    const __half lv = __float2half_rn(vs - __half2float(hv));
+    const int kc = ci / KC, k = ci % KC;
+    const uint32_t r = (uint32_t)(dy * 64 + co), c = (uint32_t)(k / 8);
+    const uint32_t off = (KC == 32 ? ptx::swz_offset<64>(r, c) : ptx::swz_offset<32>(r, c)) + (k % 8) * 2;
+    *reinterpret_cast<__half*>(out + (size_t)((0 * NK + kc) * KW + dx) * stage + off) = hv;
+    *reinterpret_cast<__half*>(out + (size_t)((1 * NK + kc) * KW + dx) * stage + off) = lv;
+  }
+}
+
+int umma_train_init(nsc_model* m, int64_t max_batch) {
+  UmmaState& u = m->umma;
+  u.cap = (max_batch + 15) / 16 * 16;
+  m->precision = NSC_PREC_SPLIT16;
+  NSC_CUDA_TRY(cudaDeviceGetAttribute(&u.num_sms, cudaDevAttrMultiProcessorCount, m->device));
+  const size_t bytes = (size_t)u.cap * kH * 32 * 64 * sizeof(uint16_t);
+  for (int p = 0; p < 2; ++p) {
+    NSC_CUDA_TRY(cudaMalloc((void**)&u.xin[p], bytes));
+    NSC_CUDA_TRY(cudaMemset(u.xin[p], 0, bytes));
+  }
+  NSC_CUDA_TRY(cudaMalloc((void**)&u.wpk1, (size_t)2 * 25 * 64 * 64 * 2));
+  NSC_CUDA_TRY(cudaMalloc((void**)&u.fc_in, 64));   // [0] absmax bits, [1] inverse scale of the data-gradient operand
+  return NSC_OK;
+}
+
+void umma_train_free(nsc_model* m) {
+  UmmaState& u = m->umma;
+  for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
+  cudaFree(u.wpk1); u.wpk1 = nullptr;
+  cudaFree(u.fc_in); u.fc_in = nullptr;
+  u.cap = 0;
+}
+
+// out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
+int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
+                    const float* resid, float* out, int64_t n, cudaStream_t s) {
+  UmmaState& u = m->umma;
+  if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_conv: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
+  const int bpad = (int)((n + 15) / 16 * 16);
+  const int64_t items = (int64_t)bpad * kH * W * 8;
+  // operand rescaled into the upper fp16 range (power of two, undone in the epilogue)
+  float* scl = u.fc_in;
+  NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
+  absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
+  NSC_CUDA_TRY(cudaGetLastError());
+  pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
+  NSC_CUDA_TRY(cudaGetLastError());
+  const int kc = W == 8 ? 16 : 32;
+  pack_train_weights_kernel<<<(64 * 64 * k * k + 255) / 256, 256, 0, s>>>(w, u.wpk1, k, k, kc, flip);
+  NSC_CUDA_TRY(cudaGetLastError());
+  m->launches += 3;
+  uint16_t* tin[3] = {u.xin[0], u.xin[1], nullptr};
+#define NSC_TC(KK, DD, WW, NKK, KCC, GPP)                                                                                       \
+  if (k == KK && dil == DD && W == WW)                                                                                          \
+    return launch_umma_conv<ConvCfg<KK, KK, DD, WW, NKK, 0, true, KCC, GPP, false>>(m, 12, tin, u.wpk1, bias, nullptr, out, nullptr, n, \
+                                                                                     0, s, kOutHiLo, resid, scl + 1)
+  NSC_TC(3, 1, 32, 2, 32, 1);
+  NSC_TC(5, 1, 32, 2, 32, 1);
+  NSC_TC(3, 2, 16, 2, 32, 1);
+  NSC_TC(5, 1, 16, 2, 32, 1);
+  NSC_TC(3, 4, 8, 4, 16, 2);
+  NSC_TC(5, 2, 8, 4, 16, 2);
+#undef NSC_TC
+  set_error("umma_train_conv: no tensor configuration for k=%d dil=%d W=%d", k, dil, W);
+  return NSC_E_INVALID;
 }
 
 }  // namespace nsc

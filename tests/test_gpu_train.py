@@ -1,7 +1,8 @@
 """GPU: the training step (csrc/nsc_train.cu through the C ABI) against the golden vectors produced by the
 unmodified reference (tests/golden/make_golden_train.py: reference network.py in train() mode, train.py's loss,
 loss.backward(), optim.SGD) and against the torch-CPU autograd oracle (oracle/train_port.py).
-Tolerances: losses 1e-4 relative; gradients 2e-4 of the tensor's largest magnitude against the float64 oracle and
+Tolerances: losses 1e-4 relative; gradients 2e-5 (fp32 convolutions) / 1e-3 (tensor convolutions, see below) of the
+tensor's largest magnitude against the float64 oracle and
 1e-2 against the reference's own fp32 gradients (their fp32 noise, measured against float64, is up to 8e-3);
 parameters after two SGD steps 2e-4 absolute."""
 import os
@@ -29,8 +30,21 @@ def _cuda_inputs(g, x):
             torch.from_numpy(g["len_labels"]).to(dev), torch.from_numpy(g["w_type"]).to(dev), torch.from_numpy(g["w_len"]).to(dev))
 
 
-def test_losses_and_gradients_match_reference_and_oracle():
+# Gradient bound against the float64 oracle, relative to the tensor's largest magnitude.  The fp32 CUDA-core convolutions
+# (NSC_TRAIN_FP32=1) are within 2e-6 (measured 1.4e-6).  The default path runs the 64 -> 64 forward / data-gradient
+# convolutions on the tensor cores (split fp16, fp32 accumulate in TMEM): its normalised activations carry ~2e-6 of
+# absolute error, which flips the ReLU mask of ONE element of this batch whose float64 pre-activation is 1.79e-6
+# (res_layers.1.bn_r1; flipping it moves that layer's bias gradient by 3.23e-4 of its maximum -- tools/relu_kink_report.py
+# lists the near-kink elements and their flip effect).  Everything not downstream of that element stays at 1e-6..1e-4.
+# The unmodified reference's own fp32 gradients are 1e-3..8e-3 from the float64 values.
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tensor", 1e-3)])
+def test_losses_and_gradients_match_reference_and_oracle(mode, tol, monkeypatch):
     from neusomatic_b200.train import Trainer
+    if mode == "fp32":
+        monkeypatch.setenv("NSC_TRAIN_FP32", "1")     # read by nsc_trainer_create
+    else:
+        monkeypatch.delenv("NSC_TRAIN_FP32", raising=False)
+        monkeypatch.delenv("NSC_TRAIN_TENSOR", raising=False)
     g, x = _golden()
     sd = synth.random_state_dict(26, seed=11)
     tr = Trainer(sd, 26, max_batch=64)
@@ -49,7 +63,11 @@ def test_losses_and_gradients_match_reference_and_oracle():
     print("max |dgrad| / max|grad| per tensor:", {k: "%.1e" % v for k, v in worst.items()})
     for name, r in ref.items():
         if float(r.abs().max()) > 1e-5:          # conv biases in front of a BatchNorm have ~0 gradient
-            assert worst[name] <= 2e-4, (name, worst[name])
+            assert worst[name] <= tol, (name, worst[name])
+    if mode == "tensor":      # the layers behind the flipped element (backward order) are unaffected by it
+        for name in ref:
+            if name.startswith(("fc", "res_layers.2", "res_layers.3")) and float(ref[name].abs().max()) > 1e-5:
+                assert worst[name] <= 2e-5, (name, worst[name])
     # and the golden gradients of the reference itself
     for k in g:
         if k.startswith("grad."):
