@@ -37,6 +37,7 @@ struct nsc_trainer {
   std::vector<std::pair<std::string, std::pair<int64_t, int64_t>>> slices;
   nsc_model dummy;              // launch counter / profiler hooks of the shared conv launcher; tensor-path workspace
   bool tensor_fwd = true;       // 64 -> 64 train-mode forward convolutions on the tensor path
+  bool tensor_wgrad = true;     // weight gradients of the 64 -> 64 convolutions on the tensor path ("wgrad" in NSC_TRAIN_TENSOR)
   bool tensor_bwd = true;       // their data gradients too (NSC_TRAIN_FP32=1: both off; NSC_TRAIN_TENSOR=fwd|bwd: one of them)
   // activations (fp32 NCHW)
   float *u0 = nullptr, *a0 = nullptr, *x[5] = {};            // x[i]: input of block i (x[4] = flatten input)
@@ -468,6 +469,7 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
 
 static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s) {
   const int T = L.k_h * L.k_w;
+  if (t->tensor_wgrad && L.cin == 64) return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
 #define NSC_WG(WW, KK)                                                                                              \
@@ -509,8 +511,11 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   t->max_batch = max_batch;
   t->dummy.device = device;
   t->tensor_fwd = t->tensor_bwd = getenv("NSC_TRAIN_FP32") == nullptr;
-  if (const char* e = getenv("NSC_TRAIN_TENSOR")) { t->tensor_fwd = strstr(e, "fwd") != nullptr; t->tensor_bwd = strstr(e, "bwd") != nullptr; }
-  if (t->tensor_fwd || t->tensor_bwd) {
+  t->tensor_wgrad = t->tensor_fwd;
+  if (const char* e = getenv("NSC_TRAIN_TENSOR")) {
+    t->tensor_fwd = strstr(e, "fwd") != nullptr; t->tensor_bwd = strstr(e, "bwd") != nullptr; t->tensor_wgrad = strstr(e, "wgrad") != nullptr;
+  }
+  if (t->tensor_fwd || t->tensor_bwd || t->tensor_wgrad) {
     int rc = umma_train_init(&t->dummy, max_batch);
     if (rc != NSC_OK) { delete t; return rc; }
   }

@@ -51,8 +51,16 @@ namespace nsc {
 
 using namespace ptx;
 
-constexpr int kUmmaThreads = 384;       // warps 0-3: TMA A, MMA, TMA W + TMEM, idle; warps 4-11: epilogue
-constexpr int kEpiThreads = 256;
+#ifndef NSC_EPI_Q
+#define NSC_EPI_Q 2
+#endif
+constexpr int kEpiQ = NSC_EPI_Q;                    // epilogue warps per TMEM lane quarter (2 or 4; measured equal: 4.93 M cand/s both)
+constexpr int kCPT = 64 / kEpiQ;                    // output channels per epilogue thread (32 or 16)
+constexpr int kEpiThreads = 128 * kEpiQ;
+constexpr int kUmmaThreads = 128 + kEpiThreads;     // warps 0-3: TMA A, MMA, TMA W + TMEM, idle; warps 4..: epilogue
+static_assert(kEpiQ == 2 || kEpiQ == 4, "epilogue width");
+__device__ __forceinline__ void tmem_ld_cpt(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cpt(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
 constexpr int kStageBytes = 32768;      // epilogue staging: hi plane + lo plane of one [128 x 64] row tile
 constexpr int kStashBytes = 20480;      // boundary columns carried between the two column blocks (W = 32)
 
@@ -465,7 +473,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     // consecutive lanes take consecutive ch, so the global traffic of the item phases is 64-byte contiguous.
     const int et = tid - 128;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;             // channels half*32 .. half*32+31
+    const int part = (warp - 4) >> 2;             // channels part*kCPT .. part*kCPT + kCPT - 1
     const int row = (Cfg::M == 128) ? (q * 32 + lane) : (q * 16 + lane);
     const bool active = (Cfg::M == 128) || lane < 16;
     constexpr int ITEMS = Cfg::M * 8 / kEpiThreads;
@@ -502,13 +510,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         t_full += clock64() - t_c;
         t_c = clock64();
         tc_fence_after_sync();
-        const uint32_t acc0 = tmem + (u_it & 1) * 192 + ((uint32_t)(q * 32) << 16) + half * 32;
+        const uint32_t acc0 = tmem + (u_it & 1) * 192 + ((uint32_t)(q * 32) << 16) + part * kCPT;
         const int w0 = sub * Cfg::TW;
         // the two accumulators the NEXT unit shares with this one are pulled into registers first and released
         // immediately, so that the MMA issuer can start on them while this unit is still being post-processed
-        uint32_t r[32], rb[32];
-        tmem_ld_32x32b_x32(acc0 + ((u_it & 1) ? 0 : 3) * 64, r);
-        tmem_ld_32x32b_x32(acc0 + ((u_it & 1) ? 1 : 4) * 64, rb);
+        uint32_t r[kCPT], rb[kCPT];
+        tmem_ld_cpt(acc0 + ((u_it & 1) ? 0 : 3) * 64, r);
+        tmem_ld_cpt(acc0 + ((u_it & 1) ? 1 : 4) * 64, rb);
         tmem_ld_wait();
         tc_fence_before_sync();
         mbar_arrive(shared_free);
@@ -519,9 +527,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           const int h = slot_row<DIL>(slot);
           if (idx == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = rb[j];
+            for (int j = 0; j < kCPT; ++j) r[j] = rb[j];
           } else if (idx >= 2) {
-            tmem_ld_32x32b_x32(acc0 + slot * 64, r);
+            tmem_ld_cpt(acc0 + slot * 64, r);
             tmem_ld_wait();
           }
           if (idx == kH - 1) { tc_fence_before_sync(); mbar_arrive(all_free + 8 * (u_it & 1)); }
@@ -531,20 +539,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             uint8_t* t0 = st_hi + (rowc & 1) * kStageBytes;
             uint8_t* t1 = t0 + 16384;
             const uint32_t sw = row & 7, rbase = row * 128;
-            uint32_t e8[8], el8[8];
+            uint32_t e8[kCPT / 4], el8[kCPT / 4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {          // 8 channels = one 16-byte chunk of the x16 row
+            for (int c = 0; c < kCPT / 8; ++c) {   // 8 channels = one 16-byte chunk of the x16 row
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                v[j] = __uint_as_float(r[c * 8 + j]) + bias_s[half * 32 + c * 8 + j];
+                v[j] = __uint_as_float(r[c * 8 + j]) + bias_s[part * kCPT + c * 8 + j];
                 if (args.relu) v[j] = fmaxf(v[j], 0.f);
               }
               uint4 hq, lq;
               split8(v, hq, lq);
-              *reinterpret_cast<uint4*>(t0 + rbase + (((half * 4 + c) ^ sw) << 4)) = hq;
+              *reinterpret_cast<uint4*>(t0 + rbase + (((part * (kCPT / 8) + c) ^ sw) << 4)) = hq;
               if (args.out_c8 == nullptr) {
-                *reinterpret_cast<uint4*>(t1 + rbase + (((half * 4 + c) ^ sw) << 4)) = lq;
+                *reinterpret_cast<uint4*>(t1 + rbase + (((part * (kCPT / 8) + c) ^ sw) << 4)) = lq;
               } else {
                 float hf[8];
                 const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&hq.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&hq.y));
@@ -556,11 +564,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 el8[2 * c + 1] = e4m3x4((v[4] - hf[4]) * kXlo8Scale, (v[5] - hf[5]) * kXlo8Scale, (v[6] - hf[6]) * kXlo8Scale, (v[7] - hf[7]) * kXlo8Scale);
               }
             }
-            if (args.out_c8 != nullptr) {          // c8 row: bytes [half*32, +32) = e4m3(x), bytes [64 + half*32, +32) = e4m3(x_lo * 2^12)
-              *reinterpret_cast<uint4*>(t1 + rbase + (((half * 2 + 0) ^ sw) << 4)) = make_uint4(e8[0], e8[1], e8[2], e8[3]);
-              *reinterpret_cast<uint4*>(t1 + rbase + (((half * 2 + 1) ^ sw) << 4)) = make_uint4(e8[4], e8[5], e8[6], e8[7]);
-              *reinterpret_cast<uint4*>(t1 + rbase + (((4 + half * 2 + 0) ^ sw) << 4)) = make_uint4(el8[0], el8[1], el8[2], el8[3]);
-              *reinterpret_cast<uint4*>(t1 + rbase + (((4 + half * 2 + 1) ^ sw) << 4)) = make_uint4(el8[4], el8[5], el8[6], el8[7]);
+            if (args.out_c8 != nullptr) {          // c8 row: bytes [part*kCPT, +kCPT) = e4m3(x), bytes [64 + part*kCPT, +kCPT) = e4m3(x_lo * 2^12)
+#pragma unroll
+              for (int c2 = 0; c2 < kCPT / 16; ++c2) {
+                const uint32_t cx = part * (kCPT / 16) + c2;
+                *reinterpret_cast<uint4*>(t1 + rbase + ((cx ^ sw) << 4)) = make_uint4(e8[4 * c2], e8[4 * c2 + 1], e8[4 * c2 + 2], e8[4 * c2 + 3]);
+                *reinterpret_cast<uint4*>(t1 + rbase + (((4 + cx) ^ sw) << 4)) = make_uint4(el8[4 * c2], el8[4 * c2 + 1], el8[4 * c2 + 2], el8[4 * c2 + 3]);
+              }
             }
             fence_proxy_async_smem();
             // the stores of the previous image row must have finished reading their tiles before anyone passes the barrier:
@@ -576,18 +586,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             ++rowc;
             continue;
           }
-          // ---- phase A: this thread's row, 32 channels
+          // ---- phase A: this thread's row, kCPT channels
           if (active) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < kCPT / 4; ++c) {
               float4 v = Cfg::NCHW ? make_float4(0.f, 0.f, 0.f, 0.f)    // training: bias follows the output scale
-                                   : *reinterpret_cast<const float4*>(bias_s + half * 32 + c * 4);   // broadcast read
+                                   : *reinterpret_cast<const float4*>(bias_s + part * kCPT + c * 4);   // broadcast read
               v.x += __uint_as_float(r[c * 4 + 0]);
               v.y += __uint_as_float(r[c * 4 + 1]);
               v.z += __uint_as_float(r[c * 4 + 2]);
               v.w += __uint_as_float(r[c * 4 + 3]);
               if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              *reinterpret_cast<float4*>(stg + row * 64 + ((half * 8 + (c ^ (row & 7))) << 2)) = v;
+              const int lc = part * (kCPT / 4) + c;      // logical 4-channel chunk of the row; XOR swizzle within each half-row
+              *reinterpret_cast<float4*>(stg + row * 64 + (((lc & 8) | ((lc ^ row) & 7)) << 2)) = v;
             }
           }
           epi_bar();
@@ -894,6 +905,8 @@ void umma_free(nsc_model* m) {
     for (int p = 0; p < 3; ++p) { cudaFree(u.buf[i][p]); u.buf[i][p] = nullptr; }
   for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
   cudaFree(u.fc_in); u.fc_in = nullptr;
+  for (int p = 0; p < 2; ++p) { cudaFree(u.buf[0][p]); u.buf[0][p] = nullptr; }
+  cudaFree(u.buf[1][0]); u.buf[1][0] = nullptr;
   u.cap = 0;
 }
 
@@ -1116,7 +1129,7 @@ pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint
   {
     const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scl)[0]);
     if (m > 0.f) scale = exp2f(floorf(log2f(16384.f / m)));
-    if (blockIdx.x == 0 && threadIdx.x == 0) scl[1] = 1.f / (scale * kTrainWScale);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scl[1] = 1.f / (scale * kTrainWScale); scl[2] = 1.f / scale; }
   }
   const int64_t total = (int64_t)Bpad * kH * W * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1168,7 +1181,10 @@ int umma_train_init(nsc_model* m, int64_t max_batch) {
     NSC_CUDA_TRY(cudaMemset(u.xin[p], 0, bytes));
   }
   NSC_CUDA_TRY(cudaMalloc((void**)&u.wpk1, (size_t)2 * 25 * 64 * 64 * 2));
-  NSC_CUDA_TRY(cudaMalloc((void**)&u.fc_in, 64));   // [0] absmax bits, [1] inverse scale of the data-gradient operand
+  NSC_CUDA_TRY(cudaMalloc((void**)&u.fc_in, 64));   // [0] absmax bits, [1], [2] inverse scales of the packed operand; [4..6]: second operand
+  // weight gradient: packed conv input (hi, lo) and the per-CTA partial sums [<= 256 CTAs][3 slots][128][64] fp32
+  for (int p = 0; p < 2; ++p) NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[0][p], bytes));
+  NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[1][0], (size_t)256 * 3 * 128 * 64 * sizeof(float)));
   return NSC_OK;
 }
 
@@ -1177,7 +1193,262 @@ void umma_train_free(nsc_model* m) {
   for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
   cudaFree(u.wpk1); u.wpk1 = nullptr;
   cudaFree(u.fc_in); u.fc_in = nullptr;
+  for (int p = 0; p < 2; ++p) { cudaFree(u.buf[0][p]); u.buf[0][p] = nullptr; }
+  cudaFree(u.buf[1][0]); u.buf[1][0] = nullptr;
   u.cap = 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient on the tensor path:  dW[co][ci][dy][dx] = sum over (b, h, w) of du[b,co,h,w] * x[b,ci,h + dy d - P,w + dx d - P]
+// Both tensors are in the packed position-major layout ([group][row][column][8 candidates][64 channels] fp16 hi / lo), so
+// the contraction index (positions) is the OUTER index of both operands: MN-major UMMA operands.  A [column][8 cand][128 B]
+// row tile staged by TMA with swizzle-128B is exactly the canonical MN-major SW128 layout (cute mma_traits_sm100.hpp:
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): one K-atom = the 8 candidates of one column (8 rows of 128 B),
+// SBO = 1 KB = the next column, and LBO = the stride between 64-channel MN atoms, which is used to put TWO kernel taps
+// (the x windows shifted by dx and dx + 1, DIL KB apart) into one M = 128 instruction:
+//     D[tap-in-pair * 64 + ci][co] += x_window(dx0 + tap)[pos][ci] * du[pos][co]        (M = 128, N = 64, K = 16 positions)
+// One CTA = one kernel row dy and a slice of the (group, column block, image row) items; it accumulates its taps in TMEM
+// over all its items and writes ONE partial per CTA; wgrad_umma_reduce_kernel sums the partials in double (deterministic).
+// Products: du_lo x_hi + du_hi x_lo + du_hi x_hi (split fp16, small terms first).
+// ---------------------------------------------------------------------------------------------
+template <int KS_, int DIL_, int W_>
+struct WgCfg {
+  static constexpr int KS = KS_, DIL = DIL_, W = W_;
+  static constexpr int TW = W >= 16 ? 16 : 8;             // columns per item
+  static constexpr int SUBS = W / TW;
+  static constexpr int P = DIL * (KS - 1) / 2;
+  static constexpr int WB = TW + 2 * P;                   // columns of the x box (zero-filled outside the image by TMA)
+  static constexpr int NSLOT = KS == 3 ? 2 : 3;           // tap pairs per kernel row: (0,1),(1,2) / (0,1),(2,3),(3,4)
+  static constexpr int DU_BYTES = TW * 1024, X_BYTES = WB * 1024;
+  static constexpr int STAGE = 2 * DU_BYTES + 2 * X_BYTES;   // du_hi | du_lo | x_hi | x_lo
+  static constexpr int NS = (226 * 1024 / STAGE) > 4 ? 4 : (226 * 1024 / STAGE);
+  static constexpr size_t SMEM = 1024 + (size_t)NS * STAGE;
+  __host__ __device__ static constexpr int slot_dx0(int p) { return KS == 3 ? p : (p == 0 ? 0 : p + 1); }
+};
+
+struct WgradArgs {
+  float* part;          // [gridDim.x][NSLOT][128][64] fp32
+  int n_groups;
+  int cta_start[6];     // CTAs [cta_start[dy], cta_start[dy+1]) work on kernel row dy
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(128, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_constant__ CUtensorMap tm_du_lo,
+                  const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo, const WgradArgs args) {
+  constexpr int NS = Cfg::NS, DIL = Cfg::DIL;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bars[2 * 4 + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[4]), done = smem_u32(&bars[8]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int dy = 0;
+  while (dy + 1 < Cfg::KS && (int)blockIdx.x >= args.cta_start[dy + 1]) ++dy;
+  const int slice = blockIdx.x - args.cta_start[dy], nslices = args.cta_start[dy + 1] - args.cta_start[dy];
+  const int h_lo = max(0, Cfg::P - dy * DIL), h_hi = min(kH - 1, kH - 1 + Cfg::P - dy * DIL);
+  const int nv = h_hi - h_lo + 1;                               // image rows whose input row h + dy d - P exists
+  const int total = nv > 0 ? args.n_groups * Cfg::SUBS * nv : 0;
+  const int n_items = total > slice ? (total - slice + nslices - 1) / nslices : 0;
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_du_hi); tma_prefetch_desc(&tm_du_lo); tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo);
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_slot), 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < n_items; ++it) {
+        const int i = slice + it * nslices;
+        const int h = h_lo + i % nv, sub = (i / nv) % Cfg::SUBS, g = i / (nv * Cfg::SUBS);
+        const uint32_t st = it % NS;
+        if (it >= NS) mbar_wait(empty + 8 * st, ((it / NS) - 1) & 1);
+        mbar_arrive_expect_tx(full + 8 * st, Cfg::STAGE);
+        const uint32_t base = smem_u32(smem + (size_t)st * Cfg::STAGE);
+        const int w0 = sub * Cfg::TW, hx = h + dy * DIL - Cfg::P;
+        tma_load_5d(base, &tm_du_hi, full + 8 * st, 0, 0, 0, w0, g * kH + h);
+        tma_load_5d(base + Cfg::DU_BYTES, &tm_du_lo, full + 8 * st, 0, 0, 0, w0, g * kH + h);
+        tma_load_5d(base + 2 * Cfg::DU_BYTES, &tm_x_hi, full + 8 * st, 0, 0, 0, w0 - Cfg::P, g * kH + hx);
+        tma_load_5d(base + 2 * Cfg::DU_BYTES + Cfg::X_BYTES, &tm_x_lo, full + 8 * st, 0, 0, 0, w0 - Cfg::P, g * kH + hx);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // A and B MN-major (bits 15, 16), fp16 operands, fp32 accumulate
+      constexpr uint32_t idesc = make_idesc_f16(128, 64, 0) | (1u << 15) | (1u << 16);
+      for (int it = 0; it < n_items; ++it) {
+        const uint32_t st = it % NS;
+        mbar_wait(full + 8 * st, (it / NS) & 1);
+        tc_fence_after_sync();
+        const uint32_t du_hi = smem_u32(smem + (size_t)st * Cfg::STAGE), du_lo = du_hi + Cfg::DU_BYTES;
+        const uint32_t x_hi = du_hi + 2 * Cfg::DU_BYTES, x_lo = x_hi + Cfg::X_BYTES;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t db = prod == 0 ? du_lo : du_hi, xb = prod == 1 ? x_lo : x_hi;
+#pragma unroll
+          for (int p = 0; p < Cfg::NSLOT; ++p) {
+#pragma unroll
+            for (int ks = 0; ks < Cfg::TW / 2; ++ks) {
+              const uint64_t ad = make_smem_desc(xb + (uint32_t)(Cfg::slot_dx0(p) * DIL + 2 * ks) * 1024u, DIL * 1024u, 1024u, kSwizzle128);
+              const uint64_t bd = make_smem_desc(db + (uint32_t)(2 * ks) * 1024u, 1024u, 1024u, kSwizzle128);
+              umma_f16(tmem + p * 64, ad, bd, idesc, (it > 0 || prod > 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty + 8 * st);
+      }
+      umma_commit(done);
+    }
+  }
+  __syncwarp();
+  // ===== epilogue: every thread owns one TMEM lane (tap-in-pair * 64 + ci) =====
+  if (n_items > 0) {
+    mbar_wait(done, 0);
+    tc_fence_after_sync();
+  }
+  float* out = args.part + ((size_t)blockIdx.x * Cfg::NSLOT * 128 + tid) * 64;
+#pragma unroll 1
+  for (int p = 0; p < Cfg::NSLOT; ++p)
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      if (n_items > 0) {
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + p * 64 + c * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      float4* o = reinterpret_cast<float4*>(out + (size_t)p * 128 * 64 + c * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 256);
+}
+
+// dW[co][ci][dy][dx] = inv_x * inv_du * sum over the CTAs of kernel row dy of part[cta][slot(dx)][half(dx) * 64 + ci][co]
+__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KS, int nslot, WgradArgs args,
+                                         const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
+  const int total = 64 * 64 * KS * KS;
+  const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i & 63, ci = (i >> 6) & 63, t = i >> 12;
+    const int dy = t / KS, dx = t % KS;
+    int slot, half;
+    if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
+    else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
+    double sum = 0.0;
+    for (int c = args.cta_start[dy]; c < args.cta_start[dy + 1]; ++c)
+      sum += part[(((size_t)c * nslot + slot) * 128 + half * 64 + ci) * 64 + co];
+    dw[((co * 64 + ci) * KS + dy) * KS + dx] = (float)(sum * scale);
+  }
+}
+
+// one image row of a packed tensor: box (64 channels, 8 candidates, 1, box_w columns, 1 row), swizzle-128B
+static int make_row_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int box_w) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    NSC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &q));
+    if (!encode) { set_error("cuTensorMapEncodeTiled is not available"); return NSC_E_CUDA; }
+  }
+  const cuuint64_t row = 128, img_row = (cuuint64_t)W * 8 * row;
+  cuuint64_t dims[5] = {64, 8, 1, (cuuint64_t)W, (cuuint64_t)(groups * kH)};
+  cuuint64_t strides[4] = {row, kH * img_row, 8 * row, img_row};
+  cuuint32_t box[5] = {64, 8, 1, (cuuint32_t)box_w, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (row tile) failed (%d)", (int)r); return NSC_E_CUDA; }
+  return NSC_OK;
+}
+
+template <class Cfg>
+static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, cudaStream_t s) {
+  UmmaState& u = m->umma;
+  CUtensorMap tdh, tdl, txh, txl;
+  int rc;
+  if ((rc = make_row_tmap(&tdh, u.xin[0], groups, Cfg::W, Cfg::TW)) != NSC_OK) return rc;
+  if ((rc = make_row_tmap(&tdl, u.xin[1], groups, Cfg::W, Cfg::TW)) != NSC_OK) return rc;
+  if ((rc = make_row_tmap(&txh, u.buf[0][0], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
+  if ((rc = make_row_tmap(&txl, u.buf[0][1], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
+  // CTAs per kernel row in proportion to its number of valid image rows
+  WgradArgs a;
+  a.part = reinterpret_cast<float*>(u.buf[1][0]);
+  a.n_groups = (int)groups;
+  int nv[5] = {}, nvt = 0;
+  for (int dy = 0; dy < Cfg::KS; ++dy) {
+    const int lo = std::max(0, Cfg::P - dy * Cfg::DIL), hi = std::min(kH - 1, kH - 1 + Cfg::P - dy * Cfg::DIL);
+    nv[dy] = std::max(0, hi - lo + 1);
+    nvt += nv[dy];
+  }
+  const int ctas = std::max(u.num_sms, Cfg::KS);
+  int acc = 0;
+  a.cta_start[0] = 0;
+  for (int dy = 0; dy < Cfg::KS; ++dy) {
+    acc += nv[dy];
+    int end = (int)((int64_t)ctas * acc / nvt);
+    end = std::max(end, a.cta_start[dy] + 1);          // at least one CTA per kernel row (it writes the zero partial)
+    a.cta_start[dy + 1] = end;
+  }
+  for (int dy = Cfg::KS + 1; dy < 6; ++dy) a.cta_start[dy] = a.cta_start[Cfg::KS];
+  const int grid = a.cta_start[Cfg::KS];
+  auto kern = wgrad_umma_kernel<Cfg>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
+  NSC_CUDA_TRY(cudaGetLastError());
+  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KS * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KS, Cfg::NSLOT, a, u.fc_in + 6, u.fc_in + 2);
+  NSC_CUDA_TRY(cudaGetLastError());
+  m->launches += 2;
+  return NSC_OK;
+}
+
+// dw[64][64][k][k] = weight gradient of a 64 -> 64 convolution from its fp32 NCHW input x and output gradient du.
+// du_packed: the packed, rescaled du is already in the workspace (left there by this function; umma_train_conv(flip) of
+// the same du can then skip its own packing).
+int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s) {
+  UmmaState& u = m->umma;
+  if (n > u.cap || u.buf[0][0] == nullptr) { set_error("umma_train_wgrad: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
+  const int bpad = (int)((n + 15) / 16 * 16);
+  const int64_t items = (int64_t)bpad * kH * W * 8;
+  const unsigned pgrid = (unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16);
+  float* scl = u.fc_in;            // [0..2]: du (absmax bits, inverse scale / weight scale, inverse scale); [4..6]: x
+  NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 32, s));
+  absmax_kernel<<<148 * 4, 256, 0, s>>>(du, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
+  NSC_CUDA_TRY(cudaGetLastError());
+  absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
+  NSC_CUDA_TRY(cudaGetLastError());
+  pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(du, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
+  NSC_CUDA_TRY(cudaGetLastError());
+  pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, u.buf[0][0], u.buf[0][1], (int)n, bpad, W, scl + 4);
+  NSC_CUDA_TRY(cudaGetLastError());
+  m->launches += 4;
+  const int64_t groups = bpad / 8;
+#define NSC_WG(KK, DD, WW) \
+  if (k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, s)
+  NSC_WG(3, 1, 32);
+  NSC_WG(5, 1, 32);
+  NSC_WG(3, 2, 16);
+  NSC_WG(5, 1, 16);
+  NSC_WG(3, 4, 8);
+  NSC_WG(5, 2, 8);
+#undef NSC_WG
+  set_error("umma_train_wgrad: no tensor configuration for k=%d dil=%d W=%d", k, dil, W);
+  return NSC_E_INVALID;
 }
 
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
