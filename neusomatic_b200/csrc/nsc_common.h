@@ -157,7 +157,7 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
 int umma_train_init(nsc_model* m, int64_t max_batch);
 void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s);
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked = 0);
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);

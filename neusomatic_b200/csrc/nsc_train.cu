@@ -49,6 +49,8 @@ struct nsc_trainer {
   float* wf = nullptr;                                       // re-packed weights: forward [tap][ci][co]
   float* wb = nullptr;                                       // data-gradient [tap'][co][ci]
   float* wpart = nullptr;                                    // weight-gradient partial sums
+  float* gpart = nullptr;                                    // split-K partials of the linear layers
+  size_t gpart_floats = 0;
   float* head_w = nullptr;                                   // [9][240] gathered head weights / gradients
   float* head_g = nullptr;
   float* zeros = nullptr;                                    // 64 zeros (bias of the data-gradient convolutions)
@@ -198,60 +200,73 @@ __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __res
   }
 }
 
-// per-channel sums for the BatchNorm backward: sum(dy), sum(dy * xhat); dy is masked by (mask_src > 0) when given.
-// Also used (u == nullptr) as a plain per-channel sum of dy (convolution bias gradient).
+// per-channel sums for the BatchNorm backward: sum(dy), sum(dy * xhat), sum(xhat); dy is masked by (mask_src > 0) when
+// given.  sum(xhat) (rounding noise of the fp32 mean) gives the gradient of the convolution bias in front of the
+// BatchNorm without another pass: sum(du) = -gamma * invstd * sum(dy * xhat) * sum(xhat) / M.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ dy,
-                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][2]*/) {
+                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][3]*/) {
   const int c = blockIdx.x, sp = blockIdx.y;
-  const float mean = u ? stats[c] : 0.f, invstd = u ? stats[64 + c] : 0.f;
-  double s = 0.0, sx = 0.0;
+  const float mean = stats[c], invstd = stats[64 + c];
+  double s = 0.0, sx = 0.0, sh1 = 0.0;
   const int64_t total = (int64_t)N * HW;
   for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < total; i += 256 * kRedSplits) {
     const int64_t idx = ((i / HW) * 64 + c) * HW + (i % HW);
     float g = dy[idx];
     if (mask_src != nullptr && !(mask_src[idx] > 0.f)) g = 0.f;
+    const float xhat = (u[idx] - mean) * invstd;
     s += g;
-    if (u) sx += (double)g * (double)((u[idx] - mean) * invstd);
+    sx += (double)g * (double)xhat;
+    sh1 += xhat;
   }
-  __shared__ double sh[2][256];
+  __shared__ double sh[3][256];
   sh[0][threadIdx.x] = s;
   sh[1][threadIdx.x] = sx;
+  sh[2][threadIdx.x] = sh1;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { sums[(c * kRedSplits + sp) * 2] = sh[0][0]; sums[(c * kRedSplits + sp) * 2 + 1] = sh[1][0]; }
+  if (threadIdx.x == 0) {
+    double* o = sums + (c * kRedSplits + sp) * 3;
+    o[0] = sh[0][0]; o[1] = sh[1][0]; o[2] = sh[2][0];
+  }
 }
 
-// [64][splits][2] -> [64][2]
+// [64][splits][3] -> [64][3]
 __global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums) {
   const int c = threadIdx.x;
   if (c >= 64) return;
-  double a = 0.0, b = 0.0;
-  for (int sp = 0; sp < kRedSplits; ++sp) { a += part[(c * kRedSplits + sp) * 2]; b += part[(c * kRedSplits + sp) * 2 + 1]; }
-  sums[c * 2] = a;
-  sums[c * 2 + 1] = b;
+  double a = 0.0, b = 0.0, d = 0.0;
+  for (int sp = 0; sp < kRedSplits; ++sp) {
+    a += part[(c * kRedSplits + sp) * 3]; b += part[(c * kRedSplits + sp) * 3 + 1]; d += part[(c * kRedSplits + sp) * 3 + 2];
+  }
+  sums[c * 3] = a;
+  sums[c * 3 + 1] = b;
+  sums[c * 3 + 2] = d;
 }
 
-// du = gamma * invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M); also writes dgamma, dbeta
+// du = gamma * invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M); also writes dgamma, dbeta and the gradient of the
+// convolution bias in front of the BatchNorm, sum(du) = -gamma * invstd * sum(dy*xhat) * sum(xhat) / M
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ dy, const float* __restrict__ mask_src, const double* __restrict__ sums,
-                                    float* __restrict__ du, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t total,
-                                    int HW, double inv_m) {
+                                    float* __restrict__ du, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ dbias, int64_t total, int HW, double inv_m) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / HW) % 64);
     float g = dy[i];
     if (mask_src != nullptr && !(mask_src[i] > 0.f)) g = 0.f;
     const float xhat = (u[i] - stats[c]) * stats[64 + c];
-    du[i] = gamma[c] * stats[64 + c] * (float)((double)g - sums[c * 2] * inv_m - (double)xhat * sums[c * 2 + 1] * inv_m);
-    if (i < 64) { dgamma[i] = (float)sums[i * 2 + 1]; dbeta[i] = (float)sums[i * 2]; }
+    du[i] = gamma[c] * stats[64 + c] * (float)((double)g - sums[c * 3] * inv_m - (double)xhat * sums[c * 3 + 1] * inv_m);
+    if (i < 64) {
+      dgamma[i] = (float)sums[i * 3 + 1];
+      dbeta[i] = (float)sums[i * 3];
+      dbias[i] = (float)(-(double)gamma[i] * (double)stats[64 + i] * sums[i * 3 + 1] * sums[i * 3 + 2] * inv_m);
+    }
   }
-}
-
-__global__ void store_channel_sums_kernel(const double* __restrict__ sums, float* __restrict__ out) {
-  if (threadIdx.x < 64) out[threadIdx.x] = (float)sums[threadIdx.x * 2];
 }
 
 // weight gradient partial sums: part[split][tap][ci][co] += x[b, ci, h + dy*d - ph, w + dx*d - pw] * du[b, co, h, w]
@@ -334,13 +349,22 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   }
 }
 
-// generic small GEMM: C[m][n] = sum_k A(m,k) * B(k,n) (+ bias[n]) (ReLU) with arbitrary element strides
+// generic small GEMM: C[m][n] = sum_k A(m,k) * B(k,n) (+ bias[n]) (ReLU) with arbitrary element strides.
+// gridDim.z > 1: split-K, block z covers k in [z * kchunk, (z + 1) * kchunk) and writes its partial [M][N] (dense, no bias)
+// at Cm + z * M * N; gemm_splitk_reduce_kernel adds the partials in a fixed order.
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B, int64_t b_rs,
-            int64_t b_cs, float* __restrict__ Cm, int64_t c_rs, const float* __restrict__ bias, int relu) {
+            int64_t b_cs, float* __restrict__ Cm, int64_t c_rs, const float* __restrict__ bias, int relu, int kchunk) {
   __shared__ float As[16][65], Bs[16][65];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (gridDim.z > 1) {
+    const int kb = blockIdx.z * kchunk;
+    A += (int64_t)kb * a_cs;
+    B += (int64_t)kb * b_rs;
+    K = min(kchunk, K - kb);
+    Cm += (int64_t)blockIdx.z * M * N;
+  }
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -459,10 +483,40 @@ __global__ void sgd_kernel(float* __restrict__ p, float* __restrict__ buf, const
 // ---------------------------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t total) { return (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8); }
 
+// C[m][n] = sum over the split-K partials (+ bias[n]) (ReLU)
+__global__ void gemm_splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, float* __restrict__ Cm, int64_t c_rs,
+                                          const float* __restrict__ bias, int relu) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[z * total + i];
+    if (bias) v += bias[n];
+    if (relu) v = fmaxf(v, 0.f);
+    Cm[(i / N) * c_rs + n] = v;
+  }
+}
+
 static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
-                    float* Cm, int64_t c_rs, const float* bias, int relu, cudaStream_t s) {
+                    float* Cm, int64_t c_rs, const float* bias, int relu, cudaStream_t s, float* scratch = nullptr,
+                    size_t scratch_floats = 0) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, Cm, c_rs, bias, relu);
+  // split K (deterministic two-stage sum) while the output tiles alone leave most of the 148 SMs idle
+  int splits = 1;
+  while (scratch != nullptr && grid.x * grid.y * splits * 2 <= 148 * 2 && K / (splits * 2) >= 32 &&
+         (size_t)(splits * 2) * M * N <= scratch_floats)
+    splits *= 2;
+  if (splits > 1) {
+    const int kchunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    grid.z = (K + kchunk - 1) / kchunk;
+    gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, scratch, N, nullptr, 0, kchunk);
+    NSC_CUDA_TRY(cudaGetLastError());
+    gemm_splitk_reduce_kernel<<<(unsigned)std::min<int64_t>(((int64_t)M * N + 255) / 256, 148 * 8), 256, 0, s>>>(scratch, (int)grid.z, M, N, Cm,
+                                                                                                                c_rs, bias, relu);
+    NSC_CUDA_TRY(cudaGetLastError());
+    return NSC_OK;
+  }
+  gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, Cm, c_rs, bias, relu, K);
   NSC_CUDA_TRY(cudaGetLastError());
   return NSC_OK;
 }
@@ -560,9 +614,11 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   e = e ? e : alloc(&t->logits, (size_t)max_batch * 9 * 4); e = e ? e : alloc(&t->dlogits, (size_t)max_batch * 9 * 4);
   e = e ? e : alloc(&t->gA, full); e = e ? e : alloc(&t->gB, full); e = e ? e : alloc(&t->gC, full);
   e = e ? e : alloc(&t->stats, 9 * 128 * 4);
-  e = e ? e : cudaMalloc((void**)&t->red, (256 + 64 * kRedSplits * 2) * sizeof(double));
+  e = e ? e : cudaMalloc((void**)&t->red, (256 + 64 * kRedSplits * 3) * sizeof(double));
   e = e ? e : alloc(&t->wf, (size_t)25 * 128 * 64 * 4); e = e ? e : alloc(&t->wb, (size_t)25 * 64 * 64 * 4);
   e = e ? e : alloc(&t->wpart, (size_t)kWgSplits * 25 * 64 * 64 * 4);
+  t->gpart_floats = std::max<size_t>((size_t)4 * max_batch * kFcHidden, (size_t)4 * kFcHidden * kFcIn);
+  e = e ? e : alloc(&t->gpart, t->gpart_floats * 4);
   e = e ? e : alloc(&t->head_w, 9 * kFcHidden * 4); e = e ? e : alloc(&t->head_g, 9 * kFcHidden * 4);
   e = e ? e : alloc(&t->zeros, 64 * 4);
   e = e ? e : cudaMemset(t->zeros, 0, 64 * 4);
@@ -632,7 +688,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     NSC_LAUNCH_OK();
   }
   const float* W1 = params + t->fc_off[0];
-  NSC_RUN(run_gemm(N, kFcHidden, kFcIn, t->x[4], kFcIn, 1, W1, 1, kFcIn, t->h, kFcHidden, params + t->fc_off[1], 1, s));
+  NSC_RUN(run_gemm(N, kFcHidden, kFcIn, t->x[4], kFcIn, 1, W1, 1, kFcIn, t->h, kFcHidden, params + t->fc_off[1], 1, s, t->gpart, t->gpart_floats));
   // heads: gather [9][240] weights (fc2 4 rows, fc3 1, fc4 4) and [9] biases
   NSC_CUDA_TRY(cudaMemcpyAsync(t->head_w, params + t->fc_off[2], 4 * kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(t->head_w + 4 * kFcHidden, params + t->fc_off[4], kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
@@ -651,7 +707,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   if (losses_dev) { loss_store_kernel<<<1, 32, 0, s>>>(t->red, losses_dev); NSC_LAUNCH_OK(); }
   // ---------------- backward: linear layers ----------------
   // d head weights [9][240] = dlogits^T h ; biases = column sums ; dh = dlogits * head_w, masked by ReLU
-  NSC_RUN(run_gemm(9, kFcHidden, N, t->dlogits, 1, 9, t->h, kFcHidden, 1, t->head_g, kFcHidden, nullptr, 0, s));
+  NSC_RUN(run_gemm(9, kFcHidden, N, t->dlogits, 1, 9, t->h, kFcHidden, 1, t->head_g, kFcHidden, nullptr, 0, s, t->gpart, t->gpart_floats));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[2], t->head_g, 4 * kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[4], t->head_g + 4 * kFcHidden, kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[6], t->head_g + 5 * kFcHidden, 4 * kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
@@ -665,7 +721,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   relu_mask_kernel<<<grid_for((int64_t)N * kFcHidden), 256, 0, s>>>(t->dh, t->h, (int64_t)N * kFcHidden);
   NSC_LAUNCH_OK();
   // dW1 [240][1280] = dh^T x4 ; db1 ; dx4 [N][1280] = dh * W1
-  NSC_RUN(run_gemm(kFcHidden, kFcIn, N, t->dh, 1, kFcHidden, t->x[4], kFcIn, 1, grads + t->fc_off[0], kFcIn, nullptr, 0, s));
+  NSC_RUN(run_gemm(kFcHidden, kFcIn, N, t->dh, 1, kFcHidden, t->x[4], kFcIn, 1, grads + t->fc_off[0], kFcIn, nullptr, 0, s, t->gpart, t->gpart_floats));
   colsum_kernel<<<(kFcHidden + 255) / 256, 256, 0, s>>>(t->dh, N, kFcHidden, grads + t->fc_off[1]);
   NSC_LAUNCH_OK();
   float* g = t->gA;       // gradient w.r.t. the current block output
@@ -681,13 +737,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16);
     NSC_LAUNCH_OK();
     bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
-                                                        grads + L.g_off, grads + L.be_off, total, HW, 1.0 / ((double)N * HW));
-    NSC_LAUNCH_OK();
-    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(nullptr, nullptr, du_buf, nullptr, N, HW, t->red + 256);   // conv bias gradient
-    NSC_LAUNCH_OK();
-    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16);
-    NSC_LAUNCH_OK();
-    store_channel_sums_kernel<<<1, 64, 0, s>>>(t->red + 16, grads + L.b_off);
+                                                        grads + L.g_off, grads + L.be_off, grads + L.b_off, total, HW,
+                                                        1.0 / ((double)N * HW));
     NSC_LAUNCH_OK();
     return run_wgrad(t, L, conv_in, du_buf, grads + L.w_off, N, s);
   };
@@ -695,7 +746,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const TLayer& L = t->L[li];
     const int T = L.k_h * L.k_w;
     if (t->tensor_bwd)   // data gradient = the same convolution with swapped channels and flipped taps
-      return umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, du, params + L.w_off, 1, t->zeros, resid, dx, N, s);
+      return umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, du, params + L.w_off, 1, t->zeros, resid, dx, N, s,
+                             /*prepacked: the weight gradient of this layer has just packed du*/ t->tensor_wgrad ? 1 : 0);
     repack_w_kernel<<<grid_for((int64_t)64 * 64 * T), 256, 0, s>>>(params + L.w_off, t->wf, t->wb, 64, T);
     NSC_LAUNCH_OK();
     return fp32_conv_generic(&t->dummy, L.k_h, L.dil, L.W, du, t->wb, t->zeros, resid, dx, N, 64, s);
@@ -741,7 +793,7 @@ int nsc_trainer_destroy(nsc_trainer* t) {
   for (int i = 0; i < 4; ++i) { cudaFree(t->u1[i]); cudaFree(t->a1[i]); cudaFree(t->u2[i]); cudaFree(t->z[i]); }
   cudaFree(t->h); cudaFree(t->dh); cudaFree(t->logits); cudaFree(t->dlogits);
   cudaFree(t->gA); cudaFree(t->gB); cudaFree(t->gC); cudaFree(t->stats); cudaFree(t->red);
-  cudaFree(t->wf); cudaFree(t->wb); cudaFree(t->wpart); cudaFree(t->head_w); cudaFree(t->head_g); cudaFree(t->zeros);
+  cudaFree(t->wf); cudaFree(t->wb); cudaFree(t->wpart); cudaFree(t->gpart); cudaFree(t->head_w); cudaFree(t->head_g); cudaFree(t->zeros);
   umma_train_free(&t->dummy);
   delete t;
   return NSC_OK;

@@ -1347,10 +1347,17 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* 
     int slot, half;
     if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
     else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
-    double sum = 0.0;
-    for (int c = args.cta_start[dy]; c < args.cta_start[dy + 1]; ++c)
-      sum += part[(((size_t)c * nslot + slot) * 128 + half * 64 + ci) * 64 + co];
-    dw[((co * 64 + ci) * KS + dy) * KS + dx] = (float)(sum * scale);
+    const float* p0 = part + ((size_t)slot * 128 + half * 64 + ci) * 64 + co;
+    const size_t cs = (size_t)nslot * 128 * 64;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four loads in flight; fixed order: deterministic
+    int c = args.cta_start[dy];
+    const int c1 = args.cta_start[dy + 1];
+    for (; c + 3 < c1; c += 4) {
+      const float a0 = p0[c * cs], a1 = p0[(c + 1) * cs], a2 = p0[(c + 2) * cs], a3 = p0[(c + 3) * cs];
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+    }
+    for (; c < c1; ++c) s0 += p0[c * cs];
+    dw[((co * 64 + ci) * KS + dy) * KS + dx] = (float)(((s0 + s1) + (s2 + s3)) * scale);
   }
 }
 
@@ -1453,22 +1460,25 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
 
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s) {
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_conv: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
   const int64_t items = (int64_t)bpad * kH * W * 8;
   // operand rescaled into the upper fp16 range (power of two, undone in the epilogue)
   float* scl = u.fc_in;
-  NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
-  absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
-  NSC_CUDA_TRY(cudaGetLastError());
-  pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
-  NSC_CUDA_TRY(cudaGetLastError());
+  if (!prepacked) {     // (prepacked: umma_train_wgrad has left this very tensor, packed and scaled, in the workspace)
+    NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
+    absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
+    NSC_CUDA_TRY(cudaGetLastError());
+    pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
+    NSC_CUDA_TRY(cudaGetLastError());
+    m->launches += 2;
+  }
   const int kc = W == 8 ? 16 : 32;
   pack_train_weights_kernel<<<(64 * 64 * k * k + 255) / 256, 256, 0, s>>>(w, u.wpk1, k, k, kc, flip);
   NSC_CUDA_TRY(cudaGetLastError());
-  m->launches += 3;
+  m->launches += 1;
   uint16_t* tin[3] = {u.xin[0], u.xin[1], nullptr};
 #define NSC_TC(KK, DD, WW, NKK, KCC, GPP)                                                                                       \
   if (k == KK && dil == DD && W == WW)                                                                                          \
