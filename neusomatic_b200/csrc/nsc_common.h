@@ -82,6 +82,8 @@ struct UmmaState {
   uint16_t* xin[2] = {};                // packed network input (hi, lo): [cap/8][5][32][8][32*nk1]
   uint16_t* buf[3][3] = {};             // 3 packed activation tensors x (hi, lo, c8): [cap/8][5][32][8][64] (c8: 128 B rows)
   float* fc_in = nullptr;               // fp32 [cap,1280] input of fc1
+  uint16_t* tpk[8][2] = {};             // training: packed (hi, lo) inputs of the eight 64 -> 64 convolutions, kept for the weight gradient
+  float* tscl = nullptr;                // training: [8][4] absmax bits / inverse scales of those tensors
   int64_t cap = 0;
   int num_sms = 148;
   bool weights_fit_fp16 = true;
@@ -157,8 +159,9 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
 int umma_train_init(nsc_model* m, int64_t max_batch);
 void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked = 0);
-int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s);
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked = 0, int xslot = -1);
+int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
+                     int xslot = -1);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);

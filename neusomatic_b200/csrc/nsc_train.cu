@@ -523,7 +523,8 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
 
 static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s) {
   const int T = L.k_h * L.k_w;
-  if (t->tensor_wgrad && L.cin == 64) return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s);
+  if (t->tensor_wgrad && L.cin == 64)   // the forward convolution of this layer left its packed input in slot li - 1
+    return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
 #define NSC_WG(WW, KK)                                                                                              \
@@ -659,7 +660,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     int r;
     if (t->tensor_fwd && L.cin == 64) {
       // train-mode forward convolution on the tensor path (split fp16, fp32 accumulate): u = conv(in, w) + b
-      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s);
+      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s, 0, li - 1);
     } else {
       repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
       NSC_LAUNCH_OK();

@@ -905,8 +905,6 @@ void umma_free(nsc_model* m) {
     for (int p = 0; p < 3; ++p) { cudaFree(u.buf[i][p]); u.buf[i][p] = nullptr; }
   for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
   cudaFree(u.fc_in); u.fc_in = nullptr;
-  for (int p = 0; p < 2; ++p) { cudaFree(u.buf[0][p]); u.buf[0][p] = nullptr; }
-  cudaFree(u.buf[1][0]); u.buf[1][0] = nullptr;
   u.cap = 0;
 }
 
@@ -1185,6 +1183,15 @@ int umma_train_init(nsc_model* m, int64_t max_batch) {
   // weight gradient: packed conv input (hi, lo) and the per-CTA partial sums [<= 256 CTAs][3 slots][128][64] fp32
   for (int p = 0; p < 2; ++p) NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[0][p], bytes));
   NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[1][0], (size_t)256 * 3 * 128 * 64 * sizeof(float)));
+  // per-layer packed inputs of the eight 64 -> 64 convolutions (kept from the forward pass for the weight gradient)
+  for (int l = 0; l < 8; ++l) {
+    const int Wl = l < 4 ? 32 : l < 6 ? 16 : 8;
+    for (int p = 0; p < 2; ++p) {
+      NSC_CUDA_TRY(cudaMalloc((void**)&u.tpk[l][p], (size_t)u.cap * kH * Wl * 64 * sizeof(uint16_t)));
+      NSC_CUDA_TRY(cudaMemset(u.tpk[l][p], 0, (size_t)u.cap * kH * Wl * 64 * sizeof(uint16_t)));
+    }
+  }
+  NSC_CUDA_TRY(cudaMalloc((void**)&u.tscl, 8 * 4 * sizeof(float)));
   return NSC_OK;
 }
 
@@ -1195,6 +1202,9 @@ void umma_train_free(nsc_model* m) {
   cudaFree(u.fc_in); u.fc_in = nullptr;
   for (int p = 0; p < 2; ++p) { cudaFree(u.buf[0][p]); u.buf[0][p] = nullptr; }
   cudaFree(u.buf[1][0]); u.buf[1][0] = nullptr;
+  for (int l = 0; l < 8; ++l)
+    for (int p = 0; p < 2; ++p) { cudaFree(u.tpk[l][p]); u.tpk[l][p] = nullptr; }
+  cudaFree(u.tscl); u.tscl = nullptr;
   u.cap = 0;
 }
 
@@ -1381,14 +1391,14 @@ static int make_row_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int
 }
 
 template <class Cfg>
-static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, cudaStream_t s) {
+static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* const xpk[2], const float* inv_x, cudaStream_t s) {
   UmmaState& u = m->umma;
   CUtensorMap tdh, tdl, txh, txl;
   int rc;
   if ((rc = make_row_tmap(&tdh, u.xin[0], groups, Cfg::W, Cfg::TW)) != NSC_OK) return rc;
   if ((rc = make_row_tmap(&tdl, u.xin[1], groups, Cfg::W, Cfg::TW)) != NSC_OK) return rc;
-  if ((rc = make_row_tmap(&txh, u.buf[0][0], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
-  if ((rc = make_row_tmap(&txl, u.buf[0][1], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
+  if ((rc = make_row_tmap(&txh, xpk[0], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
+  if ((rc = make_row_tmap(&txl, xpk[1], groups, Cfg::W, Cfg::WB)) != NSC_OK) return rc;
   // CTAs per kernel row in proportion to its number of valid image rows
   WgradArgs a;
   a.part = reinterpret_cast<float*>(u.buf[1][0]);
@@ -1418,7 +1428,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, cudaStream
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KS * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KS, Cfg::NSLOT, a, u.fc_in + 6, u.fc_in + 2);
+  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KS * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KS, Cfg::NSLOT, a, inv_x, u.fc_in + 2);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
   return NSC_OK;
@@ -1427,7 +1437,9 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, cudaStream
 // dw[64][64][k][k] = weight gradient of a 64 -> 64 convolution from its fp32 NCHW input x and output gradient du.
 // du_packed: the packed, rescaled du is already in the workspace (left there by this function; umma_train_conv(flip) of
 // the same du can then skip its own packing).
-int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s) {
+// xslot >= 0: the packed x of that layer was kept by the forward convolution (umma_train_conv with the same xslot).
+int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
+                     int xslot) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.buf[0][0] == nullptr) { set_error("umma_train_wgrad: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
@@ -1437,16 +1449,24 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 32, s));
   absmax_kernel<<<148 * 4, 256, 0, s>>>(du, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
   NSC_CUDA_TRY(cudaGetLastError());
-  absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
-  NSC_CUDA_TRY(cudaGetLastError());
   pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(du, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
   NSC_CUDA_TRY(cudaGetLastError());
-  pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, u.buf[0][0], u.buf[0][1], (int)n, bpad, W, scl + 4);
-  NSC_CUDA_TRY(cudaGetLastError());
-  m->launches += 4;
+  m->launches += 2;
+  uint16_t* xpk[2] = {u.buf[0][0], u.buf[0][1]};
+  const float* inv_x = scl + 6;
+  if (xslot >= 0 && u.tpk[xslot][0] != nullptr) {
+    xpk[0] = u.tpk[xslot][0]; xpk[1] = u.tpk[xslot][1];
+    inv_x = u.tscl + 4 * xslot + 2;
+  } else {
+    absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
+    NSC_CUDA_TRY(cudaGetLastError());
+    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4);
+    NSC_CUDA_TRY(cudaGetLastError());
+    m->launches += 2;
+  }
   const int64_t groups = bpad / 8;
 #define NSC_WG(KK, DD, WW) \
-  if (k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, s)
+  if (k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, xpk, inv_x, s)
   NSC_WG(3, 1, 32);
   NSC_WG(5, 1, 32);
   NSC_WG(3, 2, 16);
@@ -1460,18 +1480,23 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
 
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked) {
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked, int xslot) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_conv: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
   const int64_t items = (int64_t)bpad * kH * W * 8;
   // operand rescaled into the upper fp16 range (power of two, undone in the epilogue)
   float* scl = u.fc_in;
+  uint16_t* tin[3] = {u.xin[0], u.xin[1], nullptr};
+  if (xslot >= 0 && u.tpk[xslot][0] != nullptr) {   // forward: the packed input stays in its layer's slot for the weight gradient
+    tin[0] = u.tpk[xslot][0]; tin[1] = u.tpk[xslot][1];
+    scl = u.tscl + 4 * xslot;
+  }
   if (!prepacked) {     // (prepacked: umma_train_wgrad has left this very tensor, packed and scaled, in the workspace)
     NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
     absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
     NSC_CUDA_TRY(cudaGetLastError());
-    pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
+    pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, tin[0], tin[1], (int)n, bpad, W, scl);
     NSC_CUDA_TRY(cudaGetLastError());
     m->launches += 2;
   }
@@ -1479,7 +1504,6 @@ int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const 
   pack_train_weights_kernel<<<(64 * 64 * k * k + 255) / 256, 256, 0, s>>>(w, u.wpk1, k, k, kc, flip);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 1;
-  uint16_t* tin[3] = {u.xin[0], u.xin[1], nullptr};
 #define NSC_TC(KK, DD, WW, NKK, KCC, GPP)                                                                                       \
   if (k == KK && dil == DD && W == WW)                                                                                          \
     return launch_umma_conv<ConvCfg<KK, KK, DD, WW, NKK, 0, true, KCC, GPP, false>>(m, 12, tin, u.wpk1, bias, nullptr, out, nullptr, n, \
