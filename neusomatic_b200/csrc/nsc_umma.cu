@@ -619,6 +619,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             if (idx + 1 < kH) load_res(grp, sub, u_it, idx + 1);
             epi_bar();
           }
+          if (Cfg::NCHW && Cfg::POOL == 0) {
+            // ---- training: fp32 NCHW output (* scale + bias + optional fp32 addend).  A thread takes (candidate, channel)
+            // pairs and walks the unit's TW columns: 16-byte stores into the contiguous W axis of [b][c][h][:], consecutive
+            // lanes = consecutive channels (conflict-free staging reads)
+            const float osc = args.out_scale != nullptr ? __ldg(args.out_scale) : 1.f;
+#pragma unroll 1
+            for (int pi = et; pi < Cfg::RPW * 64; pi += kEpiThreads) {
+              const int c = pi & 63, mg = pi >> 6;
+              const int64_t b = ((int64_t)grp * Cfg::GP + (mg >> 3)) * 8 + (mg & 7);
+              if (b >= args.B) continue;
+              const int64_t o = ((b * 64 + c) * kH + h) * W + w0;
+              const float bs = bias_s[c];
+              const int lc = c >> 2;
+#pragma unroll
+              for (int wq = 0; wq < Cfg::TW / 4; ++wq) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int rr = (wq * 4 + j) * Cfg::RPW + mg;
+                  v[j] = stg[rr * 64 + (((lc & 8) | ((lc ^ rr) & 7)) << 2) + (c & 3)] * osc + bs;
+                }
+                if (args.res_nchw != nullptr) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(args.res_nchw + o + wq * 4);
+                  v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                }
+                *reinterpret_cast<float4*>(args.out_nchw + o + wq * 4) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+            }
+            epi_bar();   // staging is rewritten by the next row
+            continue;
+          }
           // ---- phase B2: (pool and) split to hi/lo and store (coalesced items)
 #pragma unroll
           for (int k = 0; k < ITEMS; ++k) {
@@ -628,24 +659,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const float* p0 = stg + rr * 64 + ((ch ^ (rr & 7)) << 2);
             float4 m0 = *reinterpret_cast<const float4*>(p0), m1 = *reinterpret_cast<const float4*>(p0 + 32);
             if (Cfg::POOL == 0) {
-              if (Cfg::NCHW) {
-                // training: raw fp32 NCHW output (+ optional fp32 addend); 4-byte scattered stores, small tensors
-                const int64_t b = (int64_t)ga * 8 + g;
-                if (b < args.B) {
-                  const int64_t o = ((b * 64 + ch * 4) * kH + h) * W + (w0 + wl);
-                  const int cs = kH * W;
-                  const float vv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                  const float osc = args.out_scale != nullptr ? __ldg(args.out_scale) : 1.f;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const int cj = (j & 3) + (j >> 2) * 32;
-                    const int64_t oj = o + (int64_t)cj * cs;
-                    args.out_nchw[oj] = vv[j] * osc + bias_s[ch * 4 + cj] + (args.res_nchw != nullptr ? args.res_nchw[oj] : 0.f);
-                  }
-                }
-              } else {
-                store_item(args.out_hi, args.out_lo, args.out_c8, row_off(grp, h, W, w0 + wl, rr) / 64, ch, m0, m1);
-              }
+              store_item(args.out_hi, args.out_lo, args.out_c8, row_off(grp, h, W, w0 + wl, rr) / 64, ch, m0, m1);
               continue;
             }
             // stash slots: 0 = column TW-2, 1 = column TW-1 of the first column block
