@@ -192,7 +192,8 @@ def run_train(args, rank, local_rank, world, dev):
         print(json.dumps({"metric": "NeuSomaticNet train samples/sec (fwd+bwd+SGD)", "value": world * B * args.steps / (ms / 1000.0),
                           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32", "data": "synthetic",
+                          "dtype": "split fp16 x3 on tcgen05 with fp32 accumulate for the 64->64 convolutions (forward, data and weight "
+                                   "gradient); f32 elsewhere (NSC_TRAIN_FP32=1: all f32)", "data": "synthetic",
                           "config": {"workload": "train.py step (BASELINE.json configs[4]): C=26, SGD lr 0.01 momentum 0.9, "
                                                  "BatchNorm batch statistics per GPU, one NCCL all-reduce of 873385 floats per step",
                                      "batch_per_gpu": B}, "loss": float(losses[0])}), flush=True)

@@ -176,26 +176,29 @@ __global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict_
   }
 }
 
-// backward of that pool: the gradient of an output goes to the FIRST maximal element of its window
+// backward of that pool: the gradient of an output goes to the FIRST maximal element of its window (PyTorch).
+// One thread per input element: it is the pos-th element of up to three windows {lo, lo+1, lo+2}, lo = w - pos, which
+// belong to output wo = (lo + 1) / ST when that is an integer in [0, W/ST).  It wins a window when every earlier element
+// is strictly smaller and every later element is not larger (elements outside the row count as -inf).
+template <int ST>
 __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, float* __restrict__ din, int64_t rows,
-                                int W, int st) {
-  const int Wo = W / st;
+                                int W) {
+  const int Wo = W / ST;
   const int64_t total = rows * W;
+  const float ninf = -INFINITY;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(i % W);
     const int64_t row = i / W;
     const float* r = in + row * W;
+    const float* dr = dout + row * Wo;
+    const float c = r[w];
+    const float a = w >= 2 ? r[w - 2] : ninf, b = w >= 1 ? r[w - 1] : ninf;
+    const float d = w + 1 < W ? r[w + 1] : ninf, e = w + 2 < W ? r[w + 2] : ninf;
     float g = 0.f;
-    // outputs whose window {st*wo-1, st*wo, st*wo+1} contains w
-    for (int wo = (w - 1 + st - 1) / st; wo * st - 1 <= w && wo < Wo; ++wo) {
-      if (wo < 0) continue;
-      const int lo = wo * st - 1;
-      int arg = -1;
-      float best = -INFINITY;
-      for (int j = lo; j <= lo + 2; ++j)
-        if (j >= 0 && j < W && r[j] > best) { best = r[j]; arg = j; }
-      if (arg == w) g += dout[row * Wo + wo];
-    }
+    // ascending output index: pos = 2, 1, 0
+    if (w >= 1 && (w - 1) % ST == 0 && (w - 1) / ST < Wo && c > a && c > b) g += dr[(w - 1) / ST];      // lo = w - 2
+    if (w % ST == 0 && w / ST < Wo && c > b && c >= d) g += dr[w / ST];                                   // lo = w - 1
+    if ((w + 1) % ST == 0 && (w + 1) / ST < Wo && c >= d && c >= e) g += dr[(w + 1) / ST];               // lo = w
     din[i] = g;
   }
 }
@@ -759,7 +762,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const int st = kBlocks[i].pool, Wd = widths[i];
     const int64_t rows = (int64_t)N * 64 * kH;
     // g = d(loss)/d x[i+1]  ->  gz = d/d z[i]   (also the residual branch's share of d/d x[i])
-    pool_bwd_kernel<<<grid_for(rows * Wd), 256, 0, s>>>(t->z[i], g, gz, rows, Wd, st);
+    if (st == 1) pool_bwd_kernel<1><<<grid_for(rows * Wd), 256, 0, s>>>(t->z[i], g, gz, rows, Wd);
+    else pool_bwd_kernel<2><<<grid_for(rows * Wd), 256, 0, s>>>(t->z[i], g, gz, rows, Wd);
     NSC_LAUNCH_OK();
     // bn_r2 (no ReLU), conv_r2: du2 in gu; d a1 = dgrad(du2) -> g (reused)
     NSC_RUN(bn_conv_bwd(2 + 2 * i, t->u2[i], gz, nullptr, t->a1[i], gu));
@@ -769,7 +773,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     NSC_RUN(dgrad(1 + 2 * i, gu, gz, g));
   }
   // stem: pool1 (stride 1), ReLU, bn1, conv1
-  pool_bwd_kernel<<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, g, gz, (int64_t)N * 64 * kH, 32, 1);
+  pool_bwd_kernel<1><<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, g, gz, (int64_t)N * 64 * kH, 32);
   NSC_LAUNCH_OK();
   NSC_RUN(bn_conv_bwd(0, t->u0, gz, t->a0, x_dev, gu));
 #undef NSC_RUN
