@@ -82,11 +82,13 @@ __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(const float* __restrict__ u, int N, int HW, double* __restrict__ part) {
   const int c = blockIdx.x, sp = blockIdx.y;
   double s = 0.0, ss = 0.0;
-  const int64_t total = (int64_t)N * HW;
-  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < total; i += 256 * kRedSplits) {
-    const double v = u[((i / HW) * 64 + c) * HW + (i % HW)];
-    s += v;
-    ss += v * v;
+  const int HW4 = HW >> 2, total4 = N * HW4;      // HW = 5 W is a multiple of 4: 16-byte loads, 32-bit index arithmetic
+  for (int i = sp * 256 + threadIdx.x; i < total4; i += 256 * kRedSplits) {
+    const int n = i / HW4, r = i - n * HW4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(u + ((size_t)n * 64 + c) * HW) + r);
+    const double a = v.x, b = v.y, d = v.z, e = v.w;
+    s += (a + b) + (d + e);
+    ss += (a * a + b * b) + (d * d + e * e);
   }
   __shared__ double sh[2][256];
   sh[0][threadIdx.x] = s;
@@ -212,15 +214,27 @@ bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stat
   const int c = blockIdx.x, sp = blockIdx.y;
   const float mean = stats[c], invstd = stats[64 + c];
   double s = 0.0, sx = 0.0, sh1 = 0.0;
-  const int64_t total = (int64_t)N * HW;
-  for (int64_t i = (int64_t)sp * 256 + threadIdx.x; i < total; i += 256 * kRedSplits) {
-    const int64_t idx = ((i / HW) * 64 + c) * HW + (i % HW);
-    float g = dy[idx];
-    if (mask_src != nullptr && !(mask_src[idx] > 0.f)) g = 0.f;
-    const float xhat = (u[idx] - mean) * invstd;
-    s += g;
-    sx += (double)g * (double)xhat;
-    sh1 += xhat;
+  const int HW4 = HW >> 2, total4 = N * HW4;      // 16-byte loads, 32-bit index arithmetic
+  for (int i = sp * 256 + threadIdx.x; i < total4; i += 256 * kRedSplits) {
+    const int n = i / HW4, r = i - n * HW4;
+    const size_t o = ((size_t)n * 64 + c) * HW;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + o) + r);
+    const float4 u4 = __ldg(reinterpret_cast<const float4*>(u + o) + r);
+    float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    if (mask_src != nullptr) {
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask_src + o) + r);
+      if (!(m4.x > 0.f)) g[0] = 0.f;
+      if (!(m4.y > 0.f)) g[1] = 0.f;
+      if (!(m4.z > 0.f)) g[2] = 0.f;
+      if (!(m4.w > 0.f)) g[3] = 0.f;
+    }
+    const float xh[4] = {(u4.x - mean) * invstd, (u4.y - mean) * invstd, (u4.z - mean) * invstd, (u4.w - mean) * invstd};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s += g[j];
+      sx += (double)g[j] * (double)xh[j];
+      sh1 += xh[j];
+    }
   }
   __shared__ double sh[3][256];
   sh[0][threadIdx.x] = s;
@@ -409,12 +423,22 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int6
 }
 
 // column sums of a [M][N] matrix (bias gradients of the linear layers), optional ReLU mask from `mask_src`
-__global__ void colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// block = 32 columns x 8 row groups (launch with 256 threads); fixed summation order
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int m = 0; m < M; ++m) s += A[(size_t)m * N + n];
-  out[n] = (float)s;
+  if (n < N)
+    for (int m = ty; m < M; m += 8) s += A[(size_t)m * N + n];
+  __shared__ double sh[8][33];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += sh[j][tx];
+    out[n] = (float)a;
+  }
 }
 
 __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ act, int64_t total) {
@@ -528,6 +552,8 @@ static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const fl
   const int T = L.k_h * L.k_w;
   if (t->tensor_wgrad && L.cin == 64)   // the forward convolution of this layer left its packed input in slot li - 1
     return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1);
+  if (t->tensor_wgrad && L.cin < 64 && L.k_h == 1 && L.k_w == 3)   // the stem: input channels zero-padded to 64
+    return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
 #define NSC_WG(WW, KK)                                                                                              \
@@ -716,7 +742,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[4], t->head_g + 4 * kFcHidden, kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[6], t->head_g + 5 * kFcHidden, 4 * kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   float* dbh = t->gC;   // scratch [9]
-  colsum_kernel<<<1, 32, 0, s>>>(t->dlogits, N, 9, dbh);
+  colsum_kernel<<<1, 256, 0, s>>>(t->dlogits, N, 9, dbh);
   NSC_LAUNCH_OK();
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[3], dbh, 16, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[5], dbh + 4, 4, cudaMemcpyDeviceToDevice, s));
@@ -726,7 +752,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_LAUNCH_OK();
   // dW1 [240][1280] = dh^T x4 ; db1 ; dx4 [N][1280] = dh * W1
   NSC_RUN(run_gemm(kFcHidden, kFcIn, N, t->dh, 1, kFcHidden, t->x[4], kFcIn, 1, grads + t->fc_off[0], kFcIn, nullptr, 0, s, t->gpart, t->gpart_floats));
-  colsum_kernel<<<(kFcHidden + 255) / 256, 256, 0, s>>>(t->dh, N, kFcHidden, grads + t->fc_off[1]);
+  colsum_kernel<<<(kFcHidden + 31) / 32, 256, 0, s>>>(t->dh, N, kFcHidden, grads + t->fc_off[1]);
   NSC_LAUNCH_OK();
   float* g = t->gA;       // gradient w.r.t. the current block output
   NSC_RUN(run_gemm(N, kFcIn, kFcHidden, t->dh, kFcHidden, 1, W1, kFcIn, 1, g, kFcIn, nullptr, 0, s));

@@ -1136,7 +1136,7 @@ constexpr float kTrainWScale = 256.f;
 // scale) is left at scl[1] for the epilogue of the convolution.
 __global__ void __launch_bounds__(256)
 pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B, int Bpad, int W,
-                   float* __restrict__ scl) {
+                   float* __restrict__ scl, int C = 64) {
   float scale = 1.f;
   {
     const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scl)[0]);
@@ -1153,7 +1153,7 @@ pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint
     const int64_t b = r / kH;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = b < B ? __ldg(in + ((b * 64 + c8 * 8 + j) * kH + h) * W + w) * scale : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = (b < B && c8 * 8 + j < C) ? __ldg(in + ((b * C + c8 * 8 + j) * kH + h) * W + w) * scale : 0.f;
     uint4 a, l;
     split8(v, a, l);
     const size_t off = (((((size_t)(b >> 3)) * kH + h) * W + w) * 8 + (b & 7)) * 64 + c8 * 8;
@@ -1236,9 +1236,10 @@ void umma_train_free(nsc_model* m) {
 // over all its items and writes ONE partial per CTA; wgrad_umma_reduce_kernel sums the partials in double (deterministic).
 // Products: du_lo x_hi + du_hi x_lo + du_hi x_hi (split fp16, small terms first).
 // ---------------------------------------------------------------------------------------------
-template <int KS_, int DIL_, int W_>
+template <int KS_, int DIL_, int W_, int KH_ = KS_>
 struct WgCfg {
-  static constexpr int KS = KS_, DIL = DIL_, W = W_;
+  static constexpr int KS = KS_, DIL = DIL_, W = W_, KH = KH_;   // KH x KS kernel (KH = 1: the stem's 1 x 3)
+  static constexpr int PH = DIL * (KH - 1) / 2;
   static constexpr int TW = W >= 16 ? 16 : 8;             // columns per item
   static constexpr int SUBS = W / TW;
   static constexpr int P = DIL * (KS - 1) / 2;
@@ -1269,9 +1270,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
   const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[4]), done = smem_u32(&bars[8]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int dy = 0;
-  while (dy + 1 < Cfg::KS && (int)blockIdx.x >= args.cta_start[dy + 1]) ++dy;
+  while (dy + 1 < Cfg::KH && (int)blockIdx.x >= args.cta_start[dy + 1]) ++dy;
   const int slice = blockIdx.x - args.cta_start[dy], nslices = args.cta_start[dy + 1] - args.cta_start[dy];
-  const int h_lo = max(0, Cfg::P - dy * DIL), h_hi = min(kH - 1, kH - 1 + Cfg::P - dy * DIL);
+  const int h_lo = max(0, Cfg::PH - dy * DIL), h_hi = min(kH - 1, kH - 1 + Cfg::PH - dy * DIL);
   const int nv = h_hi - h_lo + 1;                               // image rows whose input row h + dy d - P exists
   const int total = nv > 0 ? args.n_groups * Cfg::SUBS * nv : 0;
   const int n_items = total > slice ? (total - slice + nslices - 1) / nslices : 0;
@@ -1296,7 +1297,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
         if (it >= NS) mbar_wait(empty + 8 * st, ((it / NS) - 1) & 1);
         mbar_arrive_expect_tx(full + 8 * st, Cfg::STAGE);
         const uint32_t base = smem_u32(smem + (size_t)st * Cfg::STAGE);
-        const int w0 = sub * Cfg::TW, hx = h + dy * DIL - Cfg::P;
+        const int w0 = sub * Cfg::TW, hx = h + dy * DIL - Cfg::PH;
         tma_load_5d(base, &tm_du_hi, full + 8 * st, 0, 0, 0, w0, g * kH + h);
         tma_load_5d(base + Cfg::DU_BYTES, &tm_du_lo, full + 8 * st, 0, 0, 0, w0, g * kH + h);
         tma_load_5d(base + 2 * Cfg::DU_BYTES, &tm_x_hi, full + 8 * st, 0, 0, 0, w0 - Cfg::P, g * kH + hx);
@@ -1361,13 +1362,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
 }
 
 // dW[co][ci][dy][dx] = inv_x * inv_du * sum over the CTAs of kernel row dy of part[cta][slot(dx)][half(dx) * 64 + ci][co]
-__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KS, int nslot, WgradArgs args,
-                                         const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
-  const int total = 64 * 64 * KS * KS;
+__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int nslot,
+                                         WgradArgs args, const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
+  const int total = 64 * 64 * KH * KS;
   const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i & 63, ci = (i >> 6) & 63, t = i >> 12;
     const int dy = t / KS, dx = t % KS;
+    if (ci >= Cin) continue;
     int slot, half;
     if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
     else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
@@ -1381,7 +1383,7 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* 
       s0 += a0; s1 += a1; s2 += a2; s3 += a3;
     }
     for (; c < c1; ++c) s0 += p0[c * cs];
-    dw[((co * 64 + ci) * KS + dy) * KS + dx] = (float)(((s0 + s1) + (s2 + s3)) * scale);
+    dw[((co * Cin + ci) * KH + dy) * KS + dx] = (float)(((s0 + s1) + (s2 + s3)) * scale);
   }
 }
 
@@ -1405,7 +1407,8 @@ static int make_row_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int
 }
 
 template <class Cfg>
-static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* const xpk[2], const float* inv_x, cudaStream_t s) {
+static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* const xpk[2], const float* inv_x, int cin,
+                             cudaStream_t s) {
   UmmaState& u = m->umma;
   CUtensorMap tdh, tdl, txh, txl;
   int rc;
@@ -1418,22 +1421,22 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   a.part = reinterpret_cast<float*>(u.buf[1][0]);
   a.n_groups = (int)groups;
   int nv[5] = {}, nvt = 0;
-  for (int dy = 0; dy < Cfg::KS; ++dy) {
-    const int lo = std::max(0, Cfg::P - dy * Cfg::DIL), hi = std::min(kH - 1, kH - 1 + Cfg::P - dy * Cfg::DIL);
+  for (int dy = 0; dy < Cfg::KH; ++dy) {
+    const int lo = std::max(0, Cfg::PH - dy * Cfg::DIL), hi = std::min(kH - 1, kH - 1 + Cfg::PH - dy * Cfg::DIL);
     nv[dy] = std::max(0, hi - lo + 1);
     nvt += nv[dy];
   }
-  const int ctas = std::max(u.num_sms, Cfg::KS);
+  const int ctas = std::max(u.num_sms, Cfg::KH);
   int acc = 0;
   a.cta_start[0] = 0;
-  for (int dy = 0; dy < Cfg::KS; ++dy) {
+  for (int dy = 0; dy < Cfg::KH; ++dy) {
     acc += nv[dy];
     int end = (int)((int64_t)ctas * acc / nvt);
     end = std::max(end, a.cta_start[dy] + 1);          // at least one CTA per kernel row (it writes the zero partial)
     a.cta_start[dy + 1] = end;
   }
-  for (int dy = Cfg::KS + 1; dy < 6; ++dy) a.cta_start[dy] = a.cta_start[Cfg::KS];
-  const int grid = a.cta_start[Cfg::KS];
+  for (int dy = Cfg::KH + 1; dy < 6; ++dy) a.cta_start[dy] = a.cta_start[Cfg::KH];
+  const int grid = a.cta_start[Cfg::KH];
   auto kern = wgrad_umma_kernel<Cfg>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1442,7 +1445,8 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KS * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KS, Cfg::NSLOT, a, inv_x, u.fc_in + 2);
+  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KH * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, Cfg::NSLOT, a, inv_x,
+                                                                                     u.fc_in + 2);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
   return NSC_OK;
@@ -1452,8 +1456,10 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
 // du_packed: the packed, rescaled du is already in the workspace (left there by this function; umma_train_conv(flip) of
 // the same du can then skip its own packing).
 // xslot >= 0: the packed x of that layer was kept by the forward convolution (umma_train_conv with the same xslot).
+// cin < 64 (the stem, kh = 1): the input channels are zero-padded to 64 in the packed operand.
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
-                     int xslot) {
+                     int xslot, int cin, int kh) {
+  if (kh <= 0) kh = k;
   UmmaState& u = m->umma;
   if (n > u.cap || u.buf[0][0] == nullptr) { set_error("umma_train_wgrad: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
@@ -1472,15 +1478,16 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
     xpk[0] = u.tpk[xslot][0]; xpk[1] = u.tpk[xslot][1];
     inv_x = u.tscl + 4 * xslot + 2;
   } else {
-    absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
+    absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * cin * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
     NSC_CUDA_TRY(cudaGetLastError());
-    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4);
+    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4, cin);
     NSC_CUDA_TRY(cudaGetLastError());
     m->launches += 2;
   }
   const int64_t groups = bpad / 8;
 #define NSC_WG(KK, DD, WW) \
-  if (k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, xpk, inv_x, s)
+  if (kh == k && k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, xpk, inv_x, cin, s)
+  if (kh == 1 && k == 3 && dil == 1 && W == 32) return launch_wgrad_umma<WgCfg<3, 1, 32, 1>>(m, groups, dw, xpk, inv_x, cin, s);
   NSC_WG(3, 1, 32);
   NSC_WG(5, 1, 32);
   NSC_WG(3, 2, 16);
@@ -1488,7 +1495,7 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   NSC_WG(3, 4, 8);
   NSC_WG(5, 2, 8);
 #undef NSC_WG
-  set_error("umma_train_wgrad: no tensor configuration for k=%d dil=%d W=%d", k, dil, W);
+  set_error("umma_train_wgrad: no tensor configuration for k=%dx%d dil=%d W=%d", kh, k, dil, W);
   return NSC_E_INVALID;
 }
 
