@@ -161,7 +161,9 @@ void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
                     const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked = 0, int xslot = -1);
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
-                     int xslot = -1, int cin = 64, int kh = 0);
+                     int xslot = -1, int cin = 64, int kh = 0, bool du_amax_known = false);
+// where the producer of a tensor leaves max |x| (bit pattern of a float): xslot 0..7 = input of the 64 -> 64 layer, -1 = du
+unsigned int* umma_train_amax_slot(nsc_model* m, int xslot);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);

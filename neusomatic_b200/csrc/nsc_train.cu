@@ -151,22 +151,37 @@ bn_stats_kernel(const float* __restrict__ u, int N, int HW, float eps, float mom
 }
 
 // y = (u - mean) * invstd * gamma + beta ; optional ReLU ; optional residual add
+// max |x| of the tensor a kernel has just produced, as the bit pattern of a non-negative float (atomicMax on unsigned):
+// the tensor path rescales its operands by it (umma_train_conv / umma_train_wgrad), so no separate pass is needed.
+// Called by every thread of the block after its grid-stride loop.
+__device__ __forceinline__ void amax_commit(float m, unsigned int* __restrict__ amax) {
+  if (amax == nullptr) return;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
+}
+
 __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ resid, float* __restrict__ out,
-                                int64_t total, int HW, int relu) {
+                                int64_t total, int HW, int relu, unsigned int* __restrict__ amax) {
+  float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / HW) % 64);
     float v = (u[i] - stats[c]) * stats[64 + c] * gamma[c] + beta[c];
     if (relu) v = fmaxf(v, 0.f);
     if (resid != nullptr) v += resid[i];
     out[i] = v;
+    m = fmaxf(m, fabsf(v));
   }
+  amax_commit(m, amax);
 }
 
 // MaxPool2d((1,3), padding (0,1), stride (1,st)) forward
-__global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int W, int st) {
+__global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int W, int st,
+                                unsigned int* __restrict__ amax) {
   const int Wo = W / st;
   const int64_t total = rows * Wo;
+  float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int wo = (int)(i % Wo);
     const float* r = in + (i / Wo) * W;
@@ -175,7 +190,9 @@ __global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict_
     if (wc - 1 >= 0) v = fmaxf(v, r[wc - 1]);
     if (wc + 1 < W) v = fmaxf(v, r[wc + 1]);
     out[i] = v;
+    m = fmaxf(m, fabsf(v));
   }
+  amax_commit(m, amax);
 }
 
 // backward of that pool: the gradient of an output goes to the FIRST maximal element of its window (PyTorch).
@@ -254,9 +271,10 @@ bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stat
 }
 
 // [64][splits][3] -> [64][3]
-__global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums) {
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums, unsigned int* __restrict__ amax) {
   const int c = threadIdx.x;
   if (c >= 64) return;
+  if (c == 0 && amax != nullptr) *amax = 0u;      // max |du| is collected by bn_bwd_apply_kernel, which runs next
   double a = 0.0, b = 0.0, d = 0.0;
   for (int sp = 0; sp < kRedSplits; ++sp) {
     a += part[(c * kRedSplits + sp) * 3]; b += part[(c * kRedSplits + sp) * 3 + 1]; d += part[(c * kRedSplits + sp) * 3 + 2];
@@ -271,19 +289,23 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __r
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ dy, const float* __restrict__ mask_src, const double* __restrict__ sums,
                                     float* __restrict__ du, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ dbias, int64_t total, int HW, double inv_m) {
+                                    float* __restrict__ dbias, int64_t total, int HW, double inv_m, unsigned int* __restrict__ amax) {
+  float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / HW) % 64);
     float g = dy[i];
     if (mask_src != nullptr && !(mask_src[i] > 0.f)) g = 0.f;
     const float xhat = (u[i] - stats[c]) * stats[64 + c];
-    du[i] = gamma[c] * stats[64 + c] * (float)((double)g - sums[c * 3] * inv_m - (double)xhat * sums[c * 3 + 1] * inv_m);
+    const float dv = gamma[c] * stats[64 + c] * (float)((double)g - sums[c * 3] * inv_m - (double)xhat * sums[c * 3 + 1] * inv_m);
+    du[i] = dv;
+    m = fmaxf(m, fabsf(dv));
     if (i < 64) {
       dgamma[i] = (float)sums[i * 3 + 1];
       dbeta[i] = (float)sums[i * 3];
       dbias[i] = (float)(-(double)gamma[i] * (double)stats[64 + i] * sums[i * 3 + 1] * sums[i * 3 + 2] * inv_m);
     }
   }
+  amax_commit(m, amax);
 }
 
 // weight gradient partial sums: part[split][tap][ci][co] += x[b, ci, h + dy*d - ph, w + dx*d - pw] * du[b, co, h, w]
@@ -548,12 +570,13 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
   return NSC_OK;
 }
 
-static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s) {
+static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s,
+                     bool du_amax_known = false) {
   const int T = L.k_h * L.k_w;
   if (t->tensor_wgrad && L.cin == 64)   // the forward convolution of this layer left its packed input in slot li - 1
-    return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1);
+    return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1, 64, 0, du_amax_known);
   if (t->tensor_wgrad && L.cin < 64 && L.k_h == 1 && L.k_w == 3)   // the stem: input channels zero-padded to 64
-    return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1);
+    return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1, du_amax_known);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
 #define NSC_WG(WW, KK)                                                                                              \
@@ -683,13 +706,19 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
 #define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
 #define NSC_LAUNCH_OK() NSC_CUDA_TRY(cudaGetLastError())
   // ---------------- forward (training mode) ----------------
+  // max |x| of every tensor the tensor path consumes is collected by the kernel that produces it (slot li - 1 = input of
+  // layer li; -1 = the output gradient du of the layer in backward)
+  const bool fuse_amax = t->tensor_fwd && t->tensor_bwd && t->tensor_wgrad;
+  auto amax_of = [&](int li) -> unsigned int* { return fuse_amax && li >= 1 && li <= 8 ? umma_train_amax_slot(&t->dummy, li - 1) : nullptr; };
+  unsigned int* amax_du = fuse_amax ? umma_train_amax_slot(&t->dummy, -1) : nullptr;
+  if (fuse_amax) NSC_CUDA_TRY(cudaMemsetAsync(umma_train_amax_slot(&t->dummy, 0), 0, 8 * 4 * sizeof(float), s));
   auto conv_bn = [&](int li, const float* in, float* u, float* out, int relu, const float* resid) -> int {
     const TLayer& L = t->L[li];
     const int T = L.k_h * L.k_w;
     int r;
     if (t->tensor_fwd && L.cin == 64) {
       // train-mode forward convolution on the tensor path (split fp16, fp32 accumulate): u = conv(in, w) + b
-      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s, 0, li - 1);
+      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s, fuse_amax ? 2 : 0, li - 1);
     } else {
       repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
       NSC_LAUNCH_OK();
@@ -702,19 +731,22 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     bn_stats_final_kernel<<<1, 64, 0, s>>>(t->red + 256, (int64_t)N * HW, eps, bn_momentum, t->stats + li * 128, running + li * 128);
     NSC_LAUNCH_OK();
     const int64_t total = (int64_t)N * 64 * HW;
-    bn_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, params + L.be_off, resid, out, total, HW, relu);
+    // conv_r1 layers (odd li): the output a1 is the input of layer li + 1
+    bn_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, params + L.be_off, resid, out, total, HW, relu,
+                                                    (li & 1) ? amax_of(li + 1) : nullptr);
     NSC_LAUNCH_OK();
     return NSC_OK;
   };
   NSC_RUN(conv_bn(0, x_dev, t->u0, t->a0, 1, nullptr));
-  pool_fwd_kernel<<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, t->x[0], (int64_t)N * 64 * kH, 32, 1);
+  pool_fwd_kernel<<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, t->x[0], (int64_t)N * 64 * kH, 32, 1, amax_of(1));
   NSC_LAUNCH_OK();
   const int widths[4] = {32, 32, 16, 8};
   for (int i = 0; i < 4; ++i) {
     NSC_RUN(conv_bn(1 + 2 * i, t->x[i], t->u1[i], t->a1[i], 1, nullptr));
     NSC_RUN(conv_bn(2 + 2 * i, t->a1[i], t->u2[i], t->z[i], 0, t->x[i]));
     const int st = kBlocks[i].pool;
-    pool_fwd_kernel<<<grid_for((int64_t)N * 64 * kH * widths[i] / st), 256, 0, s>>>(t->z[i], t->x[i + 1], (int64_t)N * 64 * kH, widths[i], st);
+    pool_fwd_kernel<<<grid_for((int64_t)N * 64 * kH * widths[i] / st), 256, 0, s>>>(t->z[i], t->x[i + 1], (int64_t)N * 64 * kH, widths[i], st,
+                                                                                    amax_of(3 + 2 * i));
     NSC_LAUNCH_OK();
   }
   const float* W1 = params + t->fc_off[0];
@@ -764,13 +796,13 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const int64_t total = (int64_t)N * 64 * HW;
     bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 256);
     NSC_LAUNCH_OK();
-    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16);
+    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16, amax_du);
     NSC_LAUNCH_OK();
     bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
                                                         grads + L.g_off, grads + L.be_off, grads + L.b_off, total, HW,
-                                                        1.0 / ((double)N * HW));
+                                                        1.0 / ((double)N * HW), amax_du);
     NSC_LAUNCH_OK();
-    return run_wgrad(t, L, conv_in, du_buf, grads + L.w_off, N, s);
+    return run_wgrad(t, L, conv_in, du_buf, grads + L.w_off, N, s, fuse_amax);
   };
   auto dgrad = [&](int li, const float* du, const float* resid, float* dx) -> int {
     const TLayer& L = t->L[li];

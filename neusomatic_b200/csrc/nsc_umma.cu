@@ -1362,28 +1362,36 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
 }
 
 // dW[co][ci][dy][dx] = inv_x * inv_du * sum over the CTAs of kernel row dy of part[cta][slot(dx)][half(dx) * 64 + ci][co]
+// One thread = four consecutive co of one (tap, ci): 16-byte loads, four CTAs' partials in flight, fixed order (deterministic).
 __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int nslot,
                                          WgradArgs args, const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
-  const int total = 64 * 64 * KH * KS;
+  const int total = 16 * 64 * KH * KS;
   const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i & 63, ci = (i >> 6) & 63, t = i >> 12;
+    const int co4 = i & 15, ci = (i >> 4) & 63, t = i >> 10;
     const int dy = t / KS, dx = t % KS;
     if (ci >= Cin) continue;
     int slot, half;
     if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
     else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
-    const float* p0 = part + ((size_t)slot * 128 + half * 64 + ci) * 64 + co;
-    const size_t cs = (size_t)nslot * 128 * 64;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four loads in flight; fixed order: deterministic
+    const float4* p0 = reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + half * 64 + ci) * 64) + co4;
+    const size_t cs = (size_t)nslot * 128 * 16;        // float4 per CTA partial
+    double sx[4] = {0.0, 0.0, 0.0, 0.0}, sy[4] = {0.0, 0.0, 0.0, 0.0};
     int c = args.cta_start[dy];
     const int c1 = args.cta_start[dy + 1];
     for (; c + 3 < c1; c += 4) {
-      const float a0 = p0[c * cs], a1 = p0[(c + 1) * cs], a2 = p0[(c + 2) * cs], a3 = p0[(c + 3) * cs];
-      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      const float4 a0 = __ldg(p0 + c * cs), a1 = __ldg(p0 + (c + 1) * cs), a2 = __ldg(p0 + (c + 2) * cs), a3 = __ldg(p0 + (c + 3) * cs);
+      sx[0] += a0.x; sx[1] += a0.y; sx[2] += a0.z; sx[3] += a0.w;
+      sy[0] += a1.x; sy[1] += a1.y; sy[2] += a1.z; sy[3] += a1.w;
+      sx[0] += a2.x; sx[1] += a2.y; sx[2] += a2.z; sx[3] += a2.w;
+      sy[0] += a3.x; sy[1] += a3.y; sy[2] += a3.z; sy[3] += a3.w;
     }
-    for (; c < c1; ++c) s0 += p0[c * cs];
-    dw[((co * Cin + ci) * KH + dy) * KS + dx] = (float)(((s0 + s1) + (s2 + s3)) * scale);
+    for (; c < c1; ++c) {
+      const float4 a0 = __ldg(p0 + c * cs);
+      sx[0] += a0.x; sx[1] += a0.y; sx[2] += a0.z; sx[3] += a0.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dw[(((co4 * 4 + j) * Cin + ci) * KH + dy) * KS + dx] = (float)((sx[j] + sy[j]) * scale);
   }
 }
 
@@ -1445,7 +1453,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_umma_reduce_kernel<<<(64 * 64 * Cfg::KH * Cfg::KS + 255) / 256, 256, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, Cfg::NSLOT, a, inv_x,
+  wgrad_umma_reduce_kernel<<<(16 * 64 * Cfg::KH * Cfg::KS + 127) / 128, 128, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, Cfg::NSLOT, a, inv_x,
                                                                                      u.fc_in + 2);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
@@ -1458,7 +1466,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
 // xslot >= 0: the packed x of that layer was kept by the forward convolution (umma_train_conv with the same xslot).
 // cin < 64 (the stem, kh = 1): the input channels are zero-padded to 64 in the packed operand.
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
-                     int xslot, int cin, int kh) {
+                     int xslot, int cin, int kh, bool du_amax_known) {
   if (kh <= 0) kh = k;
   UmmaState& u = m->umma;
   if (n > u.cap || u.buf[0][0] == nullptr) { set_error("umma_train_wgrad: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
@@ -1466,9 +1474,12 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   const int64_t items = (int64_t)bpad * kH * W * 8;
   const unsigned pgrid = (unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16);
   float* scl = u.fc_in;            // [0..2]: du (absmax bits, inverse scale / weight scale, inverse scale); [4..6]: x
-  NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 32, s));
-  absmax_kernel<<<148 * 4, 256, 0, s>>>(du, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
-  NSC_CUDA_TRY(cudaGetLastError());
+  NSC_CUDA_TRY(cudaMemsetAsync(scl + 4, 0, 16, s));
+  if (!du_amax_known) {      // (known: bn_bwd_apply_kernel has left max |du| at scl[0])
+    NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 16, s));
+    absmax_kernel<<<148 * 4, 256, 0, s>>>(du, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
+    NSC_CUDA_TRY(cudaGetLastError());
+  }
   pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(du, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
@@ -1499,6 +1510,11 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   return NSC_E_INVALID;
 }
 
+unsigned int* umma_train_amax_slot(nsc_model* m, int xslot) {
+  UmmaState& u = m->umma;
+  return reinterpret_cast<unsigned int*>(xslot >= 0 ? u.tscl + 4 * xslot : u.fc_in);
+}
+
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
                     const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked, int xslot) {
@@ -1513,10 +1529,12 @@ int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const 
     tin[0] = u.tpk[xslot][0]; tin[1] = u.tpk[xslot][1];
     scl = u.tscl + 4 * xslot;
   }
-  if (!prepacked) {     // (prepacked: umma_train_wgrad has left this very tensor, packed and scaled, in the workspace)
-    NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
-    absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
-    NSC_CUDA_TRY(cudaGetLastError());
+  if (prepacked != 1) {     // (prepacked = 1: umma_train_wgrad has left this very tensor, packed and scaled, in the workspace)
+    if (prepacked != 2) {   // (2: the kernel that produced `in` has left max |in| at scl[0])
+      NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
+      absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
+      NSC_CUDA_TRY(cudaGetLastError());
+    }
     pack_nchw64_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(in, tin[0], tin[1], (int)n, bpad, W, scl);
     NSC_CUDA_TRY(cudaGetLastError());
     m->launches += 2;

@@ -51,10 +51,11 @@ def main():
             ms = e0.elapsed_time(e1)
             # end to end from pinned host uint8 (65 536-candidate pool, batch by batch)
             nb2 = max(65536 // B, 1)
-            eng.score_host_u8(mats[:B], meta[:B], None, 100.0)
+            host_out = eng._host_out(B, True, pin=True)          # pinned result buffers, allocated once per batch size
+            eng.score_host_u8(mats[:B], meta[:B], None, 100.0, out=host_out)
             t0 = time.perf_counter()
             for i in range(nb2):
-                eng.score_host_u8(mats[i * B:(i + 1) * B], meta[i * B:(i + 1) * B], None, 100.0)
+                eng.score_host_u8(mats[i * B:(i + 1) * B], meta[i * B:(i + 1) * B], None, 100.0, out=host_out)
             t1 = time.perf_counter()
             row = {"batch": B, "resident_cand_per_s": nb * B / ms * 1e3, "resident_us_per_batch": ms / nb * 1e3,
                    "host_u8_cand_per_s": nb2 * B / (t1 - t0), "host_u8_us_per_batch": (t1 - t0) / nb2 * 1e6}
