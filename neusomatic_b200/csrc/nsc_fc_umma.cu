@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "nsc_common.h"
 #include "umma.cuh"
@@ -271,10 +272,11 @@ int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs
   a.B = (int)n;
   a.split = m->precision == NSC_PREC_BF16 ? 0 : 1;
   a.out = o;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // bit d: the attribute is set on device d (it is per device: one process may drive
+                                              // several GPUs, e.g. under nn.DataParallel, call.py:417-419)
+  if (!((attr_set.load() >> (m->device & 63)) & 1)) {
     NSC_CUDA_TRY(cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFcSmem));
-    attr_set = true;
+    attr_set.fetch_or(1ull << (m->device & 63));
   }
   const int grid = std::min(a.n_tiles, m->umma.num_sms);
   {

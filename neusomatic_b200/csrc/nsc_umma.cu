@@ -42,6 +42,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <type_traits>
 
 #include "nsc_common.h"
@@ -994,10 +995,11 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
     if (rc != NSC_OK) return rc;
   }
   auto kern = conv_umma_kernel<Cfg>;
-  static bool attr_set = false;   // one static per template instantiation
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // bit d: the attribute is set on device d (it is per device: one process may drive
+                                              // several GPUs, e.g. under nn.DataParallel, call.py:417-419)
+  if (!((attr_set.load() >> (m->device & 63)) & 1)) {
     NSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_set = true;
+    attr_set.fetch_or(1ull << (m->device & 63));
   }
   const int grid = (int)std::min<int64_t>(groups, m->umma.num_sms);
   {
@@ -1446,10 +1448,11 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   for (int dy = Cfg::KH + 1; dy < 6; ++dy) a.cta_start[dy] = a.cta_start[Cfg::KH];
   const int grid = a.cta_start[Cfg::KH];
   auto kern = wgrad_umma_kernel<Cfg>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // bit d: the attribute is set on device d (it is per device: one process may drive
+                                              // several GPUs, e.g. under nn.DataParallel, call.py:417-419)
+  if (!((attr_set.load() >> (m->device & 63)) & 1)) {
     NSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_set = true;
+    attr_set.fetch_or(1ull << (m->device & 63));
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());

@@ -210,6 +210,25 @@ def test_module_dropin_matches_engine_and_handles_module_prefix(golden):
     assert tuple(internals[2].shape) == (8, 1280) and tuple(internals[3].shape) == (8, 240)
 
 
+def test_module_under_dataparallel_all_visible_gpus(golden):
+    """call.py:417-419 wraps the network in nn.DataParallel: one process, one thread per GPU, every replica scores its
+    slice of the batch through its own packed engine (with one visible GPU this is the degenerate single-replica case;
+    the driver's multi-GPU boxes exercise the per-device kernel attributes and workspaces)."""
+    from neusomatic_b200.network import NeuSomaticNet
+    from neusomatic_b200.call import load_checkpoint
+    name, g, ck = golden
+    sd, meta = load_checkpoint(ck)
+    x = torch.from_numpy(_assemble(g, ck)).cuda()
+    net = NeuSomaticNet(x.shape[1]).cuda()
+    net.load_state_dict(sd, strict=False)
+    dp = torch.nn.DataParallel(net)
+    dp.eval()
+    for _ in range(2):          # second pass: the replicas reuse the engines packed by the first
+        (o1, o2, o3), _ = dp(x)
+        _check_outputs(o1.cpu().numpy(), o2.cpu().numpy(), o3.cpu().numpy(), g["o1"], g["o2"], g["o3"])
+    assert len(net._nsc["engines"]) == min(torch.cuda.device_count(), x.shape[0])
+
+
 def test_call_variants_loop_matches_oracle(golden):
     """The mirrored call_variants batch loop (call.py:54-118) over a DataLoader-shaped iterable."""
     from neusomatic_b200.network import NeuSomaticNet
