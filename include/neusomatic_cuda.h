@@ -161,7 +161,11 @@ const char* nsc_model_kernel_name(const nsc_model* m);
 
 int nsc_model_destroy(nsc_model* m);
 
-/* ---- training step (fp32 CUDA-core kernels) -----------------------------------------
+/* ---- training step -------------------------------------------------------------------
+ * The 64 -> 64 convolutions (forward, data gradient, weight gradient; the stem's weight gradient too) run on tcgen05 in
+ * split fp16 with fp32 accumulation; BatchNorm, pooling, loss and the linear layers are fp32 CUDA-core kernels.
+ * Environment, read by nsc_trainer_create: NSC_TRAIN_FP32=1 -> every convolution on the fp32 CUDA-core kernels (the
+ * bit-stable reference mode of the tests); NSC_TRAIN_TENSOR=<subset of "fwd","bwd","wgrad"> -> only those on tcgen05.
  * One optimisation step of train.py:379-383,416-441: training-mode forward (BatchNorm2d batch statistics and
  * running-stat update), loss = CrossEntropyLoss(w_type)(o1,y) + SmoothL1Loss()(o2[:,0],center) +
  * CrossEntropyLoss(w_len)(o3,y_len), loss.backward(), optim.SGD(lr, momentum).step().
@@ -184,6 +188,10 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
  * sum all-reduce; momentum buffers start at zero). */
 int nsc_sgd_momentum_update(float* params, float* momentum_buf, const float* grads, int64_t n, float lr,
                             float momentum, float grad_scale, void* stream);
+/* Debug: device pointer of an internal fp32 NCHW tensor of the last step: "u0", "a0", "x0".."x4", "u1.<i>", "a1.<i>",
+ * "u2.<i>", "z.<i>" (block i = 0..3: conv_r1 output, its BN+ReLU, conv_r2 output, residual sum before the pool),
+ * "g", "gz", "gu" (backward scratch in its final state).  Valid until the next call on the handle. */
+int nsc_trainer_debug_tensor(nsc_trainer* t, const char* name, float** ptr);
 int nsc_trainer_destroy(nsc_trainer* t);
 
 /* ---- candidate TSV decoder (host side; no GPU involved) -------------------------------------------------

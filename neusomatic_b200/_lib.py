@@ -47,6 +47,7 @@ SIGNATURES = {
     "nsc_trainer_param_slice": (_i32, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "nsc_train_forward_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp]),
     "nsc_sgd_momentum_update": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
+    "nsc_trainer_debug_tensor": (_i32, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "nsc_trainer_destroy": (_i32, [_vp]),
     "nsc_tsv_open": (_i32, [C.POINTER(_vp), C.c_char_p]),
     "nsc_tsv_count": (_i64, [_vp]),

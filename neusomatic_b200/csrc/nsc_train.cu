@@ -315,7 +315,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ u, const float* __
 constexpr int kWgLd = 68;   // floats per staged position (64 channels + 4: keeps 16-byte alignment, spreads the banks)
 template <int W, int KW>
 __global__ void __launch_bounds__(256)
-wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ part, int N, int Cin, int KH, int dil) {
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ part, int N, int Cin, int KH, int dil,
+             int c0 /* first input channel of this launch's 64-channel block (the 119-channel stem takes two launches) */) {
   const int dy = blockIdx.x, split = blockIdx.y;
   const int ph = dil * (KH - 1) / 2, pw = dil * (KW - 1) / 2;
   const int oy = dy * dil - ph;
@@ -337,7 +338,7 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* _
     __syncthreads();
     for (int i = tid; i < 64 * P; i += 256) {
       const int c = i / P, pos = i - c * P;
-      xs[pos * kWgLd + c] = c < Cin ? x[((size_t)b * Cin + c) * P + pos] : 0.f;
+      xs[pos * kWgLd + c] = c0 + c < Cin ? x[((size_t)b * Cin + c0 + c) * P + pos] : 0.f;
       ds[pos * kWgLd + c] = du[(size_t)b * 64 * P + i];
     }
     __syncthreads();
@@ -377,14 +378,14 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* _
   }
 }
 
-// dW[co][ci][tap] = sum over splits of part[split][tap][ci][co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cin, int T, int splits) {
-  const int total = 64 * Cin * T;
+// dW[co][c0 + ci][tap] = sum over splits of part[split][tap][ci][co], ci < cn (one 64-channel block of the input)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cin, int T, int splits, int c0, int cn) {
+  const int total = 64 * cn * T;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int t = i % T, ci = (i / T) % Cin, co = i / (T * Cin);
+    const int t = i % T, ci = (i / T) % cn, co = i / (T * cn);
     double s = 0.0;
     for (int sp = 0; sp < splits; ++sp) s += part[(((size_t)sp * T + t) * 64 + ci) * 64 + co];
-    dw[i] = (float)s;
+    dw[((size_t)co * Cin + c0 + ci) * T + t] = (float)s;
   }
 }
 
@@ -575,25 +576,28 @@ static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const fl
   const int T = L.k_h * L.k_w;
   if (t->tensor_wgrad && L.cin == 64)   // the forward convolution of this layer left its packed input in slot li - 1
     return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1, 64, 0, du_amax_known);
-  if (t->tensor_wgrad && L.cin < 64 && L.k_h == 1 && L.k_w == 3)   // the stem: input channels zero-padded to 64
+  if (t->tensor_wgrad && L.k_h == 1 && L.k_w == 3)   // the stem: 64-channel blocks of the input, zero-padded
     return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1, du_amax_known);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
+  for (int c0 = 0; c0 < L.cin; c0 += 64) {      // 64 input channels per launch (the ensemble stem has 119)
 #define NSC_WG(WW, KK)                                                                                              \
   do {                                                                                                              \
     NSC_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<WW, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wgrad_kernel<WW, KK><<<grid, 256, smem, s>>>(xin, du, t->wpart, N, L.cin, L.k_h, L.dil);                           \
+    wgrad_kernel<WW, KK><<<grid, 256, smem, s>>>(xin, du, t->wpart, N, L.cin, L.k_h, L.dil, c0);                       \
   } while (0)
-  if (L.W == 32 && L.k_w == 3) NSC_WG(32, 3);
-  else if (L.W == 32) NSC_WG(32, 5);
-  else if (L.W == 16 && L.k_w == 3) NSC_WG(16, 3);
-  else if (L.W == 16) NSC_WG(16, 5);
-  else if (L.k_w == 3) NSC_WG(8, 3);
-  else NSC_WG(8, 5);
+    if (L.W == 32 && L.k_w == 3) NSC_WG(32, 3);
+    else if (L.W == 32) NSC_WG(32, 5);
+    else if (L.W == 16 && L.k_w == 3) NSC_WG(16, 3);
+    else if (L.W == 16) NSC_WG(16, 5);
+    else if (L.k_w == 3) NSC_WG(8, 3);
+    else NSC_WG(8, 5);
 #undef NSC_WG
-  NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_reduce_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(t->wpart, dw, L.cin, T, kWgSplits);
-  NSC_CUDA_TRY(cudaGetLastError());
+    NSC_CUDA_TRY(cudaGetLastError());
+    const int cn = std::min(64, L.cin - c0);
+    wgrad_reduce_kernel<<<grid_for((int64_t)64 * cn * T), 256, 0, s>>>(t->wpart, dw, L.cin, T, kWgSplits, c0, cn);
+    NSC_CUDA_TRY(cudaGetLastError());
+  }
   return NSC_OK;
 }
 
@@ -688,6 +692,28 @@ int nsc_trainer_param_slice(const nsc_trainer* t, const char* name, int64_t* off
     if (s.first == name) { *offset = s.second.first; *numel = s.second.second; return NSC_OK; }
   set_error("unknown parameter '%s'", name);
   return NSC_E_INVALID;
+}
+
+// Debug: device pointer of an internal fp32 NCHW tensor of the last step ("u0","a0","x0".."x4","u1.<i>","a1.<i>","u2.<i>",
+// "z.<i>" = forward tensors of block i; "g","gz","gu" = the backward scratch tensors in their final state)
+int nsc_trainer_debug_tensor(nsc_trainer* t, const char* name, float** ptr) {
+  if (!t || !name || !ptr) { set_error("NULL argument"); return NSC_E_INVALID; }
+  const std::string n(name);
+  float* p = nullptr;
+  if (n == "u0") p = t->u0;
+  else if (n == "a0") p = t->a0;
+  else if (n == "g") p = t->gA;
+  else if (n == "gz") p = t->gB;
+  else if (n == "gu") p = t->gC;
+  else if (n.size() == 2 && n[0] == 'x' && n[1] >= '0' && n[1] <= '4') p = t->x[n[1] - '0'];
+  else if (n.size() == 4 && n[2] == '.' && n[3] >= '0' && n[3] <= '3') {
+    const int i = n[3] - '0';
+    const std::string k = n.substr(0, 2);
+    p = k == "u1" ? t->u1[i] : k == "a1" ? t->a1[i] : k == "u2" ? t->u2[i] : nullptr;
+  } else if (n.size() == 3 && n[0] == 'z' && n[1] == '.' && n[2] >= '0' && n[2] <= '3') p = t->z[n[2] - '0'];
+  if (!p) { set_error("unknown tensor '%s'", name); return NSC_E_INVALID; }
+  *ptr = p;
+  return NSC_OK;
 }
 
 int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* running, const float* x_dev, const int32_t* type_labels,

@@ -1138,7 +1138,7 @@ constexpr float kTrainWScale = 256.f;
 // scale) is left at scl[1] for the epilogue of the convolution.
 __global__ void __launch_bounds__(256)
 pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B, int Bpad, int W,
-                   float* __restrict__ scl, int C = 64) {
+                   float* __restrict__ scl, int C = 64, int c0 = 0) {
   float scale = 1.f;
   {
     const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scl)[0]);
@@ -1155,7 +1155,8 @@ pack_nchw64_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint
     const int64_t b = r / kH;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (b < B && c8 * 8 + j < C) ? __ldg(in + ((b * C + c8 * 8 + j) * kH + h) * W + w) * scale : 0.f;
+    for (int j = 0; j < 8; ++j)
+      v[j] = (b < B && c0 + c8 * 8 + j < C) ? __ldg(in + ((b * C + c0 + c8 * 8 + j) * kH + h) * W + w) * scale : 0.f;
     uint4 a, l;
     split8(v, a, l);
     const size_t off = (((((size_t)(b >> 3)) * kH + h) * W + w) * 8 + (b & 7)) * 64 + c8 * 8;
@@ -1365,14 +1366,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
 
 // dW[co][ci][dy][dx] = inv_x * inv_du * sum over the CTAs of kernel row dy of part[cta][slot(dx)][half(dx) * 64 + ci][co]
 // One thread = four consecutive co of one (tap, ci): 16-byte loads, four CTAs' partials in flight, fixed order (deterministic).
-__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int nslot,
+__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int c0, int nslot,
                                          WgradArgs args, const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
   const int total = 16 * 64 * KH * KS;
   const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co4 = i & 15, ci = (i >> 4) & 63, t = i >> 10;
     const int dy = t / KS, dx = t % KS;
-    if (ci >= Cin) continue;
+    if (c0 + ci >= Cin) continue;
     int slot, half;
     if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
     else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
@@ -1393,7 +1394,7 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* 
       sx[0] += a0.x; sx[1] += a0.y; sx[2] += a0.z; sx[3] += a0.w;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dw[(((co4 * 4 + j) * Cin + ci) * KH + dy) * KS + dx] = (float)((sx[j] + sy[j]) * scale);
+    for (int j = 0; j < 4; ++j) dw[(((co4 * 4 + j) * Cin + c0 + ci) * KH + dy) * KS + dx] = (float)((sx[j] + sy[j]) * scale);
   }
 }
 
@@ -1417,7 +1418,7 @@ static int make_row_tmap(CUtensorMap* tm, void* base, int64_t groups, int W, int
 }
 
 template <class Cfg>
-static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* const xpk[2], const float* inv_x, int cin,
+static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* const xpk[2], const float* inv_x, int cin, int c0,
                              cudaStream_t s) {
   UmmaState& u = m->umma;
   CUtensorMap tdh, tdl, txh, txl;
@@ -1456,7 +1457,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_umma_reduce_kernel<<<(16 * 64 * Cfg::KH * Cfg::KS + 127) / 128, 128, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, Cfg::NSLOT, a, inv_x,
+  wgrad_umma_reduce_kernel<<<(16 * 64 * Cfg::KH * Cfg::KS + 127) / 128, 128, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, c0, Cfg::NSLOT, a, inv_x,
                                                                                      u.fc_in + 2);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
@@ -1494,14 +1495,26 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   } else {
     absmax_kernel<<<148 * 4, 256, 0, s>>>(x, n * cin * kH * W, reinterpret_cast<unsigned int*>(scl + 4));
     NSC_CUDA_TRY(cudaGetLastError());
-    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4, cin);
+    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4, cin, 0);
     NSC_CUDA_TRY(cudaGetLastError());
     m->launches += 2;
   }
   const int64_t groups = bpad / 8;
+  if (kh == 1 && k == 3 && dil == 1 && W == 32) {
+    // the stem: one pass per 64-channel block of the input (C = 26: one, C = 119: two), same scale for all blocks
+    for (int c0 = 0; c0 < cin; c0 += 64) {
+      if (c0 > 0) {
+        pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(x, xpk[0], xpk[1], (int)n, bpad, W, scl + 4, cin, c0);
+        NSC_CUDA_TRY(cudaGetLastError());
+        m->launches += 1;
+      }
+      const int rc = launch_wgrad_umma<WgCfg<3, 1, 32, 1>>(m, groups, dw, xpk, inv_x, cin, c0, s);
+      if (rc != NSC_OK) return rc;
+    }
+    return NSC_OK;
+  }
 #define NSC_WG(KK, DD, WW) \
-  if (kh == k && k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, xpk, inv_x, cin, s)
-  if (kh == 1 && k == 3 && dil == 1 && W == 32) return launch_wgrad_umma<WgCfg<3, 1, 32, 1>>(m, groups, dw, xpk, inv_x, cin, s);
+  if (kh == k && k == KK && dil == DD && W == WW) return launch_wgrad_umma<WgCfg<KK, DD, WW>>(m, groups, dw, xpk, inv_x, cin, 0, s)
   NSC_WG(3, 1, 32);
   NSC_WG(5, 1, 32);
   NSC_WG(3, 2, 16);

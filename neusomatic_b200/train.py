@@ -73,6 +73,16 @@ class Trainer:
             out[bn + ".running_var"] = self.running[i * 128 + 64:i * 128 + 128].cpu().clone()
         return out
 
+    def debug_tensor(self, name, shape):
+        """Copy of an internal fp32 NCHW tensor of the last step (nsc_trainer_debug_tensor), as a CUDA tensor of `shape`."""
+        ptr = C.c_void_p()
+        _lib.check(self.lib.nsc_trainer_debug_tensor(self.h, name.encode(), C.byref(ptr)))
+        class _View:      # zero-copy view of library-owned device memory through the CUDA array interface
+            __cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": "<f4", "data": (int(ptr.value), False),
+                                        "version": 2}
+        torch.cuda.current_stream(self.dev).synchronize()
+        return torch.as_tensor(_View(), device=self.dev).clone()
+
     def grad(self, name):
         off, num = self.slices[name]
         return self.grads[off:off + num]

@@ -33,3 +33,23 @@ for i in range(4):
     print("block", i, "max|g bn_r1.bias| %.3e" % gb.abs().max().item())
     for j in idx:
         print("   |z1| = %.2e   dL/dy1 = %.3e   (ratio to max bias grad %.2e)" % (a[j].item(), y1.grad.flatten()[j].item(), abs(y1.grad.flatten()[j].item()) / gb.abs().max().item()))
+
+
+# ---- max-pool windows whose two largest values nearly tie (the other discontinuity of the backward pass) ----------------
+if "--pools" in sys.argv:
+    def near_ties(t, st, name):
+        W = t.shape[-1]
+        pad = F.pad(t.detach(), (1, 1), value=float("-inf"))
+        win = torch.stack([pad[..., 0:W:st], pad[..., 1:W + 1:st], pad[..., 2:W + 2:st]], -1)
+        top2 = win.topk(2, dim=-1).values
+        gap = top2[..., 0] - top2[..., 1]
+        idx = torch.nonzero((gap > 0) & (gap < 3e-6 * t.detach().abs().max()))
+        print("%-8s pool windows with 0 < (max - second) < 3e-6 * max|z|: %d   [sample, channel, row, output column]: %s" % (
+            name, len(idx), idx[:8].tolist()))
+    h2 = F.max_pool2d(F.relu(bn(F.conv2d(x, p["conv1.weight"], p["conv1.bias"], padding=(0, 1)), "bn1")), (1, 3), stride=(1, 1), padding=(0, 1))
+    for i, (k1, k2, d1, d2, st) in enumerate(tp.NSBLOCKS):
+        pre = "res_layers.%d." % i
+        y1 = F.relu(bn(F.conv2d(h2, p[pre + "conv_r1.weight"], p[pre + "conv_r1.bias"], dilation=d1, padding=(d1 * (k1 - 1)) // 2), pre + "bn_r1"))
+        z = h2 + bn(F.conv2d(y1, p[pre + "conv_r2.weight"], p[pre + "conv_r2.bias"], dilation=d2, padding=(d2 * (k2 - 1)) // 2), pre + "bn_r2")
+        near_ties(z, st, "block %d" % i)
+        h2 = F.max_pool2d(z, (1, 3), stride=(1, st), padding=(0, 1))
