@@ -156,10 +156,16 @@ int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o
 int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255, float coverage_thr,
                           int64_t n, const Outputs& o, cudaStream_t s);
 // training step on the tensor path (nsc_umma.cu): workspace of the trainer's private model handle, fp32 NCHW convolutions
+// state of the activation / gradient operand `in` of umma_train_conv when it is called
+enum : int {
+  kOperandRaw = 0,        // fp32 NCHW only: take max |in|, rescale, split and pack it
+  kOperandPacked = 1,     // umma_train_wgrad has just left this very tensor, packed and rescaled, in the workspace
+  kOperandAmaxKnown = 2,  // the kernel that produced `in` has left max |in| in the operand's scale slot: pack only
+};
 int umma_train_init(nsc_model* m, int64_t max_batch);
 void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked = 0, int xslot = -1);
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand = kOperandRaw, int xslot = -1);
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
                      int xslot = -1, int cin = 64, int kh = 0, bool du_amax_known = false);
 // where the producer of a tensor leaves max |x| (bit pattern of a float): xslot 0..7 = input of the 64 -> 64 layer, -1 = du

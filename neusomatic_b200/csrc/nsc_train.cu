@@ -744,7 +744,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     int r;
     if (t->tensor_fwd && L.cin == 64) {
       // train-mode forward convolution on the tensor path (split fp16, fp32 accumulate): u = conv(in, w) + b
-      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s, fuse_amax ? 2 : 0, li - 1);
+      r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s,
+                          fuse_amax ? kOperandAmaxKnown : kOperandRaw, li - 1);
     } else {
       repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
       NSC_LAUNCH_OK();
@@ -835,7 +836,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const int T = L.k_h * L.k_w;
     if (t->tensor_bwd)   // data gradient = the same convolution with swapped channels and flipped taps
       return umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, du, params + L.w_off, 1, t->zeros, resid, dx, N, s,
-                             /*prepacked: the weight gradient of this layer has just packed du*/ t->tensor_wgrad ? 1 : 0);
+                             /* the weight gradient of this layer has just packed du */ t->tensor_wgrad ? kOperandPacked : kOperandRaw);
     repack_w_kernel<<<grid_for((int64_t)64 * 64 * T), 256, 0, s>>>(params + L.w_off, t->wf, t->wb, 64, T);
     NSC_LAUNCH_OK();
     return fp32_conv_generic(&t->dummy, L.k_h, L.dil, L.W, du, t->wb, t->zeros, resid, dx, N, 64, s);

@@ -503,9 +503,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
       }
     };
+    // training (fp32 NCHW addend): the W segments of this thread's (candidate, channel) pairs for the NEXT image row, loaded
+    // at the end of the previous row so that they are in flight across the barrier, the TMEM load and the staging phase
+    constexpr int NPAIR = Cfg::NCHW ? (Cfg::RPW * 64 / kEpiThreads) : 1, NWQ = Cfg::TW / 4;
+    float4 rn[NPAIR][NWQ];
+    auto load_res_nchw = [&](int grp_, int sub_, uint32_t u_, int idx_) {
+      const int slot_ = (u_ & 1) ? idx_ : (idx_ < 2 ? 3 + idx_ : idx_ - 2);
+      const int h_ = slot_row<DIL>(slot_);
+#pragma unroll
+      for (int k = 0; k < NPAIR; ++k) {
+        const int pi = et + k * kEpiThreads, c = pi & 63, mg = pi >> 6;
+        const int64_t b = ((int64_t)grp_ * Cfg::GP + (mg >> 3)) * 8 + (mg & 7);
+        const float4* src = reinterpret_cast<const float4*>(args.res_nchw + ((b * 64 + c) * kH + h_) * W + sub_ * Cfg::TW);
+#pragma unroll
+        for (int wq = 0; wq < NWQ; ++wq) rn[k][wq] = b < args.B ? __ldg(src + wq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
       for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
         if (args.res_hi != nullptr) load_res(grp, sub, u_it, 0);
+        if (Cfg::NCHW && args.res_nchw != nullptr) load_res_nchw(grp, sub, u_it, 0);
         long long t_c = clock64();
         mbar_wait(acc_full, u_it & 1);
         t_full += clock64() - t_c;
@@ -625,29 +642,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             // pairs and walks the unit's TW columns: 16-byte stores into the contiguous W axis of [b][c][h][:], consecutive
             // lanes = consecutive channels (conflict-free staging reads)
             const float osc = args.out_scale != nullptr ? __ldg(args.out_scale) : 1.f;
-#pragma unroll 1
-            for (int pi = et; pi < Cfg::RPW * 64; pi += kEpiThreads) {
-              const int c = pi & 63, mg = pi >> 6;
+            const bool has_res = args.res_nchw != nullptr;
+#pragma unroll
+            for (int k = 0; k < NPAIR; ++k) {
+              const int pi = et + k * kEpiThreads, c = pi & 63, mg = pi >> 6;
               const int64_t b = ((int64_t)grp * Cfg::GP + (mg >> 3)) * 8 + (mg & 7);
               if (b >= args.B) continue;
               const int64_t o = ((b * 64 + c) * kH + h) * W + w0;
               const float bs = bias_s[c];
               const int lc = c >> 2;
 #pragma unroll
-              for (int wq = 0; wq < Cfg::TW / 4; ++wq) {
+              for (int wq = 0; wq < NWQ; ++wq) {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int rr = (wq * 4 + j) * Cfg::RPW + mg;
                   v[j] = stg[rr * 64 + (((lc & 8) | ((lc ^ rr) & 7)) << 2) + (c & 3)] * osc + bs;
                 }
-                if (args.res_nchw != nullptr) {
-                  const float4 r4 = *reinterpret_cast<const float4*>(args.res_nchw + o + wq * 4);
-                  v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                }
+                if (has_res) { v[0] += rn[k][wq].x; v[1] += rn[k][wq].y; v[2] += rn[k][wq].z; v[3] += rn[k][wq].w; }
                 *reinterpret_cast<float4*>(args.out_nchw + o + wq * 4) = make_float4(v[0], v[1], v[2], v[3]);
               }
             }
+            if (has_res && idx + 1 < kH) load_res_nchw(grp, sub, u_it, idx + 1);
             epi_bar();   // staging is rewritten by the next row
             continue;
           }
@@ -1533,7 +1549,7 @@ unsigned int* umma_train_amax_slot(nsc_model* m, int xslot) {
 
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int prepacked, int xslot) {
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand, int xslot) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_conv: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
@@ -1545,8 +1561,8 @@ int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const 
     tin[0] = u.tpk[xslot][0]; tin[1] = u.tpk[xslot][1];
     scl = u.tscl + 4 * xslot;
   }
-  if (prepacked != 1) {     // (prepacked = 1: umma_train_wgrad has left this very tensor, packed and scaled, in the workspace)
-    if (prepacked != 2) {   // (2: the kernel that produced `in` has left max |in| at scl[0])
+  if (operand != kOperandPacked) {
+    if (operand != kOperandAmaxKnown) {
       NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 8, s));
       absmax_kernel<<<148 * 4, 256, 0, s>>>(in, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
       NSC_CUDA_TRY(cudaGetLastError());
