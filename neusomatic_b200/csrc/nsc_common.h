@@ -167,7 +167,13 @@ void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
                     const float* resid, float* out, int64_t n, cudaStream_t s, int operand = kOperandRaw, int xslot = -1);
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
-                     int xslot = -1, int cin = 64, int kh = 0, bool du_amax_known = false);
+                     int xslot = -1, int cin = 64, int kh = 0, int du_state = 0 /* 1: max |du| known, 2: du already packed */);
+// BatchNorm backward written straight into the packed, rescaled operand of the weight / data gradient (no fp32 du):
+// du = gamma invstd (dy [masked by relu_src > 0] - sum(dy)/M - xhat sum(dy xhat)/M); sums = [64][3] from bn_bwd_final_kernel,
+// the bound of max |du| must already be in the du scale slot (umma_train_amax_slot(m, -1)).
+int umma_train_bn_bwd_pack(nsc_model* m, int W, const float* u, const float* stats, const float* gamma, const float* dy,
+                           const float* relu_src, const double* sums, float* dgamma, float* dbeta, float* dbias, int64_t n,
+                           double inv_m, cudaStream_t s);
 // where the producer of a tensor leaves max |x| (bit pattern of a float): xslot 0..7 = input of the 64 -> 64 layer, -1 = du
 unsigned int* umma_train_amax_slot(nsc_model* m, int xslot);
 // nsc_fc_umma.cu

@@ -224,13 +224,15 @@ __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __res
 
 // per-channel sums for the BatchNorm backward: sum(dy), sum(dy * xhat), sum(xhat); dy is masked by (mask_src > 0) when
 // given.  sum(xhat) (rounding noise of the fp32 mean) gives the gradient of the convolution bias in front of the
-// BatchNorm without another pass: sum(du) = -gamma * invstd * sum(dy * xhat) * sum(xhat) / M.
+// BatchNorm without another pass: sum(du) = -gamma * invstd * sum(dy * xhat) * sum(xhat) / M.  max |dy| and max |xhat| bound
+// |du| from above before du exists, which lets bn_bwd_apply_pack_kernel write du already rescaled and packed.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ dy,
-                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][3]*/) {
+                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][5]*/) {
   const int c = blockIdx.x, sp = blockIdx.y;
   const float mean = stats[c], invstd = stats[64 + c];
   double s = 0.0, sx = 0.0, sh1 = 0.0;
+  float gmax = 0.f, xmax = 0.f;
   const int HW4 = HW >> 2, total4 = N * HW4;      // 16-byte loads, 32-bit index arithmetic
   for (int i = sp * 256 + threadIdx.x; i < total4; i += 256 * kRedSplits) {
     const int n = i / HW4, r = i - n * HW4;
@@ -251,37 +253,56 @@ bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stat
       s += g[j];
       sx += (double)g[j] * (double)xh[j];
       sh1 += xh[j];
+      gmax = fmaxf(gmax, fabsf(g[j]));
+      xmax = fmaxf(xmax, fabsf(xh[j]));
     }
   }
-  __shared__ double sh[3][256];
+  __shared__ double sh[5][256];
   sh[0][threadIdx.x] = s;
   sh[1][threadIdx.x] = sx;
   sh[2][threadIdx.x] = sh1;
+  sh[3][threadIdx.x] = gmax;
+  sh[4][threadIdx.x] = xmax;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
       sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+      sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]); sh[4][threadIdx.x] = fmax(sh[4][threadIdx.x], sh[4][threadIdx.x + o]);
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    double* o = sums + (c * kRedSplits + sp) * 3;
-    o[0] = sh[0][0]; o[1] = sh[1][0]; o[2] = sh[2][0];
+    double* o = sums + (c * kRedSplits + sp) * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) o[j] = sh[j][0];
   }
 }
 
-// [64][splits][3] -> [64][3]
-__global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums, unsigned int* __restrict__ amax) {
+// [64][splits][5] -> [64][3] sums; `amax` (when given) receives the bit pattern of an upper bound of max |du| over the tensor:
+//   |du| <= |gamma| invstd (max|dy| + |sum(dy)| / M + max|xhat| |sum(dy xhat)| / M)         (bound_only)
+// or is reset to zero for bn_bwd_apply_kernel, which collects the exact maximum while it writes du.
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __restrict__ sums, unsigned int* __restrict__ amax,
+                                    const float* __restrict__ gamma, const float* __restrict__ stats, double inv_m, int bound_only) {
   const int c = threadIdx.x;
   if (c >= 64) return;
-  if (c == 0 && amax != nullptr) *amax = 0u;      // max |du| is collected by bn_bwd_apply_kernel, which runs next
-  double a = 0.0, b = 0.0, d = 0.0;
+  double a = 0.0, b = 0.0, d = 0.0, gm = 0.0, xm = 0.0;
   for (int sp = 0; sp < kRedSplits; ++sp) {
-    a += part[(c * kRedSplits + sp) * 3]; b += part[(c * kRedSplits + sp) * 3 + 1]; d += part[(c * kRedSplits + sp) * 3 + 2];
+    const double* p = part + (c * kRedSplits + sp) * 5;
+    a += p[0]; b += p[1]; d += p[2]; gm = fmax(gm, p[3]); xm = fmax(xm, p[4]);
   }
   sums[c * 3] = a;
   sums[c * 3 + 1] = b;
   sums[c * 3 + 2] = d;
+  if (amax == nullptr) return;
+  if (!bound_only) { if (c == 0) *amax = 0u; return; }
+  __shared__ float bnd[64];
+  bnd[c] = (float)(fabs((double)gamma[c]) * (double)stats[64 + c] * (gm + fabs(a) * inv_m + xm * fabs(b) * inv_m)) * 1.0001f;
+  __syncthreads();
+  if (c == 0) {
+    float m = 0.f;
+    for (int j = 0; j < 64; ++j) m = fmaxf(m, bnd[j]);
+    *amax = (m > 0.f && m < INFINITY) ? __float_as_uint(m) : 0u;
+  }
 }
 
 // du = gamma * invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M); also writes dgamma, dbeta and the gradient of the
@@ -571,13 +592,14 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
   return NSC_OK;
 }
 
+// du_state: 0 = fp32 du only, 1 = max |du| known (left by bn_bwd_apply_kernel), 2 = du already packed in the workspace
 static int run_wgrad(nsc_trainer* t, const TLayer& L, const float* xin, const float* du, float* dw, int N, cudaStream_t s,
-                     bool du_amax_known = false) {
+                     int du_state = 0) {
   const int T = L.k_h * L.k_w;
   if (t->tensor_wgrad && L.cin == 64)   // the forward convolution of this layer left its packed input in slot li - 1
-    return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1, 64, 0, du_amax_known);
+    return umma_train_wgrad(&t->dummy, L.k_h, L.dil, L.W, xin, du, dw, N, s, t->tensor_fwd ? (int)(&L - t->L) - 1 : -1, 64, 0, du_state);
   if (t->tensor_wgrad && L.k_h == 1 && L.k_w == 3)   // the stem: 64-channel blocks of the input, zero-padded
-    return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1, du_amax_known);
+    return umma_train_wgrad(&t->dummy, L.k_w, L.dil, L.W, xin, du, dw, N, s, -1, L.cin, 1, du_state);
   const size_t smem = (size_t)2 * kWgLd * kH * L.W * sizeof(float);
   dim3 grid(L.k_h, kWgSplits);
   for (int c0 = 0; c0 < L.cin; c0 += 64) {      // 64 input channels per launch (the ensemble stem has 119)
@@ -671,7 +693,7 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   e = e ? e : alloc(&t->logits, (size_t)max_batch * 9 * 4); e = e ? e : alloc(&t->dlogits, (size_t)max_batch * 9 * 4);
   e = e ? e : alloc(&t->gA, full); e = e ? e : alloc(&t->gB, full); e = e ? e : alloc(&t->gC, full);
   e = e ? e : alloc(&t->stats, 9 * 128 * 4);
-  e = e ? e : cudaMalloc((void**)&t->red, (256 + 64 * kRedSplits * 3) * sizeof(double));
+  e = e ? e : cudaMalloc((void**)&t->red, (512 + 64 * kRedSplits * 5) * sizeof(double));
   e = e ? e : alloc(&t->wf, (size_t)25 * 128 * 64 * 4); e = e ? e : alloc(&t->wb, (size_t)25 * 64 * 64 * 4);
   e = e ? e : alloc(&t->wpart, (size_t)kWgSplits * 25 * 64 * 64 * 4);
   t->gpart_floats = std::max<size_t>((size_t)4 * max_batch * kFcHidden, (size_t)4 * kFcHidden * kFcIn);
@@ -753,9 +775,9 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     }
     if (r != NSC_OK) return r;
     const int HW = kH * L.W;
-    bn_stats_partial_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, N, HW, t->red + 256);
+    bn_stats_partial_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, N, HW, t->red + 512);
     NSC_LAUNCH_OK();
-    bn_stats_final_kernel<<<1, 64, 0, s>>>(t->red + 256, (int64_t)N * HW, eps, bn_momentum, t->stats + li * 128, running + li * 128);
+    bn_stats_final_kernel<<<1, 64, 0, s>>>(t->red + 512, (int64_t)N * HW, eps, bn_momentum, t->stats + li * 128, running + li * 128);
     NSC_LAUNCH_OK();
     const int64_t total = (int64_t)N * 64 * HW;
     // conv_r1 layers (odd li): the output a1 is the input of layer li + 1
@@ -821,15 +843,25 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const TLayer& L = t->L[li];
     const int HW = kH * L.W;
     const int64_t total = (int64_t)N * 64 * HW;
-    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 256);
+    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 512);
     NSC_LAUNCH_OK();
-    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 256, t->red + 16, amax_du);
+    // default path: du is never written in fp32 -- its bound is known from the sums, and it is written rescaled, split
+    // and packed for the weight- and data-gradient kernels (umma_train_bn_bwd_pack)
+    const bool du_packed = fuse_amax && (L.cin == 64 || (L.k_h == 1 && L.k_w == 3));
+    bn_bwd_final_kernel<<<1, 64, 0, s>>>(t->red + 512, t->red + 16, amax_du, params + L.g_off, t->stats + li * 128, 1.0 / ((double)N * HW),
+                                         du_packed ? 1 : 0);
     NSC_LAUNCH_OK();
-    bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
-                                                        grads + L.g_off, grads + L.be_off, grads + L.b_off, total, HW,
-                                                        1.0 / ((double)N * HW), amax_du);
-    NSC_LAUNCH_OK();
-    return run_wgrad(t, L, conv_in, du_buf, grads + L.w_off, N, s, fuse_amax);
+    if (du_packed) {
+      int r = umma_train_bn_bwd_pack(&t->dummy, L.W, u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, grads + L.g_off,
+                                     grads + L.be_off, grads + L.b_off, N, 1.0 / ((double)N * HW), s);
+      if (r != NSC_OK) return r;
+    } else {
+      bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
+                                                          grads + L.g_off, grads + L.be_off, grads + L.b_off, total, HW,
+                                                          1.0 / ((double)N * HW), amax_du);
+      NSC_LAUNCH_OK();
+    }
+    return run_wgrad(t, L, conv_in, du_buf, grads + L.w_off, N, s, du_packed ? 2 : (fuse_amax ? 1 : 0));
   };
   auto dgrad = [&](int li, const float* du, const float* resid, float* dx) -> int {
     const TLayer& L = t->L[li];

@@ -1486,7 +1486,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
 // xslot >= 0: the packed x of that layer was kept by the forward convolution (umma_train_conv with the same xslot).
 // cin < 64 (the stem, kh = 1): the input channels are zero-padded to 64 in the packed operand.
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
-                     int xslot, int cin, int kh, bool du_amax_known) {
+                     int xslot, int cin, int kh, int du_state) {
   if (kh <= 0) kh = k;
   UmmaState& u = m->umma;
   if (n > u.cap || u.buf[0][0] == nullptr) { set_error("umma_train_wgrad: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
@@ -1495,14 +1495,17 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
   const unsigned pgrid = (unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16);
   float* scl = u.fc_in;            // [0..2]: du (absmax bits, inverse scale / weight scale, inverse scale); [4..6]: x
   NSC_CUDA_TRY(cudaMemsetAsync(scl + 4, 0, 16, s));
-  if (!du_amax_known) {      // (known: bn_bwd_apply_kernel has left max |du| at scl[0])
+  if (du_state == 0) {      // (1: bn_bwd_apply_kernel has left max |du| at scl[0])
     NSC_CUDA_TRY(cudaMemsetAsync(scl, 0, 16, s));
     absmax_kernel<<<148 * 4, 256, 0, s>>>(du, n * 64 * kH * W, reinterpret_cast<unsigned int*>(scl));
     NSC_CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
   }
-  pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(du, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
-  NSC_CUDA_TRY(cudaGetLastError());
-  m->launches += 2;
+  if (du_state != 2) {      // (2: umma_train_bn_bwd_pack has written du packed)
+    pack_nchw64_kernel<<<pgrid, 256, 0, s>>>(du, u.xin[0], u.xin[1], (int)n, bpad, W, scl);
+    NSC_CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
+  }
   uint16_t* xpk[2] = {u.buf[0][0], u.buf[0][1]};
   const float* inv_x = scl + 6;
   if (xslot >= 0 && u.tpk[xslot][0] != nullptr) {
@@ -1540,6 +1543,78 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
 #undef NSC_WG
   set_error("umma_train_wgrad: no tensor configuration for k=%dx%d dil=%d W=%d", kh, k, dil, W);
   return NSC_E_INVALID;
+}
+
+// BatchNorm backward in the mapping of pack_nchw64_kernel: one thread = 8 channels of one (candidate, row, column); du leaves
+// rescaled (power of two from the bound at scl[0]), split and packed; candidates >= B are zero.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_pack_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
+                         const float* __restrict__ dy, const float* __restrict__ mask_src, const double* __restrict__ sums,
+                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dbias, int B, int Bpad, int W, double inv_m, float* __restrict__ scl) {
+  __shared__ float cg[64], cm[64], ci[64], c0s[64], c1s[64];      // gamma * invstd, mean, invstd, sum(dy)/M, sum(dy xhat)/M
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    cm[c] = stats[c];
+    ci[c] = stats[64 + c];
+    cg[c] = gamma[c] * stats[64 + c];
+    c0s[c] = (float)(sums[c * 3] * inv_m);
+    c1s[c] = (float)(sums[c * 3 + 1] * inv_m);
+    if (blockIdx.x == 0) {
+      dgamma[c] = (float)sums[c * 3 + 1];
+      dbeta[c] = (float)sums[c * 3];
+      dbias[c] = (float)(-(double)gamma[c] * (double)stats[64 + c] * sums[c * 3 + 1] * sums[c * 3 + 2] * inv_m);
+    }
+  }
+  __syncthreads();
+  float scale = 1.f;
+  {
+    const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(scl)[0]);
+    if (m > 0.f) scale = exp2f(floorf(log2f(16384.f / m)));
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scl[1] = 1.f / (scale * kTrainWScale); scl[2] = 1.f / scale; }
+  }
+  const int64_t total = (int64_t)Bpad * kH * W * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t r = i / W;
+    const int c8 = (int)(r % 8);
+    r /= 8;
+    const int h = (int)(r % kH);
+    const int64_t b = r / kH;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      float dv = 0.f;
+      if (b < B) {
+        const int64_t idx = ((b * 64 + c) * kH + h) * W + w;
+        float g = __ldg(dy + idx);
+        if (mask_src != nullptr && !(__ldg(mask_src + idx) > 0.f)) g = 0.f;
+        const float xhat = (__ldg(u + idx) - cm[c]) * ci[c];
+        dv = cg[c] * (g - c0s[c] - xhat * c1s[c]);
+      }
+      v[j] = dv * scale;
+    }
+    uint4 a, l;
+    split8(v, a, l);
+    const size_t off = (((((size_t)(b >> 3)) * kH + h) * W + w) * 8 + (b & 7)) * 64 + c8 * 8;
+    *reinterpret_cast<uint4*>(hi + off) = a;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+int umma_train_bn_bwd_pack(nsc_model* m, int W, const float* u_, const float* stats, const float* gamma, const float* dy,
+                           const float* relu_src, const double* sums, float* dgamma, float* dbeta, float* dbias, int64_t n,
+                           double inv_m, cudaStream_t s) {
+  UmmaState& u = m->umma;
+  if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_bn_bwd_pack: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
+  const int bpad = (int)((n + 15) / 16 * 16);
+  const int64_t items = (int64_t)bpad * kH * W * 8;
+  bn_bwd_apply_pack_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(
+      u_, stats, gamma, dy, relu_src, sums, u.xin[0], u.xin[1], dgamma, dbeta, dbias, (int)n, bpad, W, inv_m, u.fc_in);
+  NSC_CUDA_TRY(cudaGetLastError());
+  m->launches += 1;
+  return NSC_OK;
 }
 
 unsigned int* umma_train_amax_slot(nsc_model* m, int xslot) {
