@@ -158,7 +158,9 @@ __device__ __forceinline__ void amax_commit(float m, unsigned int* __restrict__ 
   if (amax == nullptr) return;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax, __float_as_uint(m));
+  // most warps see a value that is already covered: read first, so that ~10 k atomics on one address do not serialise
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(amax))
+    atomicMax(amax, __float_as_uint(m));
 }
 
 __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,

@@ -1381,36 +1381,44 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tm_du_hi, const __grid_con
 }
 
 // dW[co][ci][dy][dx] = inv_x * inv_du * sum over the CTAs of kernel row dy of part[cta][slot(dx)][half(dx) * 64 + ci][co]
-// One thread = four consecutive co of one (tap, ci): 16-byte loads, four CTAs' partials in flight, fixed order (deterministic).
-__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int c0, int nslot,
-                                         WgradArgs args, const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
+// Block = 32 outputs (four consecutive co of one (tap, ci) each, 16-byte loads) x 8 slices of the CTA range; the slices are
+// added in a fixed order through shared memory (deterministic).
+__global__ void __launch_bounds__(256)
+wgrad_umma_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int KH, int KS, int Cin, int c0, int nslot,
+                         WgradArgs args, const float* __restrict__ inv_x, const float* __restrict__ inv_du) {
   const int total = 16 * 64 * KH * KS;
-  const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co4 = i & 15, ci = (i >> 4) & 63, t = i >> 10;
-    const int dy = t / KS, dx = t % KS;
-    if (c0 + ci >= Cin) continue;
-    int slot, half;
-    if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
-    else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
+  __shared__ double red[8][32][4];
+  const int co4 = i & 15, ci = (i >> 4) & 63, t = min(i >> 10, KH * KS - 1);
+  const int dy = t / KS, dx = t % KS;
+  int slot, half;
+  if (KS == 3) { slot = dx == 2 ? 1 : 0; half = dx == 0 ? 0 : 1; }
+  else { slot = dx < 2 ? 0 : dx < 4 ? 1 : 2; half = (dx == 0 || dx == 2) ? 0 : 1; }
+  double sx[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < total) {
     const float4* p0 = reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + half * 64 + ci) * 64) + co4;
     const size_t cs = (size_t)nslot * 128 * 16;        // float4 per CTA partial
-    double sx[4] = {0.0, 0.0, 0.0, 0.0}, sy[4] = {0.0, 0.0, 0.0, 0.0};
-    int c = args.cta_start[dy];
-    const int c1 = args.cta_start[dy + 1];
-    for (; c + 3 < c1; c += 4) {
-      const float4 a0 = __ldg(p0 + c * cs), a1 = __ldg(p0 + (c + 1) * cs), a2 = __ldg(p0 + (c + 2) * cs), a3 = __ldg(p0 + (c + 3) * cs);
-      sx[0] += a0.x; sx[1] += a0.y; sx[2] += a0.z; sx[3] += a0.w;
-      sy[0] += a1.x; sy[1] += a1.y; sy[2] += a1.z; sy[3] += a1.w;
-      sx[0] += a2.x; sx[1] += a2.y; sx[2] += a2.z; sx[3] += a2.w;
-      sy[0] += a3.x; sy[1] += a3.y; sy[2] += a3.z; sy[3] += a3.w;
+    const int cb = args.cta_start[dy], ce = args.cta_start[dy + 1];
+    const int per = (ce - cb + 7) / 8;
+    const int ca = cb + ty * per, cz = min(ce, ca + per);
+    for (int c = ca; c < cz; ++c) {
+      const float4 a = __ldg(p0 + c * cs);
+      sx[0] += a.x; sx[1] += a.y; sx[2] += a.z; sx[3] += a.w;
     }
-    for (; c < c1; ++c) {
-      const float4 a0 = __ldg(p0 + c * cs);
-      sx[0] += a0.x; sx[1] += a0.y; sx[2] += a0.z; sx[3] += a0.w;
-    }
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dw[(((co4 * 4 + j) * Cin + c0 + ci) * KH + dy) * KS + dx] = (float)((sx[j] + sy[j]) * scale);
+  for (int j = 0; j < 4; ++j) red[ty][tx][j] = sx[j];
+  __syncthreads();
+  if (ty == 0 && i < total && c0 + ci < Cin) {
+    const double scale = (double)__ldg(inv_x) * (double)__ldg(inv_du);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a = 0.0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) a += red[y][tx][j];
+      dw[(((co4 * 4 + j) * Cin + c0 + ci) * KH + dy) * KS + dx] = (float)(a * scale);
+    }
   }
 }
 
@@ -1473,7 +1481,7 @@ static int launch_wgrad_umma(nsc_model* m, int64_t groups, float* dw, uint16_t* 
   }
   kern<<<grid, 128, Cfg::SMEM, s>>>(tdh, tdl, txh, txl, a);
   NSC_CUDA_TRY(cudaGetLastError());
-  wgrad_umma_reduce_kernel<<<(16 * 64 * Cfg::KH * Cfg::KS + 127) / 128, 128, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, c0, Cfg::NSLOT, a, inv_x,
+  wgrad_umma_reduce_kernel<<<(16 * 64 * Cfg::KH * Cfg::KS + 31) / 32, 256, 0, s>>>(a.part, dw, Cfg::KH, Cfg::KS, cin, c0, Cfg::NSLOT, a, inv_x,
                                                                                      u.fc_in + 2);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 2;
