@@ -418,7 +418,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B, int64_t b_rs,
             int64_t b_cs, float* __restrict__ Cm, int64_t c_rs, const float* __restrict__ bias, int relu, int kchunk) {
-  __shared__ float As[16][65], Bs[16][65];
+  __shared__ __align__(16) float As[16][68], Bs[16][68];     // 68: rows stay 16-byte aligned for the float4 fragment loads
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   if (gridDim.z > 1) {
@@ -433,21 +433,27 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int6
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // tile loads: consecutive threads walk whichever index of the operand is contiguous in memory
+  const bool a_k_fast = a_cs == 1, b_k_fast = b_rs == 1;
   for (int k0 = 0; k0 < K; k0 += 16) {
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int kk = i & 15, r = i >> 4;
-      const int m = m0 + r, n = n0 + r, k = k0 + kk;
-      As[kk][r] = (m < M && k < K) ? A[m * a_rs + k * a_cs] : 0.f;
-      Bs[kk][r] = (n < N && k < K) ? B[k * b_rs + n * b_cs] : 0.f;
+      {
+        const int kk = a_k_fast ? (i & 15) : (i >> 6), r = a_k_fast ? (i >> 4) : (i & 63);
+        const int m = m0 + r, k = k0 + kk;
+        As[kk][r] = (m < M && k < K) ? __ldg(A + m * a_rs + k * a_cs) : 0.f;
+      }
+      {
+        const int kk = b_k_fast ? (i & 15) : (i >> 6), r = b_k_fast ? (i >> 4) : (i & 63);
+        const int n = n0 + r, k = k0 + kk;
+        Bs[kk][r] = (n < N && k < K) ? __ldg(B + k * b_rs + n * b_cs) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
