@@ -166,14 +166,23 @@ __device__ __forceinline__ void amax_commit(float m, unsigned int* __restrict__ 
 __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ resid, float* __restrict__ out,
                                 int64_t total, int HW, int relu, unsigned int* __restrict__ amax) {
+  // four elements of one (sample, channel) row per thread and iteration (HW = 5 W is a multiple of 4): 16-byte accesses
+  // keep enough bytes in flight for an HBM-bound pass
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)((i / HW) % 64);
-    float v = (u[i] - stats[c]) * stats[64 + c] * gamma[c] + beta[c];
-    if (relu) v = fmaxf(v, 0.f);
-    if (resid != nullptr) v += resid[i];
-    out[i] = v;
-    m = fmaxf(m, fabsf(v));
+  const int HW4 = HW >> 2;
+  const int64_t total4 = total >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW4) & 63);
+    const float mean = stats[c], istd = stats[64 + c], ga = gamma[c], be = beta[c];
+    const float4 u4 = __ldg(reinterpret_cast<const float4*>(u) + i);
+    float v[4] = {(u4.x - mean) * istd * ga + be, (u4.y - mean) * istd * ga + be, (u4.z - mean) * istd * ga + be, (u4.w - mean) * istd * ga + be};
+    if (relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+    if (resid != nullptr) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(resid) + i);
+      v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
   }
   amax_commit(m, amax);
 }
@@ -181,18 +190,33 @@ __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __rest
 // MaxPool2d((1,3), padding (0,1), stride (1,st)) forward
 __global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int W, int st,
                                 unsigned int* __restrict__ amax) {
-  const int Wo = W / st;
-  const int64_t total = rows * Wo;
+  // four consecutive outputs of one row per thread and iteration (W/st is a multiple of 4): the 4 st input columns they
+  // start at as 16-byte loads, plus the left and (stride 1) right neighbours
+  const int Wo = W / st, Wo4 = Wo >> 2;
+  const int64_t total4 = rows * Wo4;
+  const float ninf = -INFINITY;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int wo = (int)(i % Wo);
-    const float* r = in + (i / Wo) * W;
-    const int wc = wo * st;
-    float v = r[wc];
-    if (wc - 1 >= 0) v = fmaxf(v, r[wc - 1]);
-    if (wc + 1 < W) v = fmaxf(v, r[wc + 1]);
-    out[i] = v;
-    m = fmaxf(m, fabsf(v));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Wo4);
+    const float* r = in + (i / Wo4) * W;
+    const int wc = q * 4 * st;                       // first centre column
+    float x[9];                                      // columns wc - 1 .. wc + 4 st - 1 (+ 1 for stride 1)
+    x[0] = wc > 0 ? __ldg(r + wc - 1) : ninf;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(r + wc));
+    x[1] = a.x; x[2] = a.y; x[3] = a.z; x[4] = a.w;
+    float v[4];
+    if (st == 1) {
+      x[5] = wc + 4 < W ? __ldg(r + wc + 4) : ninf;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(fmaxf(x[j], x[j + 1]), x[j + 2]);
+    } else {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(r + wc + 4));
+      x[5] = b.x; x[6] = b.y; x[7] = b.z; x[8] = b.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaxf(fmaxf(x[2 * j], x[2 * j + 1]), x[2 * j + 2]);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
   }
   amax_commit(m, amax);
 }
@@ -204,23 +228,41 @@ __global__ void pool_fwd_kernel(const float* __restrict__ in, float* __restrict_
 template <int ST>
 __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, float* __restrict__ din, int64_t rows,
                                 int W) {
-  const int Wo = W / ST;
-  const int64_t total = rows * W;
+  // four consecutive input columns per thread and iteration (16-byte accesses); the window tests of an element use its two
+  // neighbours on either side, the gradients of the <= 6 (stride 1) / 3 (stride 2) outputs it can belong to are in registers
+  const int Wo = W / ST, W4 = W >> 2;
+  const int64_t total4 = rows * W4;
   const float ninf = -INFINITY;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    const int64_t row = i / W;
+  constexpr int ND = ST == 1 ? 6 : 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W4) * 4;
+    const int64_t row = i / W4;
     const float* r = in + row * W;
     const float* dr = dout + row * Wo;
-    const float c = r[w];
-    const float a = w >= 2 ? r[w - 2] : ninf, b = w >= 1 ? r[w - 1] : ninf;
-    const float d = w + 1 < W ? r[w + 1] : ninf, e = w + 2 < W ? r[w + 2] : ninf;
-    float g = 0.f;
-    // ascending output index: pos = 2, 1, 0
-    if (w >= 1 && (w - 1) % ST == 0 && (w - 1) / ST < Wo && c > a && c > b) g += dr[(w - 1) / ST];      // lo = w - 2
-    if (w % ST == 0 && w / ST < Wo && c > b && c >= d) g += dr[w / ST];                                   // lo = w - 1
-    if ((w + 1) % ST == 0 && (w + 1) / ST < Wo && c >= d && c >= e) g += dr[(w + 1) / ST];               // lo = w
-    din[i] = g;
+    float x[8];
+    x[0] = w >= 2 ? __ldg(r + w - 2) : ninf;
+    x[1] = w >= 1 ? __ldg(r + w - 1) : ninf;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(r + w));
+    x[2] = c4.x; x[3] = c4.y; x[4] = c4.z; x[5] = c4.w;
+    x[6] = w + 4 < W ? __ldg(r + w + 4) : ninf;
+    x[7] = w + 5 < W ? __ldg(r + w + 5) : ninf;
+    const int base = ST == 1 ? w - 1 : w / 2;      // first output whose window can contain one of the four columns
+    float dd[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) dd[k] = (base + k >= 0 && base + k < Wo) ? __ldg(dr + base + k) : 0.f;
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ww = w + e;
+      const float a = x[e], b = x[e + 1], c = x[e + 2], d = x[e + 3], f = x[e + 4];
+      float acc = 0.f;
+      // ascending output index: the element is the last, the middle, the first of the window
+      if (ww >= 1 && (ww - 1) % ST == 0 && (ww - 1) / ST < Wo && c > a && c > b) acc += dd[(ww - 1) / ST - base];
+      if (ww % ST == 0 && ww / ST < Wo && c > b && c >= d) acc += dd[ww / ST - base];
+      if ((ww + 1) % ST == 0 && (ww + 1) / ST < Wo && c >= d && c >= f) acc += dd[(ww + 1) / ST - base];
+      g[e] = acc;
+    }
+    reinterpret_cast<float4*>(din)[i] = make_float4(g[0], g[1], g[2], g[3]);
   }
 }
 
