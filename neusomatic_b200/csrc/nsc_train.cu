@@ -460,7 +460,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 __global__ void __launch_bounds__(256)
 gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B, int64_t b_rs,
             int64_t b_cs, float* __restrict__ Cm, int64_t c_rs, const float* __restrict__ bias, int relu, int kchunk) {
-  __shared__ __align__(16) float As[16][68], Bs[16][68];     // 68: rows stay 16-byte aligned for the float4 fragment loads
+  constexpr int KSLAB = 32;      // k-slab per iteration; the next slab is prefetched into registers while this one is multiplied
+  __shared__ __align__(16) float As[KSLAB][68], Bs[KSLAB][68];     // 68: rows stay 16-byte aligned for the float4 fragment loads
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   if (gridDim.z > 1) {
@@ -477,22 +478,39 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int6
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   // tile loads: consecutive threads walk whichever index of the operand is contiguous in memory
   const bool a_k_fast = a_cs == 1, b_k_fast = b_rs == 1;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+  constexpr int PER = KSLAB * 64 / 256;
+  float ra[PER], rb[PER];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int i = threadIdx.x + j * 256;
       {
-        const int kk = a_k_fast ? (i & 15) : (i >> 6), r = a_k_fast ? (i >> 4) : (i & 63);
+        const int kk = a_k_fast ? (i & (KSLAB - 1)) : (i >> 6), r = a_k_fast ? (i / KSLAB) : (i & 63);
         const int m = m0 + r, k = k0 + kk;
-        As[kk][r] = (m < M && k < K) ? __ldg(A + m * a_rs + k * a_cs) : 0.f;
+        ra[j] = (m < M && k < K) ? __ldg(A + m * a_rs + k * a_cs) : 0.f;
       }
       {
-        const int kk = b_k_fast ? (i & 15) : (i >> 6), r = b_k_fast ? (i >> 4) : (i & 63);
+        const int kk = b_k_fast ? (i & (KSLAB - 1)) : (i >> 6), r = b_k_fast ? (i / KSLAB) : (i & 63);
         const int n = n0 + r, k = k0 + kk;
-        Bs[kk][r] = (n < N && k < K) ? __ldg(B + k * b_rs + n * b_cs) : 0.f;
+        rb[j] = (n < N && k < K) ? __ldg(B + k * b_rs + n * b_cs) : 0.f;
       }
     }
-    __syncthreads();
+  };
+  auto sstore = [&]() {
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int j = 0; j < PER; ++j) {
+      const int i = threadIdx.x + j * 256;
+      As[a_k_fast ? (i & (KSLAB - 1)) : (i >> 6)][a_k_fast ? (i / KSLAB) : (i & 63)] = ra[j];
+      Bs[b_k_fast ? (i & (KSLAB - 1)) : (i >> 6)][b_k_fast ? (i / KSLAB) : (i & 63)] = rb[j];
+    }
+  };
+  gload(0);
+  for (int k0 = 0; k0 < K; k0 += KSLAB) {
+    sstore();
+    __syncthreads();
+    if (k0 + KSLAB < K) gload(k0 + KSLAB);
+#pragma unroll
+    for (int kk = 0; kk < KSLAB; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -624,11 +642,11 @@ static int run_gemm(int M, int N, int K, const float* A, int64_t a_rs, int64_t a
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   // split K (deterministic two-stage sum) while the output tiles alone leave most of the 148 SMs idle
   int splits = 1;
-  while (scratch != nullptr && grid.x * grid.y * splits * 2 <= 148 * 2 && K / (splits * 2) >= 32 &&
+  while (scratch != nullptr && grid.x * grid.y * splits * 2 <= 148 * 4 && K / (splits * 2) >= 64 &&
          (size_t)(splits * 2) * M * N <= scratch_floats)
     splits *= 2;
   if (splits > 1) {
-    const int kchunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    const int kchunk = ((K + splits - 1) / splits + 31) / 32 * 32;
     grid.z = (K + kchunk - 1) / kchunk;
     gemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, scratch, N, nullptr, 0, kchunk);
     NSC_CUDA_TRY(cudaGetLastError());
@@ -746,7 +764,7 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   e = e ? e : cudaMalloc((void**)&t->red, (512 + 64 * kRedSplits * 5) * sizeof(double));
   e = e ? e : alloc(&t->wf, (size_t)25 * 128 * 64 * 4); e = e ? e : alloc(&t->wb, (size_t)25 * 64 * 64 * 4);
   e = e ? e : alloc(&t->wpart, (size_t)kWgSplits * 25 * 64 * 64 * 4);
-  t->gpart_floats = std::max<size_t>((size_t)4 * max_batch * kFcHidden, (size_t)4 * kFcHidden * kFcIn);
+  t->gpart_floats = std::max<size_t>((size_t)8 * max_batch * kFcHidden, (size_t)8 * kFcHidden * kFcIn);
   e = e ? e : alloc(&t->gpart, t->gpart_floats * 4);
   e = e ? e : alloc(&t->head_w, 9 * kFcHidden * 4); e = e ? e : alloc(&t->head_g, 9 * kFcHidden * 4);
   e = e ? e : alloc(&t->zeros, 64 * 4);
