@@ -55,6 +55,9 @@ using namespace ptx;
 #ifndef NSC_EPI_Q
 #define NSC_EPI_Q 2
 #endif
+#ifndef NSC_SLIDE
+#define NSC_SLIDE 0      // 1: sliding-window pool phase with the residual added in registers (see conv_umma_kernel)
+#endif
 constexpr int kEpiQ = NSC_EPI_Q;                    // epilogue warps per TMEM lane quarter (2 or 4; measured equal: 4.93 M cand/s both)
 constexpr int kCPT = 64 / kEpiQ;                    // output channels per epilogue thread (32 or 16)
 constexpr int kEpiThreads = 128 * kEpiQ;
@@ -514,6 +517,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
       }
     };
+    // ---- sliding-window pool phase (NSC_SLIDE): one thread = one (channel chunk, candidate) over FOUR columns.  It reads the
+    // staged columns c0-1 .. c0+4 once (3 instead of 6 16-byte shared loads per stored item; 4.5 instead of 8 with stride 2),
+    // adds the residual to them in registers (no read-modify-write pass over the staging tile, one barrier less per row)
+    // and emits its columns' pooled outputs.
+    constexpr bool SLIDE = (NSC_SLIDE != 0) && (Cfg::POOL != 0) && !Cfg::NCHW && (kEpiThreads == 256);
+    constexpr int NCOL = ST == 1 ? 6 : 5;                       // window columns c0-1 .. c0+NCOL-2
+    const int s_ch = et & 7, s_mg = (et >> 3) % Cfg::RPW, s_c0 = (et / (8 * Cfg::RPW)) * 4;
+    uint2 sres_h[SLIDE ? NCOL : 1][2], sres_l[SLIDE ? NCOL : 1][2];      // residual of the window for the NEXT row
+    auto load_res_slide = [&](int grp_, int sub_, uint32_t u_, int idx_) {
+      const int slot_ = (u_ & 1) ? idx_ : (idx_ < 2 ? 3 + idx_ : idx_ - 2);
+      const int h_ = slot_row<DIL>(slot_);
+#pragma unroll
+      for (int j = 0; j < (SLIDE ? NCOL : 1); ++j) {
+        const int col = s_c0 - 1 + j;
+        if (col < 0 || col >= Cfg::TW) continue;
+        const size_t go = row_off(grp_, h_, W, sub_ * Cfg::TW + col, col * Cfg::RPW + s_mg) + s_ch * 4;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          sres_h[j][hh] = *reinterpret_cast<const uint2*>(args.res_hi + go + hh * 32);
+          sres_l[j][hh] = *reinterpret_cast<const uint2*>(args.res_lo + go + hh * 32);
+        }
+      }
+    };
     // training (fp32 NCHW addend): the W segments of this thread's (candidate, channel) pairs for the NEXT image row, loaded
     // at the end of the previous row so that they are in flight across the barrier, the TMEM load and the staging phase
     constexpr int NPAIR = Cfg::NCHW ? (Cfg::RPW * 64 / kEpiThreads) : 1, NWQ = Cfg::TW / 4;
@@ -532,7 +558,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     };
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
       for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
-        if (args.res_hi != nullptr) load_res(grp, sub, u_it, 0);
+        if (args.res_hi != nullptr) {
+          if (SLIDE) load_res_slide(grp, sub, u_it, 0);
+          else load_res(grp, sub, u_it, 0);
+        }
         if (Cfg::NCHW && args.res_nchw != nullptr) load_res_nchw(grp, sub, u_it, 0);
         long long t_c = clock64();
         mbar_wait(acc_full, u_it & 1);
@@ -632,7 +661,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           }
           epi_bar();
           // ---- phase B1: residual add (coalesced items; the operands were prefetched one row ahead)
-          if (args.res_hi != nullptr) {
+          if (!SLIDE && args.res_hi != nullptr) {
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
               const int i = et + k * kEpiThreads, rr = i >> 3, ch = i & 7;
@@ -647,6 +676,69 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             }
             if (idx + 1 < kH) load_res(grp, sub, u_it, idx + 1);
             epi_bar();
+          }
+          if (SLIDE) {
+            const float4 ninf = make_float4(__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
+            const bool has_res = args.res_hi != nullptr;
+            const int g = s_mg & 7, ga = grp * Cfg::GP + (s_mg >> 3);
+            float* s0 = stash_f + ((0 * kH + h) * 8 + g) * 64 + s_ch * 4;       // column TW-2 of the first column block
+            float* s1 = stash_f + ((1 * kH + h) * 8 + g) * 64 + s_ch * 4;       // column TW-1
+            auto max4 = [](float4& a, const float4& b) {
+              a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w);
+            };
+            auto emit = [&](const float4& b0, const float4& b1, int wo) {
+              store_item(args.out_hi, args.out_lo, args.out_c8, ((((size_t)ga * kH + h) * Cfg::WOUT + wo) * 8 + g), s_ch, b0, b1);
+            };
+            // rolling window over the columns: (pa, pb) = column j-2, (ca, cb) = column j-1, (na, nb) = column j
+            float4 pa = ninf, pb = ninf, ca = ninf, cb = ninf, na, nb;
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) {
+              const int col = s_c0 - 1 + j;
+              if (col >= 0 && col < Cfg::TW) {
+                const int rr = col * Cfg::RPW + s_mg;
+                const float* p = stg + rr * 64 + ((s_ch ^ (rr & 7)) << 2);
+                na = *reinterpret_cast<const float4*>(p);
+                nb = *reinterpret_cast<const float4*>(p + 32);
+                if (has_res) {
+                  const float2 a0 = join2(sres_h[j][0].x, sres_l[j][0].x), b0 = join2(sres_h[j][0].y, sres_l[j][0].y);
+                  const float2 a1 = join2(sres_h[j][1].x, sres_l[j][1].x), b1 = join2(sres_h[j][1].y, sres_l[j][1].y);
+                  na.x += a0.x; na.y += a0.y; na.z += b0.x; na.w += b0.y;
+                  nb.x += a1.x; nb.y += a1.y; nb.z += b1.x; nb.w += b1.y;
+                }
+              } else if (col < 0 && Cfg::STASH && sub == 1) {      // left neighbour of the second column block: from the stash
+                na = *reinterpret_cast<const float4*>(s1);
+                nb = *reinterpret_cast<const float4*>(s1 + 32);
+              } else {
+                na = ninf;
+                nb = ninf;
+              }
+              // the first block's last two columns go to the stash (its last column is emitted by the second block)
+              if (Cfg::STASH && sub == 0 && s_c0 + 4 == Cfg::TW && (j == 3 || j == 4)) {
+                float* sd = j == 3 ? s0 : s1;
+                *reinterpret_cast<float4*>(sd) = na;
+                *reinterpret_cast<float4*>(sd + 32) = nb;
+              }
+              if (ST == 1 && j == 1 && Cfg::STASH && sub == 1 && s_c0 == 0) {   // ... here: max(column TW-2, TW-1 of block 0, column 0)
+                float4 b0 = na, b1 = nb;
+                max4(b0, ca); max4(b1, cb);
+                max4(b0, *reinterpret_cast<const float4*>(s0)); max4(b1, *reinterpret_cast<const float4*>(s0 + 32));
+                emit(b0, b1, w0 - 1);
+              }
+              const bool centre = (ST == 1) ? (j >= 2) : (j == 2 || j == 4);     // column j-1 is an output centre
+              if (centre) {
+                const int oc = col - 1;                                          // = s_c0 + j - 2
+                if (!(ST == 1 && Cfg::STASH && sub == 0 && oc == Cfg::TW - 1)) {
+                  float4 b0 = ca, b1 = cb;
+                  max4(b0, pa); max4(b1, pb);
+                  max4(b0, na); max4(b1, nb);
+                  emit(b0, b1, (w0 + oc) / ST);
+                }
+              }
+              pa = ca; pb = cb; ca = na; cb = nb;
+            }
+            if (has_res && idx + 1 < kH) load_res_slide(grp, sub, u_it, idx + 1);
+            epi_bar();   // staging is rewritten by the next row
+            continue;
           }
           if (Cfg::NCHW && Cfg::POOL == 0) {
             // ---- training: fp32 NCHW output (* scale + bias + optional fp32 addend).  A thread takes (candidate, channel)
