@@ -56,7 +56,7 @@ using namespace ptx;
 #define NSC_EPI_Q 2
 #endif
 #ifndef NSC_SLIDE
-#define NSC_SLIDE 0      // 1: sliding-window pool phase with the residual added in registers (see conv_umma_kernel)
+#define NSC_SLIDE 2      // sliding-window pool phase (see conv_umma_kernel): 0 = off, 1 = every pooled layer, 2 = the stem only (default)
 #endif
 constexpr int kEpiQ = NSC_EPI_Q;                    // epilogue warps per TMEM lane quarter (2 or 4; measured equal: 4.93 M cand/s both)
 constexpr int kCPT = 64 / kEpiQ;                    // output channels per epilogue thread (32 or 16)
@@ -521,15 +521,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     // staged columns c0-1 .. c0+4 once (3 instead of 6 16-byte shared loads per stored item; 4.5 instead of 8 with stride 2),
     // adds the residual to them in registers (no read-modify-write pass over the staging tile, one barrier less per row)
     // and emits its columns' pooled outputs.
-    constexpr bool SLIDE = (NSC_SLIDE != 0) && (Cfg::POOL != 0) && !Cfg::NCHW && (kEpiThreads == 256);
+    // Measured (A/B/A on one box): the stem, which has no residual window to keep in registers, gains 12 % (1.51 -> 1.33 ms per
+    // 65 536 candidates); the stride-2 conv_r2 layers are unchanged and the 5x5 stride-1 layer spills 80 bytes with the
+    // six-column residual window and loses -- so the default (NSC_SLIDE = 2) uses it for the stem only; 1 = every pooled layer.
+    constexpr bool SLIDE_RES = Cfg::KH != 1;                     // the stem has no residual input, the conv_r2 layers always do
+    constexpr bool SLIDE = (NSC_SLIDE == 1 || (NSC_SLIDE == 2 && !SLIDE_RES)) && (Cfg::POOL != 0) && !Cfg::NCHW && (kEpiThreads == 256);
     constexpr int NCOL = ST == 1 ? 6 : 5;                       // window columns c0-1 .. c0+NCOL-2
     const int s_ch = et & 7, s_mg = (et >> 3) % Cfg::RPW, s_c0 = (et / (8 * Cfg::RPW)) * 4;
-    uint2 sres_h[SLIDE ? NCOL : 1][2], sres_l[SLIDE ? NCOL : 1][2];      // residual of the window for the NEXT row
+    uint2 sres_h[(SLIDE && SLIDE_RES) ? NCOL : 1][2], sres_l[(SLIDE && SLIDE_RES) ? NCOL : 1][2];      // residual of the window for the NEXT row
     auto load_res_slide = [&](int grp_, int sub_, uint32_t u_, int idx_) {
       const int slot_ = (u_ & 1) ? idx_ : (idx_ < 2 ? 3 + idx_ : idx_ - 2);
       const int h_ = slot_row<DIL>(slot_);
 #pragma unroll
-      for (int j = 0; j < (SLIDE ? NCOL : 1); ++j) {
+      for (int j = 0; j < ((SLIDE && SLIDE_RES) ? NCOL : 1); ++j) {
         const int col = s_c0 - 1 + j;
         if (col < 0 || col >= Cfg::TW) continue;
         const size_t go = row_off(grp_, h_, W, sub_ * Cfg::TW + col, col * Cfg::RPW + s_mg) + s_ch * 4;
@@ -559,8 +563,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x)
       for (int sub = 0; sub < Cfg::SUBS; ++sub, ++u_it) {
         if (args.res_hi != nullptr) {
-          if (SLIDE) load_res_slide(grp, sub, u_it, 0);
-          else load_res(grp, sub, u_it, 0);
+          if (SLIDE && SLIDE_RES) load_res_slide(grp, sub, u_it, 0);
+          else if (!SLIDE) load_res(grp, sub, u_it, 0);
         }
         if (Cfg::NCHW && args.res_nchw != nullptr) load_res_nchw(grp, sub, u_it, 0);
         long long t_c = clock64();
@@ -679,7 +683,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           }
           if (SLIDE) {
             const float4 ninf = make_float4(__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
-            const bool has_res = args.res_hi != nullptr;
+            const bool has_res = SLIDE_RES && args.res_hi != nullptr;
             const int g = s_mg & 7, ga = grp * Cfg::GP + (s_mg >> 3);
             float* s0 = stash_f + ((0 * kH + h) * 8 + g) * 64 + s_ch * 4;       // column TW-2 of the first column block
             float* s1 = stash_f + ((1 * kH + h) * 8 + g) * 64 + s_ch * 4;       // column TW-1
@@ -700,8 +704,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 na = *reinterpret_cast<const float4*>(p);
                 nb = *reinterpret_cast<const float4*>(p + 32);
                 if (has_res) {
-                  const float2 a0 = join2(sres_h[j][0].x, sres_l[j][0].x), b0 = join2(sres_h[j][0].y, sres_l[j][0].y);
-                  const float2 a1 = join2(sres_h[j][1].x, sres_l[j][1].x), b1 = join2(sres_h[j][1].y, sres_l[j][1].y);
+                  constexpr int jj = 0;   // (index clamp for the instantiations without a residual window)
+                  const int jr = SLIDE_RES ? j : jj;
+                  const float2 a0 = join2(sres_h[jr][0].x, sres_l[jr][0].x), b0 = join2(sres_h[jr][0].y, sres_l[jr][0].y);
+                  const float2 a1 = join2(sres_h[jr][1].x, sres_l[jr][1].x), b1 = join2(sres_h[jr][1].y, sres_l[jr][1].y);
                   na.x += a0.x; na.y += a0.y; na.z += b0.x; na.w += b0.y;
                   nb.x += a1.x; nb.y += a1.y; nb.z += b1.x; nb.w += b1.y;
                 }
