@@ -84,6 +84,7 @@ struct UmmaState {
   float* fc_in = nullptr;               // fp32 [cap,1280] input of fc1
   uint16_t* tpk[8][2] = {};             // training: packed (hi, lo) inputs of the eight 64 -> 64 convolutions, kept for the weight gradient
   float* tscl = nullptr;                // training: [8][4] absmax bits / inverse scales of those tensors
+  uint8_t* twpk[8][2] = {};             // training: packed weight stages of those layers for this step (forward, data gradient)
   int64_t cap = 0;
   int num_sms = 148;
   bool weights_fit_fp16 = true;
@@ -165,7 +166,9 @@ enum : int {
 int umma_train_init(nsc_model* m, int64_t max_batch);
 void umma_train_free(nsc_model* m);
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand = kOperandRaw, int xslot = -1);
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand = kOperandRaw, int xslot = -1,
+                    int wslot = -1 /* >= 0: the layer's weights were packed by umma_train_pack_all_weights */);
+int umma_train_pack_all_weights(nsc_model* m, const float* const w[8], const int k[8], const int Wl[8], cudaStream_t s);
 int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const float* du, float* dw, int64_t n, cudaStream_t s,
                      int xslot = -1, int cin = 64, int kh = 0, int du_state = 0 /* 1: max |du| known, 2: du already packed */);
 // BatchNorm backward written straight into the packed, rescaled operand of the weight / data gradient (no fp32 du):

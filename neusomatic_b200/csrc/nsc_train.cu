@@ -828,6 +828,14 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   auto amax_of = [&](int li) -> unsigned int* { return fuse_amax && li >= 1 && li <= 8 ? umma_train_amax_slot(&t->dummy, li - 1) : nullptr; };
   unsigned int* amax_du = fuse_amax ? umma_train_amax_slot(&t->dummy, -1) : nullptr;
   if (fuse_amax) NSC_CUDA_TRY(cudaMemsetAsync(umma_train_amax_slot(&t->dummy, 0), 0, 8 * 4 * sizeof(float), s));
+  const bool w_packed = t->tensor_fwd || t->tensor_bwd;       // the step's sixteen weight images in one launch
+  if (w_packed) {
+    const float* wl[8];
+    int kl[8], Wl[8];
+    for (int l = 0; l < 8; ++l) { wl[l] = params + t->L[l + 1].w_off; kl[l] = t->L[l + 1].k_h; Wl[l] = t->L[l + 1].W; }
+    int r = umma_train_pack_all_weights(&t->dummy, wl, kl, Wl, s);
+    if (r != NSC_OK) return r;
+  }
   auto conv_bn = [&](int li, const float* in, float* u, float* out, int relu, const float* resid) -> int {
     const TLayer& L = t->L[li];
     const int T = L.k_h * L.k_w;
@@ -835,7 +843,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     if (t->tensor_fwd && L.cin == 64) {
       // train-mode forward convolution on the tensor path (split fp16, fp32 accumulate): u = conv(in, w) + b
       r = umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, in, params + L.w_off, 0, params + L.b_off, nullptr, u, N, s,
-                          fuse_amax ? kOperandAmaxKnown : kOperandRaw, li - 1);
+                          fuse_amax ? kOperandAmaxKnown : kOperandRaw, li - 1, li - 1);
     } else {
       repack_w_kernel<<<grid_for((int64_t)64 * L.cin * T), 256, 0, s>>>(params + L.w_off, t->wf, nullptr, L.cin, T);
       NSC_LAUNCH_OK();
@@ -936,7 +944,8 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     const int T = L.k_h * L.k_w;
     if (t->tensor_bwd)   // data gradient = the same convolution with swapped channels and flipped taps
       return umma_train_conv(&t->dummy, L.k_h, L.dil, L.W, du, params + L.w_off, 1, t->zeros, resid, dx, N, s,
-                             /* the weight gradient of this layer has just packed du */ t->tensor_wgrad ? kOperandPacked : kOperandRaw);
+                             /* the weight gradient of this layer has just packed du */ t->tensor_wgrad ? kOperandPacked : kOperandRaw, -1,
+                             li - 1);
     repack_w_kernel<<<grid_for((int64_t)64 * 64 * T), 256, 0, s>>>(params + L.w_off, t->wf, t->wb, 64, T);
     NSC_LAUNCH_OK();
     return fp32_conv_generic(&t->dummy, L.k_h, L.dil, L.W, du, t->wb, t->zeros, resid, dx, N, 64, s);

@@ -1311,6 +1311,49 @@ __global__ void pack_train_weights_kernel(const float* __restrict__ w, uint8_t* 
   }
 }
 
+// all sixteen weight images of a step (eight 64 -> 64 layers x {forward, data gradient}) in ONE launch: the weights do not
+// change between the forward and the backward pass of a step
+struct TrainWeightJobs { const float* w[8]; uint8_t* out[8][2]; int k[8]; int kc[8]; };
+__global__ void pack_train_weights_all_kernel(const TrainWeightJobs jobs) {
+  const int layer = blockIdx.y >> 1, flip = blockIdx.y & 1;
+  const float* __restrict__ w = jobs.w[layer];
+  uint8_t* __restrict__ out = jobs.out[layer][flip];
+  const int KH = jobs.k[layer], KW = KH, KC = jobs.kc[layer];
+  const int NK = 64 / KC;
+  const size_t stage = (size_t)KH * 64 * KC * 2;
+  const int total = 64 * 64 * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int dx = i % KW, dy = (i / KW) % KH, ci = (i / (KW * KH)) % 64, co = i / (KW * KH * 64);
+    const float v = flip ? w[((ci * 64 + co) * KH + (KH - 1 - dy)) * KW + (KW - 1 - dx)] : w[i];
+    const float vs = fminf(fmaxf(v * kTrainWScale, -65504.f), 65504.f);
+    const __half hv = __float2half_rn(vs);
+    const __half lv = __float2half_rn(vs - __half2float(hv));
+    const int kc = ci / KC, k = ci % KC;
+    const uint32_t r = (uint32_t)(dy * 64 + co), c = (uint32_t)(k / 8);
+    const uint32_t off = (KC == 32 ? ptx::swz_offset<64>(r, c) : ptx::swz_offset<32>(r, c)) + (k % 8) * 2;
+    *reinterpret_cast<__half*>(out + (size_t)((0 * NK + kc) * KW + dx) * stage + off) = hv;
+    *reinterpret_cast<__half*>(out + (size_t)((1 * NK + kc) * KW + dx) * stage + off) = lv;
+  }
+}
+
+// w[l]: fp32 [64][64][k[l]][k[l]] weights of the l-th 64 -> 64 convolution (module order), Wl[l] its input width
+int umma_train_pack_all_weights(nsc_model* m, const float* const w[8], const int k[8], const int Wl[8], cudaStream_t s) {
+  UmmaState& u = m->umma;
+  TrainWeightJobs jobs;
+  for (int l = 0; l < 8; ++l) {
+    if (u.twpk[l][0] == nullptr) { set_error("umma_train_pack_all_weights: workspace not initialised"); return NSC_E_STATE; }
+    jobs.w[l] = w[l];
+    jobs.out[l][0] = u.twpk[l][0];
+    jobs.out[l][1] = u.twpk[l][1];
+    jobs.k[l] = k[l];
+    jobs.kc[l] = Wl[l] == 8 ? 16 : 32;
+  }
+  pack_train_weights_all_kernel<<<dim3(64, 16), 256, 0, s>>>(jobs);
+  NSC_CUDA_TRY(cudaGetLastError());
+  m->launches += 1;
+  return NSC_OK;
+}
+
 int umma_train_init(nsc_model* m, int64_t max_batch) {
   UmmaState& u = m->umma;
   u.cap = (max_batch + 15) / 16 * 16;
@@ -1335,6 +1378,8 @@ int umma_train_init(nsc_model* m, int64_t max_batch) {
     }
   }
   NSC_CUDA_TRY(cudaMalloc((void**)&u.tscl, 8 * 4 * sizeof(float)));
+  for (int l = 0; l < 8; ++l)
+    for (int f = 0; f < 2; ++f) NSC_CUDA_TRY(cudaMalloc((void**)&u.twpk[l][f], (size_t)2 * 25 * 64 * 64 * 2));
   return NSC_OK;
 }
 
@@ -1348,6 +1393,8 @@ void umma_train_free(nsc_model* m) {
   for (int l = 0; l < 8; ++l)
     for (int p = 0; p < 2; ++p) { cudaFree(u.tpk[l][p]); u.tpk[l][p] = nullptr; }
   cudaFree(u.tscl); u.tscl = nullptr;
+  for (int l = 0; l < 8; ++l)
+    for (int f = 0; f < 2; ++f) { cudaFree(u.twpk[l][f]); u.twpk[l][f] = nullptr; }
   u.cap = 0;
 }
 
@@ -1742,7 +1789,7 @@ unsigned int* umma_train_amax_slot(nsc_model* m, int xslot) {
 
 // out[N,64,5,W] = conv(in[N,64,5,W], w) + bias (+ resid), k x k kernel with dilation dil and "same" padding
 int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const float* w, int flip, const float* bias,
-                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand, int xslot) {
+                    const float* resid, float* out, int64_t n, cudaStream_t s, int operand, int xslot, int wslot) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_conv: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
@@ -1765,12 +1812,17 @@ int umma_train_conv(nsc_model* m, int k, int dil, int W, const float* in, const 
     m->launches += 2;
   }
   const int kc = W == 8 ? 16 : 32;
-  pack_train_weights_kernel<<<(64 * 64 * k * k + 255) / 256, 256, 0, s>>>(w, u.wpk1, k, k, kc, flip);
-  NSC_CUDA_TRY(cudaGetLastError());
-  m->launches += 1;
+  const uint8_t* wpk = u.wpk1;
+  if (wslot >= 0 && u.twpk[wslot][flip ? 1 : 0] != nullptr) {      // packed for the whole step by umma_train_pack_all_weights
+    wpk = u.twpk[wslot][flip ? 1 : 0];
+  } else {
+    pack_train_weights_kernel<<<(64 * 64 * k * k + 255) / 256, 256, 0, s>>>(w, u.wpk1, k, k, kc, flip);
+    NSC_CUDA_TRY(cudaGetLastError());
+    m->launches += 1;
+  }
 #define NSC_TC(KK, DD, WW, NKK, KCC, GPP)                                                                                       \
   if (k == KK && dil == DD && W == WW)                                                                                          \
-    return launch_umma_conv<ConvCfg<KK, KK, DD, WW, NKK, 0, true, KCC, GPP, false>>(m, 12, tin, u.wpk1, bias, nullptr, out, nullptr, n, \
+    return launch_umma_conv<ConvCfg<KK, KK, DD, WW, NKK, 0, true, KCC, GPP, false>>(m, 12, tin, wpk, bias, nullptr, out, nullptr, n, \
                                                                                      0, s, kOutHiLo, resid, scl + 1)
   NSC_TC(3, 1, 32, 2, 32, 1);
   NSC_TC(5, 1, 32, 2, 32, 1);
