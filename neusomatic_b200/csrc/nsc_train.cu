@@ -535,20 +535,20 @@ gemm_kernel(int M, int N, int K, const float* __restrict__ A, int64_t a_rs, int6
 }
 
 // column sums of a [M][N] matrix (bias gradients of the linear layers), optional ReLU mask from `mask_src`
-// block = 32 columns x 8 row groups (launch with 256 threads); fixed summation order
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out) {
+// block = 32 columns x 32 row groups (launch with 1024 threads); fixed summation order
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ A, int M, int N, float* __restrict__ out) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   double s = 0.0;
   if (n < N)
-    for (int m = ty; m < M; m += 8) s += A[(size_t)m * N + n];
-  __shared__ double sh[8][33];
+    for (int m = ty; m < M; m += 32) s += A[(size_t)m * N + n];
+  __shared__ double sh[32][33];
   sh[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && n < N) {
     double a = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a += sh[j][tx];
+    for (int j = 0; j < 32; ++j) a += sh[j][tx];
     out[n] = (float)a;
   }
 }
@@ -899,7 +899,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[4], t->head_g + 4 * kFcHidden, kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[6], t->head_g + 5 * kFcHidden, 4 * kFcHidden * 4, cudaMemcpyDeviceToDevice, s));
   float* dbh = t->gC;   // scratch [9]
-  colsum_kernel<<<1, 256, 0, s>>>(t->dlogits, N, 9, dbh);
+  colsum_kernel<<<1, 1024, 0, s>>>(t->dlogits, N, 9, dbh);
   NSC_LAUNCH_OK();
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[3], dbh, 16, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(grads + t->fc_off[5], dbh + 4, 4, cudaMemcpyDeviceToDevice, s));
@@ -909,7 +909,7 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_LAUNCH_OK();
   // dW1 [240][1280] = dh^T x4 ; db1 ; dx4 [N][1280] = dh * W1
   NSC_RUN(run_gemm(kFcHidden, kFcIn, N, t->dh, 1, kFcHidden, t->x[4], kFcIn, 1, grads + t->fc_off[0], kFcIn, nullptr, 0, s, t->gpart, t->gpart_floats));
-  colsum_kernel<<<(kFcHidden + 31) / 32, 256, 0, s>>>(t->dh, N, kFcHidden, grads + t->fc_off[1]);
+  colsum_kernel<<<(kFcHidden + 31) / 32, 1024, 0, s>>>(t->dh, N, kFcHidden, grads + t->fc_off[1]);
   NSC_LAUNCH_OK();
   float* g = t->gA;       // gradient w.r.t. the current block output
   NSC_RUN(run_gemm(N, kFcIn, kFcHidden, t->dh, kFcHidden, 1, W1, kFcIn, 1, g, kFcIn, nullptr, 0, s));
