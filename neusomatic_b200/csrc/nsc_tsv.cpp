@@ -92,6 +92,39 @@ inline bool parse_int(const char* p, size_t n, long* v) {
   return *e == 0;
 }
 
+// Exact fast path of decimal -> double for plain "[-]digits[.digits]" with at most 15 significant digits and at most 22
+// fraction digits (Clinger): the digits are an exact integer below 2^53 and 10^k (k <= 22) is an exact double, so ONE
+// correctly rounded division gives the same double as strtod / Python's float().  Returns false for anything else
+// (exponents, inf/nan, long mantissas): the caller falls back to strtod.
+inline bool fast_decimal(const char* p, size_t n, double* out) {
+  static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  size_t i = 0;
+  bool neg = false;
+  if (i < n && (p[i] == '-' || p[i] == '+')) { neg = p[i] == '-'; ++i; }
+  uint64_t mant = 0;
+  int digits = 0, frac = 0, seen = 0;
+  bool dot = false;
+  for (; i < n; ++i) {
+    const char c = p[i];
+    if (c >= '0' && c <= '9') {
+      ++seen;
+      if (mant != 0 || c != '0') ++digits;
+      if (digits > 15) return false;
+      mant = mant * 10 + (uint64_t)(c - '0');
+      if (dot) ++frac;
+    } else if (c == '.' && !dot) {
+      dot = true;
+    } else {
+      return false;
+    }
+  }
+  if (seen == 0 || frac > 22) return false;
+  const double v = (double)mant / kPow10[frac];
+  *out = neg ? -v : v;
+  return true;
+}
+
 const char* kTypes[4] = {"DEL", "INS", "NONE", "SNP"};   // call.py:407
 
 struct DecodeJob {
@@ -180,13 +213,16 @@ void decode_range(DecodeJob* job) {
         Field a;
         while (next_field(p, end, &a)) {
           if (na < job->num_anns && job->anns255) {
-            char buf[64];
-            const size_t m = a.n < 63 ? a.n : 63;
-            memcpy(buf, a.p, m);
-            buf[m] = 0;
-            char* e;
-            const double v = strtod(buf, &e);
-            if (*e != 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: bad annotation '%s'", li, buf); break; }
+            double v;
+            if (!fast_decimal(a.p, a.n, &v)) {      // exponents, long mantissas, inf / nan: the C library
+              char buf[64];
+              const size_t m = a.n < 63 ? a.n : 63;
+              memcpy(buf, a.p, m);
+              buf[m] = 0;
+              char* e;
+              v = strtod(buf, &e);
+              if (*e != 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: bad annotation '%s'", li, buf); break; }
+            }
             job->anns255[(size_t)k * job->num_anns + na] = (float)(v * 255.0);
           }
           ++na;

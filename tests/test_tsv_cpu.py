@@ -63,6 +63,47 @@ def test_annotation_text_is_parsed_like_python_float(tmp_path, built):
     np.testing.assert_array_equal(got.anns255[0], ref)
 
 
+def test_annotation_fast_decimal_path_equals_python_float(tmp_path, built):
+    """The decoder parses plain decimals on an exact fast path (<= 15 significant digits: one correctly rounded division)
+    and leaves the rest to strtod: both must give Python's float(text) bit for bit, for every shape of literal the
+    ensemble TSVs can hold (generate_dataset.py:1570-1571 writes str(round(x, 4)), but any float literal is legal)."""
+    from neusomatic_b200.tsv import CandidateTSV
+    rng = np.random.default_rng(7)
+    cand = synth.structured_pileups(40, seed=3, ensemble=True)
+    p = str(tmp_path / "d.tsv")
+    all_texts = []
+    with open(p, "w") as f:
+        for i in range(40):
+            texts = []
+            for _ in range(93):
+                kind = rng.integers(0, 8)
+                nd = int(rng.integers(1, 18))                       # up to 17 significant digits: beyond the fast path too
+                digs = "".join(str(int(d)) for d in rng.integers(0, 10, size=nd))
+                if kind == 0:
+                    t = "0." + digs
+                elif kind == 1:
+                    t = digs[:1] + "." + digs[1:] if nd > 1 else digs
+                elif kind == 2:
+                    t = "0.000" + digs
+                elif kind == 3:
+                    t = str(round(float(rng.random()), 4))          # what the reference writes
+                elif kind == 4:
+                    t = "%.3e" % float(rng.random())                # exponent form -> strtod
+                elif kind == 5:
+                    t = "-0." + digs
+                elif kind == 6:
+                    t = digs + "." if nd < 6 else "." + digs        # "12." and ".5" are legal Python float literals
+                else:
+                    t = "0." + digs + "0" * int(rng.integers(0, 6))   # trailing zeros
+                texts.append(t)
+            all_texts.append(texts)
+            line = oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i], None).rstrip("\n")
+            f.write(line + "\t" + "\t".join(texts) + "\n")
+    got = CandidateTSV(p, num_anns=93).decode()
+    ref = (np.array([[float(t) for t in row] for row in all_texts], np.float64) * 255.0).astype(np.float32)
+    np.testing.assert_array_equal(got.anns255, ref)
+
+
 def test_empty_and_malformed_files(tmp_path, built):
     from neusomatic_b200.tsv import CandidateTSV
     from neusomatic_b200._lib import NscError
