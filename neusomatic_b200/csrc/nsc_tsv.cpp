@@ -66,9 +66,23 @@ const B64 kB64;
 inline int b64_decode(const char* s, size_t n, uint8_t* out, size_t cap) {
   while (n > 0 && s[n - 1] == '=') --n;
   size_t o = 0;
+  size_t i = 0;
+  // whole groups: four characters -> three bytes, one validity test per group
+  const size_t groups = n / 4;
+  if (groups * 3 > cap) return -1;
+  for (size_t g = 0; g < groups; ++g, i += 4) {
+    const int a = kB64.t[(unsigned char)s[i]], b = kB64.t[(unsigned char)s[i + 1]], c = kB64.t[(unsigned char)s[i + 2]],
+              d = kB64.t[(unsigned char)s[i + 3]];
+    if ((a | b | c | d) < 0) return -1;
+    const uint32_t v = ((uint32_t)a << 18) | ((uint32_t)b << 12) | ((uint32_t)c << 6) | (uint32_t)d;
+    out[o] = (uint8_t)(v >> 16);
+    out[o + 1] = (uint8_t)(v >> 8);
+    out[o + 2] = (uint8_t)v;
+    o += 3;
+  }
   uint32_t acc = 0;
   int bits = 0;
-  for (size_t i = 0; i < n; ++i) {
+  for (; i < n; ++i) {
     const int v = kB64.t[(unsigned char)s[i]];
     if (v < 0) return -1;
     acc = (acc << 6) | (uint32_t)v;
