@@ -210,6 +210,9 @@ int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* 
                    float* anns255, int32_t* labels, int num_threads);
 /* pointer into the mapped file + length of candidate i's tag (field 3 of the line; not NUL-terminated) */
 int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len);
+/* tags of candidates [first, first + n), each followed by '\n', copied into buf (cap bytes); *needed = bytes required
+ * (call with buf = NULL to size the buffer).  One call instead of n: the tag strings are the keys of call.py's dictionaries. */
+int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t cap, int64_t* needed);
 int nsc_tsv_close(nsc_tsv* t);
 
 #ifdef __cplusplus

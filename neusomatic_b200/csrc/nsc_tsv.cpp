@@ -318,6 +318,26 @@ int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len) {
   return NSC_OK;
 }
 
+int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t cap, int64_t* needed) {
+  if (!t || !needed || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  int64_t o = 0;
+  for (int64_t i = first; i < first + n; ++i) {
+    const char* p = t->data + t->line_start[(size_t)i];
+    const char* end = t->data + t->line_start[(size_t)i + 1];
+    Field f;
+    for (int k = 0; k < 3; ++k)
+      if (!next_field(p, end, &f)) { nsc::set_error("line %lld: no tag field", (long long)i); return NSC_E_INVALID; }
+    if (buf != nullptr && o + (int64_t)f.n + 1 <= cap) {
+      memcpy(buf + o, f.p, f.n);
+      buf[o + f.n] = '\n';
+    }
+    o += (int64_t)f.n + 1;
+  }
+  *needed = o;
+  if (buf != nullptr && o > cap) { nsc::set_error("tag buffer too small: %lld of %lld bytes", (long long)cap, (long long)o); return NSC_E_INVALID; }
+  return NSC_OK;
+}
+
 int nsc_tsv_close(nsc_tsv* t) {
   if (!t) return NSC_OK;
   if (t->data) munmap((void*)t->data, t->size);

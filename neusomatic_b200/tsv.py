@@ -29,6 +29,17 @@ class CandidateTSV:
         _lib.check(self.lib.nsc_tsv_tag(self.h, i, C.byref(p), C.byref(n)))
         return C.string_at(p, n.value).decode()
 
+    def tags(self, first=0, n=None):
+        """Tags of candidates [first, first + n) in one library call (the keys of call.py's dictionaries)."""
+        n = len(self) - first if n is None else n
+        if n == 0:
+            return []
+        need = C.c_int64()
+        _lib.check(self.lib.nsc_tsv_tags(self.h, first, n, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        _lib.check(self.lib.nsc_tsv_tags(self.h, first, n, buf, need.value, C.byref(need)))
+        return buf.raw[:need.value - 1].decode().split("\n")
+
     def decode(self, first=0, n=None, out=None, with_tags=True):
         """Returns Candidates(matrices uint8 [n,5,32,23], center, tumor_cov, normal_cov, anns255-or-None, tags).
         ``out`` may hold preallocated (pinned) arrays: dict(matrices=, meta=, anns255=)."""
@@ -46,7 +57,7 @@ class CandidateTSV:
         labels = np.empty((n, 2), np.int32)
         _lib.check(self.lib.nsc_tsv_decode(self.h, first, n, self.num_anns, _lib.ptr(m), _lib.ptr(meta),
                                            _lib.ptr(a255) if self.num_anns else None, labels.ctypes.data, self.num_threads))
-        tags = [self.tag(first + i) for i in range(n)] if with_tags else []
+        tags = self.tags(first, n) if with_tags else []
         meta_np = np.asarray(meta)
         c = Candidates(m, meta_np[:, 0], meta_np[:, 1], meta_np[:, 2], None, tags)
         c.anns255 = a255

@@ -104,6 +104,18 @@ def test_annotation_fast_decimal_path_equals_python_float(tmp_path, built):
     np.testing.assert_array_equal(got.anns255, ref)
 
 
+def test_bulk_tags_equal_per_candidate_tags(tmp_path, built):
+    """nsc_tsv_tags (one call for a range) == nsc_tsv_tag candidate by candidate == the tag field the oracle wrote."""
+    from neusomatic_b200.tsv import CandidateTSV
+    cand = synth.structured_pileups(37, seed=9)
+    p = str(tmp_path / "t.tsv")
+    _write(p, cand, False)
+    t = CandidateTSV(p)
+    assert t.tags() == [t.tag(i) for i in range(len(t))] == list(cand.tags)
+    assert t.tags(5, 0) == [] and t.tags(36, 1) == [cand.tags[36]] and t.tags(3, 4) == list(cand.tags[3:7])
+    t.close()
+
+
 def test_empty_and_malformed_files(tmp_path, built):
     from neusomatic_b200.tsv import CandidateTSV
     from neusomatic_b200._lib import NscError
