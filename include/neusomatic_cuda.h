@@ -204,7 +204,8 @@ int nsc_tsv_open(nsc_tsv** out, const char* path);
 int64_t nsc_tsv_count(const nsc_tsv* t);
 /* matrices [n,5,32,23] uint8; meta [n,3] int32 = (center, tumor_cov, normal_cov); anns255 [n,num_anns] fp32 =
  * float(double(text) * 255.0) or NULL when num_anns == 0; labels [n,2] int32 = (type index in
- * DEL,INS,NONE,SNP or -1, length) or NULL.  num_threads <= 0: all hardware threads.  Fails (NSC_E_INVALID,
+ * DEL,INS,NONE,SNP, min(length, 3) -- the two class labels of dataloader.py:55,415) or NULL; an unknown type fails like
+ * the reference's KeyError.  num_threads <= 0: all hardware threads.  Fails (NSC_E_INVALID,
  * text in nsc_last_error) on malformed lines, like the reference's worker returning None. */
 int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* matrices, int32_t* meta,
                    float* anns255, int32_t* labels, int num_threads);

@@ -140,7 +140,10 @@ def call_sharded(cand, score_fn, rank=None, world_size=None, group=None):
     from .synth import Candidates
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if not 0 <= rank < world_size:
+        raise ValueError("rank %d outside [0, %d)" % (rank, world_size))
     lo, hi = shard_ranges(len(cand), world_size)[rank]
     part = Candidates(cand.matrices[lo:hi], cand.center[lo:hi], cand.tumor_cov[lo:hi], cand.normal_cov[lo:hi],
                       None if cand.anns is None else cand.anns[lo:hi], cand.tags[lo:hi])

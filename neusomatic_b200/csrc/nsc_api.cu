@@ -21,18 +21,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 // expected parameter sizes (network.py:41-64); returns -1 for unknown names, 0 for ignored
 static int64_t expected_numel(const nsc_model* m, const std::string& name) {
   auto ends_with = [&](const char* suf) {
@@ -135,8 +123,9 @@ static void free_workspace(nsc_model* m) {
   m->fc1_cap = 0;
 }
 
-// Allocates the workspace of the ACTIVE precision mode and sets m->chunk_cap to its chunk size.
-static int ensure_workspace(nsc_model* m) {
+// Sets m->chunk_cap to the chunk size of the ACTIVE precision mode and allocates what passes of min(B, chunk) candidates
+// need here (the tensor path sizes its own packed workspace per pass, grown on demand: umma_ensure_workspace).
+static int ensure_workspace(nsc_model* m, int64_t B) {
   int64_t cap;
   if (m->precision == NSC_PREC_FP32) {
     if (m->fp32_cap == 0) {
@@ -152,11 +141,15 @@ static int ensure_workspace(nsc_model* m) {
     if (c < 0) return NSC_E_CUDA;
     cap = c;
   }
-  if (m->fc1_cap < cap) {
+  const int64_t need = std::max<int64_t>(std::min<int64_t>(B, cap), 1);
+  if (m->fc1_cap < need) {
+    NSC_CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(m->fc1_out);
     m->fc1_out = nullptr;
-    NSC_CUDA_TRY(cudaMalloc((void**)&m->fc1_out, (size_t)cap * kFcHidden * sizeof(float)));
-    m->fc1_cap = cap;
+    m->fc1_cap = 0;
+    const int64_t n = std::min<int64_t>(cap, std::max<int64_t>(need, 2 * m->fc1_cap));
+    NSC_CUDA_TRY(cudaMalloc((void**)&m->fc1_out, (size_t)n * kFcHidden * sizeof(float)));
+    m->fc1_cap = n;
   }
   m->chunk_cap = cap;
   return NSC_OK;
@@ -166,6 +159,7 @@ static int ensure_xin(nsc_model* m) {
   if (m->xin && m->xin_cap >= m->chunk_cap) return NSC_OK;
   cudaFree(m->xin);
   m->xin = nullptr;
+  m->xin_cap = 0;
   NSC_CUDA_TRY(cudaMalloc((void**)&m->xin, (size_t)m->chunk_cap * m->C * kH * kW * sizeof(float)));
   m->xin_cap = m->chunk_cap;
   return NSC_OK;
@@ -331,13 +325,13 @@ int nsc_forward_f32(nsc_model* m, const float* x_dev, int64_t B, float* type_log
   if (B > 0 && x_dev == nullptr) { set_error("x_dev is NULL"); return NSC_E_INVALID; }
   DeviceGuard g(m->device);
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
-  if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
+  if ((rc = ensure_workspace(m, B)) != NSC_OK) return rc;
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = ws_acquire(m, s)) != NSC_OK) return rc;
   for (int64_t i = 0; i < B; i += m->chunk_cap) {
     int64_t n = std::min<int64_t>(m->chunk_cap, B - i);
-    if ((rc = forward_chunk(m, x_dev + i * m->C * kH * kW, n, o.offset(i), s)) != NSC_OK) return rc;
+    if ((rc = forward_chunk(m, x_dev + i * m->C * kH * kW, n, o.offset(i), s)) != NSC_OK) { ws_release(m, s); return rc; }
   }
   return ws_release(m, s);
 }
@@ -353,7 +347,7 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
   if (!(coverage_thr > 0.f)) { set_error("coverage_thr must be positive"); return NSC_E_INVALID; }
   DeviceGuard g(m->device);
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
-  if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
+  if ((rc = ensure_workspace(m, B)) != NSC_OK) return rc;
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
   cudaStream_t s = (cudaStream_t)stream;
   const int na = m->C - kBaseCh;
@@ -361,8 +355,10 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
   for (int64_t i = 0; i < B; i += m->chunk_cap) {
     int64_t n = std::min<int64_t>(m->chunk_cap, B - i);
     if ((rc = forward_chunk_u8(m, matrices_dev + i * (kH * kW * kStoredCh), meta_dev + i * 3,
-                               anns255_dev ? anns255_dev + i * na : nullptr, coverage_thr, n, o.offset(i), s)) != NSC_OK)
+                               anns255_dev ? anns255_dev + i * na : nullptr, coverage_thr, n, o.offset(i), s)) != NSC_OK) {
+      ws_release(m, s);
       return rc;
+    }
   }
   return ws_release(m, s);
 }
@@ -382,11 +378,11 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
   }
   DeviceGuard g(m->device);
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
-  if ((rc = ensure_workspace(m)) != NSC_OK) return rc;
+  if ((rc = ensure_workspace(m, std::min<int64_t>(B, u8 ? 16384 : 8192))) != NSC_OK) return rc;
   if ((rc = ensure_host_path(m)) != NSC_OK) return rc;
   // slice size of the copy/compute pipeline: small enough that the first H2D does not delay the first kernel,
   // large enough to keep the layer kernels efficient
-  const int64_t cap = std::min<int64_t>(m->chunk_cap, u8 ? 16384 : 8192);
+  const int64_t cap = std::min<int64_t>(std::min<int64_t>(m->chunk_cap, u8 ? 16384 : 8192), std::max<int64_t>(B, 1024));
   const int na = m->C - kBaseCh;
   const size_t in_per = u8 ? (size_t)kH * kW * kStoredCh : (size_t)m->C * kH * kW * sizeof(float);
   const size_t meta_per = u8 ? 3 * sizeof(int32_t) : 0;
@@ -394,19 +390,23 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
   const size_t in_bytes = (in_per + meta_per + ann_per) * cap + 1024;
   const size_t out_per = 19 * sizeof(float);
   if (m->hstage_in_bytes < in_bytes) {
+    NSC_CUDA_TRY(cudaDeviceSynchronize());
+    m->hstage_in_bytes = 0;        // a failed allocation below must not leave a stale size behind a NULL buffer
     for (int i = 0; i < 2; ++i) {
       cudaFree(m->hstage_in[i]);
       m->hstage_in[i] = nullptr;
-      NSC_CUDA_TRY(cudaMalloc(&m->hstage_in[i], in_bytes));
     }
+    for (int i = 0; i < 2; ++i) NSC_CUDA_TRY(cudaMalloc(&m->hstage_in[i], in_bytes));
     m->hstage_in_bytes = in_bytes;
   }
   if (m->hstage_out_cap < cap) {
+    NSC_CUDA_TRY(cudaDeviceSynchronize());
+    m->hstage_out_cap = 0;
     for (int i = 0; i < 2; ++i) {
       cudaFree(m->hstage_out[i]);
       m->hstage_out[i] = nullptr;
-      NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
     }
+    for (int i = 0; i < 2; ++i) NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
     m->hstage_out_cap = cap;
   }
   cudaStream_t s_in = m->hstream[0], s_cmp = m->hstream[1], s_out = m->hstream[2];
@@ -417,43 +417,56 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
   cudaEvent_t* out_free = &m->hevent[6];
   // the first slice is small: its host-to-device copy is the only one no kernel overlaps
   const int64_t first = std::min<int64_t>(cap, 4096);
-  int64_t it = 0, n_prev = 0;
-  for (int64_t i = 0; i < B; i += n_prev, ++it) {
-    const int slot = (int)(it & 1);
-    const int64_t n = std::min<int64_t>(it == 0 ? first : cap, B - i);
-    n_prev = n;
-    char* din = (char*)m->hstage_in[slot];
-    char* dmeta = din + ((in_per * cap + 255) / 256) * 256;
-    char* dann = dmeta + ((meta_per * cap + 255) / 256) * 256;
-    if (it >= 2) NSC_CUDA_TRY(cudaStreamWaitEvent(s_in, in_free[slot], 0));
-    NSC_CUDA_TRY(cudaMemcpyAsync(din, (const char*)in_host + i * in_per, in_per * n, cudaMemcpyHostToDevice, s_in));
-    if (u8) {
-      NSC_CUDA_TRY(cudaMemcpyAsync(dmeta, meta_host + i * 3, meta_per * n, cudaMemcpyHostToDevice, s_in));
-      if (ann_per) NSC_CUDA_TRY(cudaMemcpyAsync(dann, anns_host + i * na, ann_per * n, cudaMemcpyHostToDevice, s_in));
+  // the slices are enqueued by a lambda so that EVERY failure leaves through the same exit: the copies into the caller's
+  // host buffers that are already in flight are waited for and the workspace event is recorded before the error returns
+  auto enqueue = [&]() -> int {
+    int64_t it = 0, n_prev = 0;
+    for (int64_t i = 0; i < B; i += n_prev, ++it) {
+      const int slot = (int)(it & 1);
+      const int64_t n = std::min<int64_t>(it == 0 ? first : cap, B - i);
+      n_prev = n;
+      char* din = (char*)m->hstage_in[slot];
+      char* dmeta = din + ((in_per * cap + 255) / 256) * 256;
+      char* dann = dmeta + ((meta_per * cap + 255) / 256) * 256;
+      if (it >= 2) NSC_CUDA_TRY(cudaStreamWaitEvent(s_in, in_free[slot], 0));
+      NSC_CUDA_TRY(cudaMemcpyAsync(din, (const char*)in_host + i * in_per, in_per * n, cudaMemcpyHostToDevice, s_in));
+      if (u8) {
+        NSC_CUDA_TRY(cudaMemcpyAsync(dmeta, meta_host + i * 3, meta_per * n, cudaMemcpyHostToDevice, s_in));
+        if (ann_per) NSC_CUDA_TRY(cudaMemcpyAsync(dann, anns_host + i * na, ann_per * n, cudaMemcpyHostToDevice, s_in));
+      }
+      NSC_CUDA_TRY(cudaEventRecord(in_ready[slot], s_in));
+      NSC_CUDA_TRY(cudaStreamWaitEvent(s_cmp, in_ready[slot], 0));
+      if (it >= 2) NSC_CUDA_TRY(cudaStreamWaitEvent(s_cmp, out_free[slot], 0));
+      float* dout = (float*)m->hstage_out[slot];
+      Outputs od{dout, dout + 4 * cap, dout + 5 * cap, dout + 9 * cap, dout + 13 * cap,
+                 (int32_t*)(dout + 17 * cap), (int32_t*)(dout + 18 * cap)};
+      if (u8) {
+        if ((rc = forward_chunk_u8(m, (const uint8_t*)din, (const int32_t*)dmeta, ann_per ? (const float*)dann : nullptr,
+                                   coverage_thr, n, od, s_cmp)) != NSC_OK) return rc;
+      } else {
+        if ((rc = forward_chunk(m, (const float*)din, n, od, s_cmp)) != NSC_OK) return rc;
+      }
+      NSC_CUDA_TRY(cudaEventRecord(in_free[slot], s_cmp));
+      NSC_CUDA_TRY(cudaEventRecord(out_ready[slot], s_cmp));
+      NSC_CUDA_TRY(cudaStreamWaitEvent(s_out, out_ready[slot], 0));
+      NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_logits + 4 * i, od.type_logits, 16 * n, cudaMemcpyDeviceToHost, s_out));
+      NSC_CUDA_TRY(cudaMemcpyAsync(oh.pos + i, od.pos, 4 * n, cudaMemcpyDeviceToHost, s_out));
+      NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_logits + 4 * i, od.len_logits, 16 * n, cudaMemcpyDeviceToHost, s_out));
+      if (oh.type_prob) NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_prob + 4 * i, od.type_prob, 16 * n, cudaMemcpyDeviceToHost, s_out));
+      if (oh.len_prob) NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_prob + 4 * i, od.len_prob, 16 * n, cudaMemcpyDeviceToHost, s_out));
+      if (oh.type_argmax) NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_argmax + i, od.type_argmax, 4 * n, cudaMemcpyDeviceToHost, s_out));
+      if (oh.len_argmax) NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_argmax + i, od.len_argmax, 4 * n, cudaMemcpyDeviceToHost, s_out));
+      NSC_CUDA_TRY(cudaEventRecord(out_free[slot], s_out));
     }
-    NSC_CUDA_TRY(cudaEventRecord(in_ready[slot], s_in));
-    NSC_CUDA_TRY(cudaStreamWaitEvent(s_cmp, in_ready[slot], 0));
-    if (it >= 2) NSC_CUDA_TRY(cudaStreamWaitEvent(s_cmp, out_free[slot], 0));
-    float* dout = (float*)m->hstage_out[slot];
-    Outputs od{dout, dout + 4 * cap, dout + 5 * cap, dout + 9 * cap, dout + 13 * cap,
-               (int32_t*)(dout + 17 * cap), (int32_t*)(dout + 18 * cap)};
-    if (u8) {
-      if ((rc = forward_chunk_u8(m, (const uint8_t*)din, (const int32_t*)dmeta, ann_per ? (const float*)dann : nullptr,
-                                 coverage_thr, n, od, s_cmp)) != NSC_OK) return rc;
-    } else {
-      if ((rc = forward_chunk(m, (const float*)din, n, od, s_cmp)) != NSC_OK) return rc;
-    }
-    NSC_CUDA_TRY(cudaEventRecord(in_free[slot], s_cmp));
-    NSC_CUDA_TRY(cudaEventRecord(out_ready[slot], s_cmp));
-    NSC_CUDA_TRY(cudaStreamWaitEvent(s_out, out_ready[slot], 0));
-    NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_logits + 4 * i, od.type_logits, 16 * n, cudaMemcpyDeviceToHost, s_out));
-    NSC_CUDA_TRY(cudaMemcpyAsync(oh.pos + i, od.pos, 4 * n, cudaMemcpyDeviceToHost, s_out));
-    NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_logits + 4 * i, od.len_logits, 16 * n, cudaMemcpyDeviceToHost, s_out));
-    if (oh.type_prob) NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_prob + 4 * i, od.type_prob, 16 * n, cudaMemcpyDeviceToHost, s_out));
-    if (oh.len_prob) NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_prob + 4 * i, od.len_prob, 16 * n, cudaMemcpyDeviceToHost, s_out));
-    if (oh.type_argmax) NSC_CUDA_TRY(cudaMemcpyAsync(oh.type_argmax + i, od.type_argmax, 4 * n, cudaMemcpyDeviceToHost, s_out));
-    if (oh.len_argmax) NSC_CUDA_TRY(cudaMemcpyAsync(oh.len_argmax + i, od.len_argmax, 4 * n, cudaMemcpyDeviceToHost, s_out));
-    NSC_CUDA_TRY(cudaEventRecord(out_free[slot], s_out));
+    return NSC_OK;
+  };
+  rc = enqueue();
+  if (rc != NSC_OK) {
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_cmp);
+    cudaStreamSynchronize(s_out);
+    cudaEventRecord(m->ws_event, s_cmp);
+    return rc;
   }
   if ((rc = ws_release(m, s_cmp)) != NSC_OK) return rc;
   NSC_CUDA_TRY(cudaStreamSynchronize(s_out));

@@ -39,6 +39,22 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
+// RAII: make `dev` current for the duration of an entry point and restore the caller's device (PyTorch owns the
+// process's current-device state; the library must not change it behind its back)
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct Outputs {
   float* type_logits;
   float* pos;

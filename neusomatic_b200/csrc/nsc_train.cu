@@ -54,6 +54,10 @@ struct nsc_trainer {
   float* head_w = nullptr;                                   // [9][240] gathered head weights / gradients
   float* head_g = nullptr;
   float* zeros = nullptr;                                    // 64 zeros (bias of the data-gradient convolutions)
+  // bad-label flag: host-mapped, written by the loss kernels (a class label outside [0,4) -- the reference's
+  // CrossEntropyLoss raises on those); read without a synchronisation at the next entry point
+  int* flag_h = nullptr;
+  int* flag_d = nullptr;
 };
 
 namespace nsc {
@@ -560,9 +564,14 @@ __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict_
 
 // sum of class weights of the batch (normaliser of the weighted cross entropies)
 __global__ void loss_weights_kernel(const int32_t* __restrict__ y1, const int32_t* __restrict__ y3, const float* __restrict__ w1,
-                                    const float* __restrict__ w3, int N, double* __restrict__ acc /*[8]*/) {
+                                    const float* __restrict__ w3, int N, double* __restrict__ acc /*[8]*/, int* __restrict__ flag) {
   double a = 0.0, b = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) { a += w1[y1[i]]; b += w3[y3[i]]; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int c1 = y1[i], c3 = y3[i];
+    if ((unsigned)c1 >= 4u || (unsigned)c3 >= 4u) { *flag = 1; continue; }   // never index the weights with it
+    a += w1[c1];
+    b += w3[c3];
+  }
   atomicAdd(&acc[0], a);
   atomicAdd(&acc[1], b);
 }
@@ -579,6 +588,10 @@ __global__ void loss_kernel(const float* __restrict__ logits, const int32_t* __r
     for (int g = 0; g < 2; ++g) {
       const float* z = o + (g ? 5 : 0);
       const int y = g ? y3[i] : y1[i];
+      if ((unsigned)y >= 4u) {                       // flagged by loss_weights_kernel: no loss, no gradient from this row
+        for (int j = 0; j < 4; ++j) d[(g ? 5 : 0) + j] = 0.f;
+        continue;
+      }
       const float wy = g ? w3[y] : w1[y];
       const double sw = g ? sw3 : sw1;
       float mx = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
@@ -598,8 +611,9 @@ __global__ void loss_kernel(const float* __restrict__ logits, const int32_t* __r
   atomicAdd(&acc[4], l3);
 }
 
-__global__ void loss_store_kernel(const double* __restrict__ acc, float* __restrict__ out /*[4]*/) {
+__global__ void loss_store_kernel(const double* __restrict__ acc, float* __restrict__ out /*[4]*/, const int* __restrict__ flag) {
   if (threadIdx.x == 0) {
+    if (*flag) { out[0] = out[1] = out[2] = out[3] = __int_as_float(0x7fc00000); return; }   // NaN: a label was out of range
     out[0] = (float)(acc[2] + acc[3] + acc[4]);
     out[1] = (float)acc[2];
     out[2] = (float)acc[3];
@@ -705,8 +719,16 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
     set_error("no CUDA device %d available; libneusomatic_cuda has no CPU fallback", device);
     return NSC_E_CUDA;
   }
-  NSC_CUDA_TRY(cudaSetDevice(device));
-  nsc_trainer* t = new nsc_trainer();
+  cudaDeviceProp prop;
+  NSC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return NSC_E_CUDA;
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", device); return NSC_E_CUDA; }
+  nsc_trainer* t = new (std::nothrow) nsc_trainer();
+  if (!t) { set_error("out of host memory"); return NSC_E_NOMEM; }
   t->device = device;
   t->C = num_channels;
   t->max_batch = max_batch;
@@ -718,7 +740,7 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   }
   if (t->tensor_fwd || t->tensor_bwd || t->tensor_wgrad) {
     int rc = umma_train_init(&t->dummy, max_batch);
-    if (rc != NSC_OK) { delete t; return rc; }
+    if (rc != NSC_OK) { nsc_trainer_destroy(t); return rc; }
   }
   // parameter layout: nn.Module.named_parameters() order (network.py:41-64)
   int64_t off = 0;
@@ -769,7 +791,14 @@ int nsc_trainer_create(nsc_trainer** out, int device, int num_channels, int64_t 
   e = e ? e : alloc(&t->head_w, 9 * kFcHidden * 4); e = e ? e : alloc(&t->head_g, 9 * kFcHidden * 4);
   e = e ? e : alloc(&t->zeros, 64 * 4);
   e = e ? e : cudaMemset(t->zeros, 0, 64 * 4);
-  if (e != cudaSuccess) { set_error("trainer workspace allocation failed: %s", cudaGetErrorString(e)); return NSC_E_NOMEM; }
+  e = e ? e : cudaHostAlloc((void**)&t->flag_h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+  if (!e) { *t->flag_h = 0; e = cudaHostGetDevicePointer((void**)&t->flag_d, t->flag_h, 0); }
+  if (e != cudaSuccess) {
+    set_error("trainer workspace allocation failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    nsc_trainer_destroy(t);        // frees whatever was allocated so far
+    return NSC_E_NOMEM;
+  }
   *out = t;
   return NSC_OK;
 }
@@ -814,7 +843,14 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
     return NSC_E_INVALID;
   }
   if (B < 2 || B > t->max_batch) { set_error("batch size %lld outside [2, %lld]", (long long)B, (long long)t->max_batch); return NSC_E_INVALID; }
-  NSC_CUDA_TRY(cudaSetDevice(t->device));
+  DeviceGuard guard(t->device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", t->device); return NSC_E_CUDA; }
+  if (*(volatile int*)t->flag_h) {
+    *t->flag_h = 0;
+    set_error("an earlier step was given class labels outside [0,4) (type in DEL,INS,NONE,SNP; length = min(len, 3), "
+              "dataloader.py:415); its losses are NaN and its gradients skip those rows");
+    return NSC_E_INVALID;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const int N = (int)B;
   const float eps = 1e-5f;
@@ -887,11 +923,11 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_RUN(run_gemm(N, 9, kFcHidden, t->h, kFcHidden, 1, t->head_w, 1, kFcHidden, t->logits, 9, head_b, 0, s));
   // ---------------- loss ----------------
   NSC_CUDA_TRY(cudaMemsetAsync(t->red, 0, 8 * sizeof(double), s));
-  loss_weights_kernel<<<8, 256, 0, s>>>(type_labels, len_labels, w_type_dev, w_len_dev, N, t->red);
+  loss_weights_kernel<<<8, 256, 0, s>>>(type_labels, len_labels, w_type_dev, w_len_dev, N, t->red, t->flag_d);
   NSC_LAUNCH_OK();
   loss_kernel<<<8, 256, 0, s>>>(t->logits, type_labels, centers, len_labels, w_type_dev, w_len_dev, N, t->red, t->dlogits);
   NSC_LAUNCH_OK();
-  if (losses_dev) { loss_store_kernel<<<1, 32, 0, s>>>(t->red, losses_dev); NSC_LAUNCH_OK(); }
+  if (losses_dev) { loss_store_kernel<<<1, 32, 0, s>>>(t->red, losses_dev, t->flag_d); NSC_LAUNCH_OK(); }
   // ---------------- backward: linear layers ----------------
   // d head weights [9][240] = dlogits^T h ; biases = column sums ; dh = dlogits * head_w, masked by ReLU
   NSC_RUN(run_gemm(9, kFcHidden, N, t->dlogits, 1, 9, t->h, kFcHidden, 1, t->head_g, kFcHidden, nullptr, 0, s, t->gpart, t->gpart_floats));
@@ -978,6 +1014,11 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
 int nsc_sgd_momentum_update(float* params, float* momentum_buf, const float* grads, int64_t n, float lr, float momentum,
                             float grad_scale, void* stream) {
   if (!params || !momentum_buf || !grads || n < 0) { set_error("bad argument"); return NSC_E_INVALID; }
+  cudaPointerAttributes pa;
+  NSC_CUDA_TRY(cudaPointerGetAttributes(&pa, params));
+  if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) { set_error("params is not device memory"); return NSC_E_INVALID; }
+  DeviceGuard guard(pa.device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", pa.device); return NSC_E_CUDA; }
   sgd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(params, momentum_buf, grads, n, lr, momentum, grad_scale);
   NSC_CUDA_TRY(cudaGetLastError());
   return NSC_OK;
@@ -985,8 +1026,9 @@ int nsc_sgd_momentum_update(float* params, float* momentum_buf, const float* gra
 
 int nsc_trainer_destroy(nsc_trainer* t) {
   if (!t) return NSC_OK;
-  cudaSetDevice(t->device);
+  DeviceGuard guard(t->device);
   cudaDeviceSynchronize();
+  if (t->flag_h) cudaFreeHost(t->flag_h);
   cudaFree(t->u0); cudaFree(t->a0);
   for (int i = 0; i < 5; ++i) cudaFree(t->x[i]);
   for (int i = 0; i < 4; ++i) { cudaFree(t->u1[i]); cudaFree(t->a1[i]); cudaFree(t->u2[i]); cudaFree(t->z[i]); }

@@ -196,6 +196,8 @@ void decode_range(DecodeJob* job) {
           for (int i = 0; i < 4; ++i)
             if (strlen(kTypes[i]) == tn && memcmp(kTypes[i], dots[4] + 1, tn) == 0) type_idx = i;
           if (!ok) snprintf(msg, sizeof msg, "line %zu: non-integer tag field", li);
+          // type_class_dict[tag.split(".")[4]] raises KeyError in the reference (dataloader.py:55)
+          else if (type_idx < 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: unknown variant type in tag", li); }
         }
       }
       // image: base64 -> zlib -> uint8[5,32,23]  (dataloader.py:38-39)
@@ -221,7 +223,7 @@ void decode_range(DecodeJob* job) {
         job->meta[k * 3 + 0] = (int32_t)center;
         job->meta[k * 3 + 1] = (int32_t)tcov;
         job->meta[k * 3 + 2] = (int32_t)ncov;
-        if (job->labels) { job->labels[k * 2 + 0] = type_idx; job->labels[k * 2 + 1] = (int32_t)length; }
+        if (job->labels) { job->labels[k * 2 + 0] = type_idx; job->labels[k * 2 + 1] = (int32_t)(length < 3 ? length : 3); }   // varlen_label = min(length, 3), dataloader.py:415
         // annotations: float(text) * 255.0 in float64, cast to fp32 (dataloader.py:395-396, then .float())
         int na = 0;
         Field a;

@@ -1048,25 +1048,53 @@ void umma_free(nsc_model* m) {
   u.cap = 0;
 }
 
-static int umma_ensure_workspace(nsc_model* m) {
+static int64_t umma_chunk_limit() {
+  int64_t cap = 32768;   // candidates per pass over the layer kernels
+  if (const char* e = getenv("NSC_CHUNK")) cap = std::max<int64_t>(64, atoll(e));
+  return (cap + 7) / 8 * 8;
+}
+
+static void umma_free_workspace(UmmaState& u) {
+  for (int i = 0; i < 3; ++i)
+    for (int p = 0; p < 3; ++p) { cudaFree(u.buf[i][p]); u.buf[i][p] = nullptr; }
+  for (int p = 0; p < 2; ++p) { cudaFree(u.xin[p]); u.xin[p] = nullptr; }
+  cudaFree(u.fc_in); u.fc_in = nullptr;
+  u.cap = 0;
+}
+
+// Workspace for passes of up to `need` candidates (grown on demand, at least doubling, never beyond the chunk limit).
+// Per candidate: 9 packed tensors of 5 x 32 x 64 x 2 B (three activations x {fp16 hi, fp16 lo, c8}) = 184 KB, the packed
+// network input 2 x 5 x 32 x Cpad x 2 B (20 KB for C = 26, 82 KB for C = 119) and 5 KB of fc1 input: ~210 KB (C = 26),
+// i.e. 6.9 GB at the 32 768-candidate chunk limit and 0.2 GB for a batch of 1000.
+static int umma_ensure_workspace(nsc_model* m, int64_t need) {
   UmmaState& u = m->umma;
-  if (u.cap > 0) return NSC_OK;
+  const int64_t limit = umma_chunk_limit();
+  need = std::min<int64_t>(std::max<int64_t>(need, 8), limit);
+  if (u.cap >= need) return NSC_OK;
   if (!u.weights_fit_fp16) {
     set_error("folded convolution weights exceed the fp16 range; use NSC_PREC_FP32 for this checkpoint");
     return NSC_E_STATE;
   }
-  int64_t cap = 32768;   // candidates per pass over the layer kernels (workspace: ~125 KB per candidate)
-  if (const char* e = getenv("NSC_CHUNK")) cap = std::max<int64_t>(64, atoll(e));
-  cap = (cap + 7) / 8 * 8;
+  int64_t cap = std::min<int64_t>(limit, std::max<int64_t>(need, 2 * u.cap));
+  cap = std::max<int64_t>((cap + 7) / 8 * 8, 1024);
+  NSC_CUDA_TRY(cudaDeviceSynchronize());      // nothing may still be reading the old buffers
+  umma_free_workspace(u);
   const size_t bytes = (size_t)cap * kH * 32 * 64 * sizeof(uint16_t);
-  for (int i = 0; i < 3; ++i)
-    for (int p = 0; p < 3; ++p) {   // x16 | exact lo16 | c8 (128 bytes per position: the same size)
-      NSC_CUDA_TRY(cudaMalloc((void**)&u.buf[i][p], bytes));
-      NSC_CUDA_TRY(cudaMemset(u.buf[i][p], 0, bytes));
-    }
   const size_t xbytes = (size_t)cap * kH * 32 * (u.nk1 * 32) * sizeof(uint16_t);
-  for (int p = 0; p < 2; ++p) NSC_CUDA_TRY(cudaMalloc((void**)&u.xin[p], xbytes));
-  NSC_CUDA_TRY(cudaMalloc((void**)&u.fc_in, (size_t)cap * kFcIn * sizeof(float)));
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 3 && !e; ++i)
+    for (int p = 0; p < 3 && !e; ++p) {   // x16 | exact lo16 | c8 (128 bytes per position: the same size)
+      e = cudaMalloc((void**)&u.buf[i][p], bytes);
+      if (!e) e = cudaMemset(u.buf[i][p], 0, bytes);
+    }
+  for (int p = 0; p < 2 && !e; ++p) e = cudaMalloc((void**)&u.xin[p], xbytes);
+  if (!e) e = cudaMalloc((void**)&u.fc_in, (size_t)cap * kFcIn * sizeof(float));
+  if (e != cudaSuccess) {
+    set_error("tensor-path workspace for %lld candidates: %s", (long long)cap, cudaGetErrorString(e));
+    cudaGetLastError();
+    umma_free_workspace(u);       // no half-allocated state behind cap == 0
+    return e == cudaErrorMemoryAllocation ? NSC_E_NOMEM : NSC_E_CUDA;
+  }
   u.cap = cap;
   NSC_CUDA_TRY(cudaDeviceGetAttribute(&u.num_sms, cudaDevAttrMultiProcessorCount, m->device));
   return NSC_OK;
@@ -1157,8 +1185,8 @@ static int dbg_unpack(nsc_model* m, int which, uint16_t* const t[2], int W, int6
 }
 
 int umma_max_chunk(nsc_model* m) {
-  int rc = umma_ensure_workspace(m);
-  return rc == NSC_OK ? (int)m->umma.cap : -1;
+  (void)m;
+  return (int)umma_chunk_limit();     // the workspace itself is sized by the passes that run (umma_ensure_workspace)
 }
 
 static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s);
@@ -1166,7 +1194,7 @@ static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s);
 int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o, cudaStream_t s) {
   if (n == 0) return NSC_OK;
   int rc;
-  if ((rc = umma_ensure_workspace(m)) != NSC_OK) return rc;
+  if ((rc = umma_ensure_workspace(m, n)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
   {
     ProfScope prof(m, 11, s);
@@ -1182,7 +1210,7 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
                           int64_t n, const Outputs& o, cudaStream_t s) {
   if (n == 0) return NSC_OK;
   int rc;
-  if ((rc = umma_ensure_workspace(m)) != NSC_OK) return rc;
+  if ((rc = umma_ensure_workspace(m, n)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
   if ((rc = assemble_pack(m, mat, meta, anns255, coverage_thr, n, u.xin[0], u.xin[1], u.nk1 * 32, s)) != NSC_OK) return rc;
   return umma_run(m, n, o, s);

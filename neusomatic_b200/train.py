@@ -87,9 +87,28 @@ class Trainer:
         off, num = self.slices[name]
         return self.grads[off:off + num]
 
+    def _check(self, name, t, dtype, shape):
+        """The C ABI takes raw pointers: a wrong dtype (e.g. PyTorch's default int64 labels), device, stride or shape would
+        be read as garbage.  Label VALUES are range-checked on the device (a label outside [0,4) makes the step's losses NaN
+        and the next call fail; the reference's CrossEntropyLoss raises)."""
+        if not isinstance(t, torch.Tensor) or t.device != self.dev:
+            raise ValueError("%s must be a tensor on %s" % (name, self.dev))
+        if t.dtype != dtype:
+            raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+
     def forward_backward(self, x, labels, centers, len_labels, w_type, w_len):
         """x [B,C,5,32] fp32 CUDA; labels / len_labels int32 CUDA [B]; centers fp32 CUDA [B]; class weights CUDA [4]."""
         B = x.shape[0]
+        self._check("x", x, torch.float32, (B, self.C, 5, 32))
+        self._check("labels", labels, torch.int32, (B,))
+        self._check("centers", centers, torch.float32, (B,))
+        self._check("len_labels", len_labels, torch.int32, (B,))
+        self._check("w_type", w_type, torch.float32, (4,))
+        self._check("w_len", w_len, torch.float32, (4,))
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         _lib.check(self.lib.nsc_train_forward_backward(
             self.h, self.params.data_ptr(), self.running.data_ptr(), x.data_ptr(), labels.data_ptr(), centers.data_ptr(),
