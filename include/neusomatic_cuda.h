@@ -214,6 +214,9 @@ int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len);
 /* tags of candidates [first, first + n), each followed by '\n', copied into buf (cap bytes); *needed = bytes required
  * (call with buf = NULL to size the buffer).  One call instead of n: the tag strings are the keys of call.py's dictionaries. */
 int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t cap, int64_t* needed);
+/* lens [n,2] int32 = (len(ref), len(alt)) of the tags of candidates [first, first + n): what call.py:343-350
+ * (pred_vcf_records_none) branches on, so that the none.vcf filter can run on whole arrays */
+int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* lens);
 int nsc_tsv_close(nsc_tsv* t);
 
 #ifdef __cplusplus

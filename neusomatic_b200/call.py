@@ -10,16 +10,29 @@
                                ``nsc_score_host_u8`` (channel assembly fused on the device).
   * ``shard_ranges``        -- contiguous per-rank candidate ranges for multi-GPU scoring
                                (no collective; replaces nn.DataParallel of call.py:417-419).
+  * ``PredTable``           -- the same ``{path: entry}`` dictionaries kept as whole-batch arrays and materialised
+                               per entry on access (the reference builds ~40 Python objects per candidate; most
+                               candidates are NONE and are only ever looked at by the none.vcf filter).
+  * ``call_neusomatic``     -- call.py:389-554, same signature: candidate TSVs + FASTA + checkpoint -> ``pred.vcf`` /
+                               ``none.vcf``, decode / score / post-processing overlapped.
+  * ``pred_vcf_records*``, ``get_vcf_records``, ``write_vcf``, ``get_type`` -- re-exported from ``vcf.py``
+                               (call.py:121-387).
 """
 from __future__ import annotations
 
+import collections.abc
+import concurrent.futures
 import gc
 import logging
+import os
 
 import numpy as np
 import torch
 
 from .engine import Engine, VARTYPE_CLASSES, anns_to_255
+from .fasta import open_fasta
+from .vcf import (get_type, get_vcf_records, pred_vcf_records, pred_vcf_records_none,      # noqa: F401  (reference names)
+                  pred_vcf_records_path, vcf_lines, write_vcf)
 
 logger = logging.getLogger(__name__)
 
@@ -82,36 +95,168 @@ def build_pred_dicts(o1, o2, o3, p1, p3, arg1, arg3, paths, vartype_classes=VART
     return final_preds, none_preds
 
 
+def non_transformed_images(matrices, center):
+    """dataloader.py:398-404: uint8 [n,5,32,3] = (reference plane, tumor plane, centre marker) of compact candidates --
+    the image call.py:89-95 hands to pred_vcf_records_path (there through a PNG file)."""
+    matrices = np.asarray(matrices)
+    n = matrices.shape[0]
+    out = np.zeros((n, 5, 32, 3), np.uint8)
+    out[..., 0:2] = matrices[..., 0:2]
+    mx = matrices[..., 0].reshape(n, -1).max(1) if n else np.zeros(0, np.uint8)
+    out[np.arange(n), :, np.asarray(center, np.int64), 2] = mx[:, None]
+    return out
+
+
+class PredTable(collections.abc.Mapping):
+    """``{path: [type, pos, len, probs_type, probs_len, logits_type, logits_len]}`` of call.py:96-114 held as whole-batch
+    arrays.  Entries are materialised on access with the reference's element types (np.float32 scalars in the four lists,
+    the [1]-shaped row of ``o2``, the numpy integer of the length argmax); a later candidate with the same tag replaces an
+    earlier one and keeps its place in the iteration order, like assignment into a dict.  ``none_records`` is the
+    whole-array form of pred_vcf_records_none (call.py:336-354)."""
+
+    def __init__(self, vartype_classes=VARTYPE_CLASSES):
+        self.classes = list(vartype_classes)
+        self._paths = []                  # all rows, in arrival order
+        self._parts = []                  # per add(): (a1, o2, a3, P1, P3, O1, O3, lens)
+        self._cat = None
+        self._index = {}
+        self._indexed = 0
+
+    def add(self, paths, a1, o2, a3, p1, p3, o1, o3, lens=None):
+        """Rows of one batch; the probability / logit arrays are rounded here (np.round on float32 == round(x, 4))."""
+        if len(paths) == 0:
+            return
+        f32 = lambda a: np.asarray(a, np.float32)
+        self._paths.extend(paths)
+        self._parts.append((np.asarray(a1, np.int64), f32(o2).reshape(len(paths), -1), np.asarray(a3, np.int64),
+                            np.round(f32(p1), 4), np.round(f32(p3), 4), np.round(f32(o1), 4), np.round(f32(o3), 4),
+                            None if lens is None else np.asarray(lens, np.int32)))
+        self._cat = None
+
+    def _arrays(self):
+        if self._cat is None:
+            parts = self._parts
+            cols = [np.concatenate([p[j] for p in parts]) for j in range(7)] if parts else [np.zeros((0,))] * 7
+            lens = None
+            if parts and all(p[7] is not None for p in parts):
+                lens = np.concatenate([p[7] for p in parts])
+            self._cat = cols + [lens]
+            self._parts = [tuple(self._cat)] if parts else []
+        return self._cat
+
+    def _idx(self):
+        n = len(self._paths)
+        if self._indexed != n:
+            self._index.update(zip(self._paths[self._indexed:], range(self._indexed, n)))
+            self._indexed = n
+        return self._index
+
+    def _entry(self, r):
+        a1, o2, a3, P1, P3, O1, O3, _ = self._arrays()
+        return [self.classes[a1[r]], o2[r], a3[r], list(P1[r]), list(P3[r]), list(O1[r]), list(O3[r])]
+
+    def __getitem__(self, path):
+        return self._entry(self._idx()[path])
+
+    def __iter__(self):
+        return iter(self._idx())
+
+    def __len__(self):
+        return len(self._idx())
+
+    def __contains__(self, path):
+        return path in self._idx()
+
+    def none_records(self, chroms):
+        """call.py:336-354 on arrays: prob by allele-length class in float32, keep prob > 0.005, materialise only those."""
+        idx = self._idx()
+        if not idx:
+            return {}.items()
+        rows = np.fromiter(idx.values(), np.int64, len(idx))
+        _, _, _, P1, P3, _, _, lens = self._arrays()
+        if lens is None:
+            lens = np.array([[len(f[2]), len(f[3])] for f in (p.split(".") for p in self._paths)], np.int32).reshape(-1, 2)
+        rl, al = lens[rows, 0], lens[rows, 1]
+        P1r, P3r = P1[rows], P3[rows]
+        one = np.float32(1)
+        prob = np.where(rl == al, P1r[:, 3] * P3r[:, 1], np.where(rl < al, P1r[:, 1] * (one - P3r[:, 0]), P1r[:, 0] * (one - P3r[:, 0])))
+        records = {}
+        for j in np.nonzero(prob > 0.005)[0]:
+            r = rows[j]
+            path = self._paths[r]
+            chrom, pos, ref, alt = path.split(".")[:4]
+            records[path] = [chroms[int(chrom)], pos, ref, alt, prob[j], [path, self._entry(r)]]
+        return records.items()
+
+
+def _score_batch(net, matrices):
+    """One batch through the drop-in module -> host array [B,19] = (o1 4, o2 1, o3 4, softmax(o1) 4, softmax(o3) 4, argmax
+    o1, argmax o3): logits, probabilities and argmax all come out of the library's fused head kernel, one D2H per batch.
+    Under nn.DataParallel (call.py:417-419) the batch is split over the module's devices by hand: every device runs its
+    own engine on its slice (launches are asynchronous, so the devices overlap)."""
+    inner, devices = net, None
+    if isinstance(net, torch.nn.DataParallel):
+        inner, devices = net.module, list(net.device_ids)
+    if not hasattr(inner, "score"):
+        raise TypeError("call_variants needs a neusomatic_b200.network.NeuSomaticNet")
+    if not devices or len(devices) == 1 or matrices.shape[0] < 2 * len(devices):
+        dev = next(inner.parameters()).device
+        outs = [inner.score(matrices.to(dev, non_blocking=True))]
+    else:
+        outs = [inner.score(c.to("cuda:%d" % d, non_blocking=True))
+                for c, d in zip(matrices.chunk(len(devices)), devices)]
+    parts = []
+    for o1, o2, o3, p1, p3, a1, a3 in outs:
+        parts.append(torch.cat([o1, o2, o3, p1, p3, a1.float()[:, None], a3.float()[:, None]], 1).cpu())
+    return torch.cat(parts, 0).numpy()
+
+
 def call_variants(net, vartype_classes, call_loader, out_dir, model_tag, use_cuda):
-    """call.py:54-118.  ``net`` is a ``neusomatic_b200.network.NeuSomaticNet`` (possibly wrapped
-    in nn.DataParallel).  ``true_path`` maps each non-NONE candidate to its in-memory
-    ``non_transformed[:, :, 0:3]`` uint8 matrix (the reference writes it to a PNG, a lossless
-    round trip: call.py:89-95,128)."""
+    """call.py:54-118, same signature and return value ``(final_preds, none_preds, true_path)``.
+
+    ``net`` is a ``neusomatic_b200.network.NeuSomaticNet`` (possibly wrapped in nn.DataParallel).  ``true_path`` maps
+    every non-NONE candidate to its ``non_transformed[:, :, 0:3]`` image.  When the reference's hand-over directory
+    ``{out_dir}/matrices_{model_tag}`` exists and ``imageio`` is installed -- i.e. inside the reference's own
+    call_neusomatic -- the image is written there as a PNG and ``true_path`` holds the file name, exactly as call.py:89-95
+    does, so the unmodified ``pred_vcf_records_path`` (call.py:128 ``imread``) keeps working.  Otherwise ``true_path`` holds
+    the uint8 [5,32,3] array itself, which this package's ``pred_vcf_records_path`` accepts (the PNG is a lossless round
+    trip of exactly these bytes)."""
     if not use_cuda:
         raise RuntimeError("neusomatic_b200 scores on CUDA only")
     net.eval()
     final_preds, none_preds, true_path = {}, {}, {}
+    png_dir, imwrite = None, None
+    if out_dir is not None:
+        d = "{}/matrices_{}".format(out_dir, model_tag)
+        if os.path.isdir(d):
+            try:
+                from imageio import imwrite
+                png_dir = d
+            except ImportError:
+                png_dir = None
     iii = j = 0
     for data in call_loader:
         (matrices, labels, var_pos_s, var_len_s, non_transformed_matrices), (paths) = data
         iii += 1
         j += len(paths[0])
-        matrices = matrices.cuda(non_blocking=True)
         with torch.no_grad():
-            outputs, _ = net(matrices)
-        o1, o2, o3 = outputs
-        # one D2H per batch; softmax / argmax batched on the device
-        packed = torch.cat([o1, o2, o3, torch.softmax(o1, 1), torch.softmax(o3, 1),
-                            torch.max(o1, 1)[1].float()[:, None], torch.max(o3, 1)[1].float()[:, None]], 1).cpu().numpy()
+            packed = _score_batch(net, matrices)
         n_before = len(final_preds)
         build_pred_dicts(packed[:, 0:4], packed[:, 4:5], packed[:, 5:9], packed[:, 9:13], packed[:, 13:17],
                          packed[:, 17].astype(np.int64), packed[:, 18].astype(np.int64), paths[0],
                          vartype_classes, final_preds, none_preds)
-        if len(final_preds) != n_before:
+        if len(final_preds) != n_before or png_dir is not None:
             nt = np.asarray(non_transformed_matrices)
             for i, path_ in enumerate(paths[0]):
                 path = path_.split("/")[-1]
-                if path in final_preds and path not in true_path:
+                if path not in final_preds:
+                    continue
+                if png_dir is not None:
+                    file_name = "{}/{}.png".format(png_dir, path)
+                    if not os.path.exists(file_name):
+                        imwrite(file_name, np.array(nt[i, :, :, 0:3]))
+                    true_path[path] = file_name
+                elif path not in true_path:
                     true_path[path] = np.array(nt[i, :, :, 0:3])
         if iii % 10 == 0:
             logger.info("Called {} candidates in this batch.".format(j))
@@ -179,6 +324,8 @@ class CandidateScorer:
             raise ValueError("checkpoint has %d input channels" % C)
         self.meta = meta
         self.coverage_thr = float(meta["coverage_thr"])
+        if precision is None and os.environ.get("NSC_PRECISION"):      # NSC_PREC_* for entry points without a precision argument
+            precision = int(os.environ["NSC_PRECISION"])
         self.engine = Engine(sd, C, device=device, precision=precision,
                              normalize_channels=meta["normalize_channels"])
         self.C = C
@@ -208,15 +355,207 @@ class CandidateScorer:
         return build_pred_dicts(r["o1"], r["o2"], r["o3"], r["p1"], r["p3"], r["arg1"], r["arg3"], cand.tags,
                                 VARTYPE_CLASSES, final_preds, none_preds)
 
-    def call_tsv(self, path, batch=65536, num_threads=0, final_preds=None, none_preds=None):
-        """call.py:504-534 for one candidates_*.tsv: C++ decode (csrc/nsc_tsv.cpp) -> nsc_score_host_u8 ->
-        (final_preds, none_preds), in slices of ``batch`` candidates."""
-        from .tsv import CandidateTSV
-        tsv = CandidateTSV(path, num_anns=self.C - 26, num_threads=num_threads)
-        final_preds = {} if final_preds is None else final_preds
-        none_preds = {} if none_preds is None else none_preds
-        for first in range(0, len(tsv), batch):
-            cand = tsv.decode(first, min(batch, len(tsv) - first))
-            self.call(cand, final_preds, none_preds)
-        tsv.close()
+    def call_table(self, cand, final_preds=None, none_preds=None, true_path=None):
+        """Like ``call`` but into PredTables (arrays, entries on access); fills ``true_path`` with the images of the
+        non-NONE candidates when a dict is given."""
+        final_preds = PredTable() if final_preds is None else final_preds
+        none_preds = PredTable() if none_preds is None else none_preds
+        r = self.score(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, cand.anns, getattr(cand, "anns255", None))
+        _split_into_tables(r, cand.tags, None, cand.matrices, cand.center, final_preds, none_preds, true_path)
         return final_preds, none_preds
+
+    def call_tsv(self, path, batch=65536, num_threads=0, final_preds=None, none_preds=None, true_path=None):
+        """call.py:504-534 for one candidates_*.tsv: C++ decode (csrc/nsc_tsv.cpp) -> nsc_score_host_u8 -> PredTables
+        ``(final_preds, none_preds)``, in slices of ``batch`` candidates, the three stages overlapped (the decoder threads
+        fill slot k+1 while the GPU scores slot k and the host files slot k-1)."""
+        final_preds = PredTable() if final_preds is None else final_preds
+        none_preds = PredTable() if none_preds is None else none_preds
+        run_tsv_pipeline([self], [(path, 0, None)], batch, num_threads, final_preds, none_preds, true_path)
+        return final_preds, none_preds
+
+
+def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds, true_path):
+    """Files one scored slice: rows predicted NONE go to ``none_preds``, the others to ``final_preds`` (call.py:88-114);
+    ``true_path`` receives the non_transformed image of every non-NONE candidate (call.py:89-95)."""
+    a1 = np.asarray(r["arg1"])
+    none_idx = VARTYPE_CLASSES.index("NONE")
+    var = np.nonzero(a1 != none_idx)[0]
+    if any("/" in t for t in tags[:1]) or (len(tags) and "/" in tags[-1]):
+        tags = [t[t.rfind("/") + 1:] for t in tags]                  # path_.split("/")[-1]
+    cols = ("arg1", "o2", "arg3", "p1", "p3", "o1", "o3")
+    if len(var) == 0:
+        none_preds.add(tags, *[np.array(r[c]) for c in cols], lens=lens)
+        return
+    non = np.nonzero(a1 == none_idx)[0]
+    vt = [tags[i] for i in var]
+    final_preds.add(vt, *[np.asarray(r[c])[var] for c in cols], lens=None if lens is None else lens[var])
+    none_preds.add([tags[i] for i in non], *[np.asarray(r[c])[non] for c in cols], lens=None if lens is None else lens[non])
+    if true_path is not None:
+        img = non_transformed_images(np.asarray(matrices)[var], np.asarray(center)[var])
+        for t, im in zip(vt, img):
+            true_path[t] = im
+
+
+class _Slot:
+    """Pinned host buffers of one in-flight slice: decoder output = scorer input, and the scorer's host results."""
+
+    def __init__(self, n, num_anns):
+        pin = torch.cuda.is_available()
+        mk = lambda shape, dt: (torch.empty(shape, dtype=dt).pin_memory() if pin else torch.empty(shape, dtype=dt))
+        self.n = n
+        self.matrices = mk((n, 5, 32, 23), torch.uint8)
+        self.meta = mk((n, 3), torch.int32)
+        self.anns = mk((n, num_anns), torch.float32) if num_anns else None
+        self.out = Engine._host_out(n, True, pin)
+
+
+def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_preds, true_path=None):
+    """Decode -> score -> file, overlapped.  ``pieces`` = [(tsv path, first candidate, count or None)]; slices of at most
+    ``batch`` candidates go round-robin to ``scorers`` (one per GPU: the path shards by candidate, no collective).  One
+    decoder thread (the C++ decoder fans out over ``num_threads`` itself), one scoring thread per GPU and one filing
+    thread; the ctypes calls release the GIL, so only the filing stage competes for it."""
+    from .tsv import CandidateTSV
+    num_anns = scorers[0].C - 26
+    tsvs, slices = {}, []
+    try:
+        for path, first, count in pieces:
+            if path not in tsvs:
+                tsvs[path] = CandidateTSV(path, num_anns=num_anns, num_threads=num_threads)
+            n = len(tsvs[path]) - first if count is None else count
+            for f0 in range(first, first + n, batch):
+                slices.append((path, f0, min(batch, first + n - f0)))
+        if not slices:
+            return
+        cap = max(s[2] for s in slices)
+        slots = [_Slot(cap, num_anns) for _ in range(min(len(slices), 2 + len(scorers)))]
+
+        def decode(k, wait_for):
+            if wait_for is not None:
+                wait_for.result()                       # the slot's previous slice has been filed
+            path, f0, n = slices[k]
+            slot = slots[k % len(slots)]
+            t = tsvs[path]
+            t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
+                                 "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
+            return t.tags(f0, n), t.allele_lens(f0, n)
+
+        def score(k, fdec):
+            tags, lens = fdec.result()
+            n = slices[k][2]
+            slot = slots[k % len(slots)]
+            sc = scorers[k % len(scorers)]
+            outs = [None if t is None else t[:n] for t in slot.out]
+            sc.engine.score_host_u8(slot.matrices[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
+                                    sc.coverage_thr, extras=True, out=outs)
+            return tags, lens, outs
+
+        def file_slice(k, fsc):
+            tags, lens, outs = fsc.result()
+            n = slices[k][2]
+            slot = slots[k % len(slots)]
+            names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
+            r = {nm: t.numpy() for nm, t in zip(names, outs)}
+            _split_into_tables(r, tags, lens, slot.matrices[:n].numpy(), slot.meta[:n, 0].numpy(), final_preds, none_preds,
+                               true_path)
+
+        TPE = concurrent.futures.ThreadPoolExecutor
+        with TPE(1) as dec_ex, TPE(1) as file_ex:
+            sc_ex = [TPE(1) for _ in scorers]
+            try:
+                filed = []
+                for k in range(len(slices)):
+                    wait_for = filed[k - len(slots)] if k >= len(slots) else None
+                    fd = dec_ex.submit(decode, k, wait_for)
+                    fs = sc_ex[k % len(scorers)].submit(score, k, fd)
+                    filed.append(file_ex.submit(file_slice, k, fs))
+                for f in filed:
+                    f.result()
+            finally:
+                for ex in sc_ex:
+                    ex.shutdown(wait=True)
+    finally:
+        for t in tsvs.values():
+            t.close()
+
+
+def plan_call_groups(counts, max_load_candidates):
+    """The grouping of call.py:468-507 on candidate counts: files longer than max_load_candidates / 2 are cut into pieces
+    of max(1, max_load_candidates / 2) candidates (the reference re-writes them with merge_tsvs; here a piece is a range of
+    the same file), the pieces are sorted by size and taken in groups that end as soon as they hold more than
+    max_load_candidates / 10 candidates.  ``counts`` = [(path, candidates)]; returns [[(path, first, count), ...], ...]."""
+    pieces = []
+    for path, L in counts:
+        if L + 1 > max_load_candidates / 2:
+            per = int(max(1, max_load_candidates / 2))
+            pieces += [(path, f0, min(per, L - f0)) for f0 in range(0, L, per)]
+        else:
+            pieces.append((path, 0, L))
+    pieces.sort(key=lambda x: x[2])
+    groups, cur, cur_l = [], [], 0
+    for i, pc in enumerate(pieces):
+        cur.append(pc)
+        cur_l += pc[2]
+        if cur_l > max_load_candidates / 10 or i == len(pieces) - 1:
+            groups.append(cur)
+            cur, cur_l = [], 0
+    return groups
+
+
+def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, batch_size, max_load_candidates,
+                    pass_threshold, lowqual_threshold, ensemble, use_cuda):
+    """call.py:389-554, same arguments and outputs (``{out_dir}/pred.vcf`` -- returned -- and ``{out_dir}/none.vcf``).
+
+    Differences in mechanism, none in results: the candidates are decoded by the C++ reader into pinned batches and scored
+    through ``nsc_score_host_u8`` on every visible GPU (candidate slices round-robin; the reference wraps the module in
+    nn.DataParallel, call.py:417-419); oversized TSVs are read in ranges instead of being re-written by merge_tsvs; the
+    pileup images go to pred_vcf_records_path in memory instead of through PNG files; ``batch_size`` only bounds the slice
+    size from below (a slice is the unit of the decode / score / file pipeline, not of the arithmetic)."""
+    from .tsv import CandidateTSV
+    if not use_cuda:
+        raise RuntimeError("neusomatic_b200 scores on CUDA only (no CPU fallback); the reference's CPU path is call.py itself")
+    logger.info("-----------------Call Somatic Mutations--------------------")
+    fasta = open_fasta(ref_file)
+    chroms = list(fasta.references)
+    chroms_order = {c: i for i, c in enumerate(chroms)}
+    vartype_classes = list(VARTYPE_CLASSES)
+    ck = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location="cpu", weights_only=True)
+    n_dev = max(1, torch.cuda.device_count())
+    if n_dev > 1:
+        logger.info("We use {} GPUs!".format(n_dev))
+    scorers = [CandidateScorer(ck, ensemble=ensemble, device=d) for d in range(n_dev)]
+    logger.info("tag: {}".format(scorers[0].meta["tag"]))
+    if not os.path.exists(out_dir):
+        os.mkdir(out_dir)
+    try:
+        counts = []
+        for f in candidates_tsv:
+            t = CandidateTSV(f, num_anns=scorers[0].C - 26)
+            counts.append((f, len(t)))
+            t.close()
+        all_vcf_records, all_vcf_records_none = [], []
+        slice_size = int(min(65536, max(batch_size, 16384)))
+        for group in plan_call_groups(counts, max_load_candidates):
+            logger.info("Run for candidate files: {}".format(sorted({g[0] for g in group})))
+            n_group = sum(g[2] for g in group)
+            logger.info("N_dataset: {}".format(n_group))
+            if n_group == 0:
+                logger.warning("Skip {} with 0 candidates".format(group[-1][0]))
+                continue
+            final_preds, none_preds, true_path = PredTable(vartype_classes), PredTable(vartype_classes), {}
+            run_tsv_pipeline(scorers, group, slice_size, num_threads, final_preds, none_preds, true_path)
+            logger.info("Called {} candidates in this batch.".format(n_group))
+            all_vcf_records.extend(pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, num_threads))
+            all_vcf_records_none.extend(pred_vcf_records_none(none_preds, chroms))
+    finally:
+        for sc in scorers:
+            sc.engine.close()
+    all_vcf_records = dict(all_vcf_records)
+    all_vcf_records_none = dict(all_vcf_records_none)
+    logger.info("Prepare Output VCF")
+    output_vcf = "{}/pred.vcf".format(out_dir)
+    write_vcf(get_vcf_records(all_vcf_records), output_vcf, chroms_order, pass_threshold, lowqual_threshold)
+    logger.info("Prepare Non-Somatics VCF")
+    write_vcf(get_vcf_records(all_vcf_records_none), "{}/none.vcf".format(out_dir), chroms_order, pass_threshold,
+              lowqual_threshold)
+    logger.info("Calling is Done.")
+    return output_vcf

@@ -340,6 +340,37 @@ int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t 
   return NSC_OK;
 }
 
+int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* lens) {
+  if (!t || !lens || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  for (int64_t i = first; i < first + n; ++i) {
+    const char* p = t->data + t->line_start[(size_t)i];
+    const char* end = t->data + t->line_start[(size_t)i + 1];
+    Field f;
+    for (int k = 0; k < 3; ++k)
+      if (!next_field(p, end, &f)) { nsc::set_error("line %lld: no tag field", (long long)i); return NSC_E_INVALID; }
+    const char* tb = f.p;
+    const char* te = f.p + f.n;
+    for (const char* q = te; q > tb; --q)
+      if (q[-1] == '/') { tb = q; break; }          // path_.split("/")[-1]
+    // chrom.pos.ref.alt.type...: lengths of the third and fourth dot-separated fields
+    int field = 0;
+    const char* fs = tb;
+    int32_t rl = -1, al = -1;
+    for (const char* q = tb; q <= te; ++q) {
+      if (q == te || *q == '.') {
+        if (field == 2) rl = (int32_t)(q - fs);
+        if (field == 3) { al = (int32_t)(q - fs); break; }
+        ++field;
+        fs = q + 1;
+      }
+    }
+    if (rl < 0 || al < 0) { nsc::set_error("line %lld: tag does not have 9 fields", (long long)i); return NSC_E_INVALID; }
+    lens[(i - first) * 2] = rl;
+    lens[(i - first) * 2 + 1] = al;
+  }
+  return NSC_OK;
+}
+
 int nsc_tsv_close(nsc_tsv* t) {
   if (!t) return NSC_OK;
   if (t->data) munmap((void*)t->data, t->size);

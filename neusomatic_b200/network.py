@@ -34,6 +34,20 @@ def _(x, engine_key):
     return [x.new_empty((B, 4)), x.new_empty((B, 1)), x.new_empty((B, 4))]
 
 
+@torch.library.custom_op("neusomatic_b200::score_f32", mutates_args=())
+def _score_f32_op(x: torch.Tensor, engine_key: int) -> list[torch.Tensor]:
+    """Logits + the fused softmax / argmax of both classification heads (call.py:80-83,97-100) from the same launch."""
+    return _ENGINES[engine_key].forward_f32(x, extras=True)
+
+
+@_score_f32_op.register_fake
+def _(x, engine_key):
+    B = x.shape[0]
+    i32 = dict(dtype=torch.int32)
+    return [x.new_empty((B, 4)), x.new_empty((B, 1)), x.new_empty((B, 4)), x.new_empty((B, 4)), x.new_empty((B, 4)),
+            x.new_empty((B,), **i32), x.new_empty((B,), **i32)]
+
+
 class NSBlock(nn.Module):
     """network.py:17-36 (module structure only; the fused kernels implement the forward)."""
 
@@ -114,6 +128,16 @@ class NeuSomaticNet(nn.Module):
         x3 = F.relu(self.fc1(x2))
         internal_outs.extend([x2, x3])
         return [self.fc2(x3), self.fc3(x3), self.fc4(x3)], internal_outs
+
+    def score(self, x):
+        """[o1, o2, o3, softmax(o1), softmax(o3), argmax(o1), argmax(o3)] of a CUDA batch in one library call: what
+        call_variants reads per batch (call.py:77-83, 97-100)."""
+        if not x.is_cuda:
+            raise RuntimeError("neusomatic_b200.NeuSomaticNet scores on CUDA only (sm_100a kernels); no CPU fallback")
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        return _score_f32_op(x, self.engine(x.device))
 
     def forward(self, x):
         if self.training:

@@ -65,8 +65,14 @@ def uniform_pileups(n, seed=1234, ensemble=False):
     return Candidates(m, center, tcov, ncov, anns, _tags(rng, vtype, center, length, tcov, ncov))
 
 
-def structured_pileups(n, seed=1234, ensemble=False):
-    """S2: one-hot reference row, tumor/normal count rows with a planted variant at ``center``.
+def _structured(n, seed, ensemble, window=None):
+    """S2 (see structured_pileups); also returns the planted layout for genome_candidates.
+
+    ``window``: None = all 32 columns populated (the golden parity sets); an int = the scanner's layout
+    (generate_dataset.py:452-458: 2 * matrix_base_pad + 1 = 15 reference columns plus the insertion columns, centred in the
+    32-column matrix, empty columns either side, the variant in the middle of the window).
+
+    S2: one-hot reference row, tumor/normal count rows with a planted variant at ``center``.
 
     Channel semantics follow generate_dataset.py:598-653: 0 reference, 1/2 tumor/normal base
     counts, 3/4 mean BQ, 5/6 mean MQ, 7/8 forward strand, 9-12 clips, 13-22 five tag means;
@@ -78,6 +84,12 @@ def structured_pileups(n, seed=1234, ensemble=False):
     center = rng.integers(7, 25, size=n).astype(np.int32)
     vtype = rng.choice(4, size=n, p=[0.15, 0.15, 0.35, 0.35])  # DEL, INS, NONE, SNP
     length = np.where(vtype == 2, 0, np.where(vtype == 3, 1, rng.integers(1, 5, size=n)))
+    colmask = None
+    if window is not None:
+        ncols = window + np.where(vtype == 1, length, 0)
+        off = (W - ncols) // 2
+        center = (off + window // 2).astype(np.int32)
+        colmask = (np.arange(W)[None, :] >= off[:, None]) & (np.arange(W)[None, :] < (off + ncols)[:, None])
     tcov = rng.integers(10, 401, size=n).astype(np.int32)
     ncov = rng.integers(10, 401, size=n).astype(np.int32)
     af_t = np.where(vtype == 2, rng.uniform(0.0, 0.02, size=n), rng.uniform(0.03, 0.6, size=n))
@@ -126,12 +138,66 @@ def structured_pileups(n, seed=1234, ensemble=False):
         for t, (lo, hi) in enumerate(((0, 6), (80, 100), (0, 60), (0, 100), (0, 12))):
             m[..., 13 + 2 * t + k] = on * rng.uniform(lo, hi, size=(n, H, W)) / 100.0 * 255
     mat = np.clip(m, 0, 255).astype(np.uint8)
+    if colmask is not None:
+        mat *= colmask[:, None, :, None].astype(np.uint8)
+        refrow = np.where(colmask, refrow, -1)              # -1: empty column (neither gap nor base)
     anns = None
     if ensemble:
         a = rng.random(size=(n, NUM_ANNS)) * (rng.random(size=(n, NUM_ANNS)) < 0.7)
         anns = np.round(a, 4).astype(np.float32)
+    layout = dict(vtype=vtype, length=length, refrow=refrow, altrow=altrow)
+    return rng, mat, center, tcov, ncov, anns, layout
+
+
+def structured_pileups(n, seed=1234, ensemble=False):
+    """S2: planted SNP/INS/DEL pileups with random (inconsistent) chrom/pos/ref/alt tag fields."""
+    rng, mat, center, tcov, ncov, anns, lay = _structured(n, seed, ensemble)
     return Candidates(mat, center, tcov, ncov, anns,
-                      _tags(rng, vtype, center, length, tcov, ncov))
+                      _tags(rng, lay["vtype"], center, lay["length"], tcov, ncov))
+
+
+GENOME_CHROMS = ["chr1", "chr2", "chrX"]
+
+
+def genome_candidates(n, seed=1234, ensemble=False, window=15):
+    """S2 pileups whose tags AND a synthetic reference genome are consistent with the matrices, so that the
+    reference's VCF stage (call.py:121-305) accepts them: the non-gap reference columns of candidate i map to
+    consecutive positions of its own 1 kb region of chromosome ``i % 3`` and the tag carries the pos/ref/alt the
+    scanner would have written (generate_dataset.py:598-657 anchors: SNP column = pos, DEL column = pos + 1,
+    INS column - 1 = pos).  Returns (Candidates, {chrom name: sequence}, chrom names)."""
+    rng, mat, center, tcov, ncov, anns, lay = _structured(n, seed, ensemble, window)
+    g = np.random.Generator(np.random.PCG64(seed + 7919))
+    acgt = "ACGT"
+    per = (n + len(GENOME_CHROMS) - 1) // len(GENOME_CHROMS)
+    seqs = [list(np.array(list(acgt))[g.integers(0, 4, size=1000 * per + 200)]) for _ in GENOME_CHROMS]
+    tags = []
+    for i in range(n):
+        ci, g0 = i % len(GENOME_CHROMS), 1000 * (i // len(GENOME_CHROMS)) + 101      # 1-based position of the first column
+        refrow, altrow = lay["refrow"][i], lay["altrow"][i]
+        nz = [c for c in range(W) if refrow[c] > 0]
+        col2pos = {c: g0 + j for j, c in enumerate(nz)}
+        for c in nz:
+            seqs[ci][col2pos[c] - 1] = acgt[refrow[c] - 1]
+        vt, ce, ln = int(lay["vtype"][i]), int(center[i]), int(lay["length"][i])
+        base = lambda pos: seqs[ci][pos - 1]
+        if vt == 0:                                   # DEL: ref = anchor base + deleted bases
+            pos = col2pos[ce] - 1
+            ref = "".join(base(pos + k) for k in range(ln + 1))
+            alt = base(pos)
+        elif vt == 1:                                 # INS: alt = anchor base + inserted bases
+            pos = col2pos[ce - 1]
+            ref = base(pos)
+            alt = ref + "".join(acgt[max(int(altrow[ce + k]), 1) - 1] for k in range(ln))
+        else:                                         # SNP / NONE
+            pos = col2pos[ce]
+            ref = base(pos)
+            alt = acgt[int(altrow[ce]) - 1] if altrow[ce] > 0 else acgt[(acgt.index(ref) + 1) % 4]
+        tags.append("{}.{}.{}.{}.{}.{}.{}.{}.{}".format(ci, pos, ref, alt, VARTYPE_CLASSES[vt], ce, ln,
+                                                        int(tcov[i]), int(ncov[i])))
+    fasta = {name: "".join(sq) for name, sq in zip(GENOME_CHROMS, seqs)}
+    return Candidates(mat, center, tcov, ncov, anns, tags), fasta, list(GENOME_CHROMS)
+
+
 
 
 def random_state_dict(num_channels, seed=0):

@@ -40,6 +40,14 @@ class CandidateTSV:
         _lib.check(self.lib.nsc_tsv_tags(self.h, first, n, buf, need.value, C.byref(need)))
         return buf.raw[:need.value - 1].decode().split("\n")
 
+    def allele_lens(self, first=0, n=None):
+        """int32 [n,2] = (len(ref), len(alt)) of the candidates' tags (what the none.vcf filter branches on, call.py:343-350)."""
+        n = len(self) - first if n is None else n
+        lens = np.empty((n, 2), np.int32)
+        if n:
+            _lib.check(self.lib.nsc_tsv_allele_lens(self.h, first, n, lens.ctypes.data))
+        return lens
+
     def decode(self, first=0, n=None, out=None, with_tags=True):
         """Returns Candidates(matrices uint8 [n,5,32,23], center, tumor_cov, normal_cov, anns255-or-None, tags).
         ``out`` may hold preallocated (pinned) arrays: dict(matrices=, meta=, anns255=)."""

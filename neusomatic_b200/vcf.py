@@ -1,0 +1,305 @@
+"""Dictionaries -> VCF: the host stage behind the scoring path (reference neusomatic/python/call.py:121-387 and
+utils.py:84-95), restated on the in-memory pileup matrices this package keeps instead of PNG files.
+
+Same entry points, argument meaning and results as the reference:
+
+  * ``pred_vcf_records_path(record)``   call.py:121-305  one non-NONE candidate -> ``[path, [chrom, pos, ref, alt, prob,
+                                        [path, pred]]]`` or ``[]``; ``record[1]`` may be the reference's PNG file name or the
+                                        uint8 ``[5, 32, 3]`` matrix itself, ``record[5]`` a FASTA path or an open reader
+  * ``pred_vcf_records``                call.py:308-333
+  * ``pred_vcf_records_none``           call.py:336-354
+  * ``get_vcf_records`` / ``write_vcf`` call.py:357-387
+  * ``prob2phred``                      utils.py:84-95 (the arithmetic stays in the type of ``p``: np.float32 here)
+
+Parity is pinned by ``tests/golden/vcf_*.npz`` (outputs of the UNMODIFIED reference functions and of the reference's whole
+``call_neusomatic`` on synthetic candidates; ``tests/golden/make_golden_vcf.py``) and checked in ``tests/test_vcf.py``.
+The expressions that decide a comparison are kept in the reference's form on purpose (Python ``sum`` / ``min`` / ``max`` /
+``round`` over np.float32 scalars, comparisons against Python floats): the dictionaries hold np.float32 values and numpy's
+scalar promotion decides borderline cases.
+"""
+from __future__ import annotations
+
+import logging
+import multiprocessing
+import traceback
+
+import numpy as np
+
+from .fasta import open_fasta
+
+ACGT = "ACGT"
+# constants of the centre refinement (call.py:148-151)
+MIN_ACCEPTABLE_PROBMAX = 0.05
+CENTER_DIST_ROUNDBACK = 0.8
+TOO_FAR_CENTER = 3
+NEIGH_BASES = 7
+
+
+def get_type(ref, alt):
+    """call.py:43-51."""
+    d = len(ref) - len(alt.split(",")[0])
+    return "DEL" if d > 0 else ("INS" if d < 0 else "SNP")
+
+
+def prob2phred(p, max_phred=100):
+    """utils.py:84-95."""
+    assert 0 <= p <= 1
+    if p == 1:
+        return max_phred
+    if p == 0:
+        return 0
+    q = -10 * np.log10(1 - p)
+    return max_phred if q > max_phred else q
+
+
+def _load_image(src):
+    """The ``non_transformed_matrices[i, :, :, 0:3]`` image of a candidate as float64 in [0, 1] (call.py:128)."""
+    if isinstance(src, str):
+        from imageio import imread            # the reference's PNG hand-over, if a caller still uses it
+        src = imread(src)
+    return np.asarray(src) / 255.0
+
+
+class _Pileup:
+    """Column bookkeeping of one candidate image: plane 0 = reference, plane 1 = tumor counts, rows = (gap, A, C, G, T)."""
+
+    def __init__(self, image):
+        self.I = image
+        self.width = image.shape[1]
+        ref = image[:, :, 0]
+        top = np.argmax(ref, 0)
+        depth = sum(ref, 0) > 0                # Python sum over the rows, as the reference
+        self.gap_cols = np.where((top == 0) & depth)[0]       # zref_pos: reference gap = insertion columns
+        self.base_cols = np.where((top > 0) & depth)[0]       # nzref_pos
+
+    def ref_base(self, col):
+        return ACGT[np.argmax(self.I[1:, col, 0])]
+
+    def tumor_base(self, col):
+        return ACGT[np.argmax(self.I[1:, col, 1])]
+
+    def tumor_depth(self, col):
+        return sum(self.I[1:, col, 1])
+
+    def second_tumor_base(self, col):
+        """The tumor base after the reference base's row is taken out (call.py:223-226)."""
+        rb = np.argmax(self.I[1:, col, 0])
+        t = self.I[1:, col, 1].copy()
+        t[rb] = 0
+        return ACGT[rb], ACGT[np.argmax(t)]
+
+
+def _refine_center(pl, pred, center, ref, alt, vartype_classes):
+    """call.py:152-191: walks the type probabilities from the largest down until one gives a centre column within
+    TOO_FAR_CENTER of the candidate's.  Mutates ``pred[3]`` in place (a rejected class is zeroed), as the reference does on
+    its shallow copy.  Returns (type or "NONE", centre column, ins_no_zref_pos, centre prediction)."""
+    ins_no_gap = False
+    center_pred = None
+    while True:
+        probs = pred[3]
+        if sum(probs) < MIN_ACCEPTABLE_PROBMAX:
+            break
+        amx = np.argmax(probs)
+        type_pred = vartype_classes[amx]
+        if type_pred == "NONE":
+            break
+        center_pred = min(max(0, pred[1][0]), pl.width - 1)
+        if abs(center_pred - center) < CENTER_DIST_ROUNDBACK:
+            col = center
+        else:
+            col = int(round(center_pred))
+        if type_pred != "INS" and col in pl.gap_cols:
+            if center in pl.base_cols:
+                col = center
+            elif len(pl.base_cols) > 0:
+                col = pl.base_cols[np.argmin(abs(pl.base_cols - center_pred))]
+            else:
+                break
+        elif type_pred == "INS" and col in pl.base_cols:
+            if len(pl.gap_cols) == 0:
+                if len(alt) < len(ref) + NEIGH_BASES:
+                    break
+                col = center
+                ins_no_gap = True
+            elif center in pl.gap_cols:
+                col = center
+            else:
+                col = pl.gap_cols[np.argmin(abs(pl.gap_cols - center_pred))]
+        if abs(col - center) > TOO_FAR_CENTER:
+            pred[3][amx] = 0
+            continue
+        pred[0] = type_pred
+        return type_pred, col, ins_no_gap, center_pred
+    return "NONE", None, ins_no_gap, center_pred
+
+
+def _snp_alleles(pl, col, len_pred):
+    """call.py:215-231."""
+    ref_, alt_ = "", ""
+    for i in range(len_pred):
+        right = pl.base_cols[pl.base_cols >= (col + i)]
+        if len(right) > 0:
+            c = right[np.argmin(abs(right - (col + i)))]
+            rb, ab = pl.second_tumor_base(c)
+            ref_ += rb
+            alt_ += ab
+            if pl.tumor_depth(c) == 0:
+                break
+    return ref_, alt_
+
+
+def pred_vcf_records_path(record):
+    """call.py:121-305.  Returns the VCF record of one candidate predicted as a variant, ``[]`` when the prediction does
+    not survive the checks, ``None`` after an exception (the reference logs and returns None; pred_vcf_records raises)."""
+    path, true_path_, pred_all, chroms, vartype_classes, ref_file = record
+    log = logging.getLogger("{} ({})".format(pred_vcf_records_path.__name__, multiprocessing.current_process().name))
+    try:
+        fasta = open_fasta(ref_file)
+        pl = _Pileup(_load_image(true_path_))
+        chrom, pos, ref, alt, _, center, _, _, _ = path.split(".")
+        center, pos = int(center), int(pos)
+
+        pred = list(pred_all)                  # shallow: pred[3] is the dictionary entry's own list
+        type_pred, col, ins_no_gap, center_pred = _refine_center(pl, pred, center, ref, alt, vartype_classes)
+        if type_pred == "NONE":
+            return []
+        len_pred = pred[2]
+
+        # column <-> reference position, anchored at the candidate's own column (call.py:199-216)
+        kind = get_type(ref, alt)
+        anchor = {"DEL": (pos + 1, center), "INS": (pos, center - 1), "SNP": (pos, center)}[kind]
+        col_2_pos = {c: j for j, c in enumerate(pl.base_cols)}
+        if anchor[1] not in col_2_pos:
+            return []
+        shift = anchor[0] - col_2_pos[anchor[1]]
+        for c in pl.base_cols:
+            col_2_pos[c] += shift
+        pos_2_col = {v: k for k, v in col_2_pos.items()}
+
+        if not abs(center_pred - center) < TOO_FAR_CENTER:
+            return []
+        if type_pred == "SNP":
+            pos_ = col_2_pos[col]
+            ref_, alt_ = _snp_alleles(pl, col, len_pred)
+            if not ref_:
+                return []
+        elif type_pred == "INS":
+            if ins_no_gap:
+                pos_, ref_, alt_ = pos, ref.upper(), alt.upper()
+            else:
+                pos_, left = -1, col - 1
+                for left in range(col - 1, 0, -1):           # nearest reference column left of the insertion
+                    if left in pl.base_cols:
+                        pos_ = col_2_pos[left]
+                        break
+                if pos_ == -1:
+                    return []
+                if pl.tumor_depth(left) == 0:
+                    return []
+                ref_ = pl.ref_base(left)
+                alt_ = ref_
+                if len_pred == 3:                            # class 3 = "3 or longer": trust the candidate's length
+                    len_pred = max(len(alt) - len(ref), len_pred)
+                for c in range(left + 1, pl.width):
+                    if c in pl.gap_cols:
+                        alt_ += pl.tumor_base(c)
+                    else:
+                        break
+                    if (len(alt_) - len(ref_)) >= len_pred:
+                        break
+        else:                                                # DEL
+            pos_ = col_2_pos[col] - 1
+            if pos_ not in pos_2_col:
+                return []
+            ref_ = pl.ref_base(pos_2_col[pos_])
+            alt_ = ref_
+            if len_pred == 3:
+                len_pred = max(len(ref) - len(alt), len_pred)
+            for c in range(col, pl.width):
+                if c in pl.base_cols:
+                    ref_ += pl.ref_base(c)
+                if (len(ref_) - len(alt_)) >= len_pred:
+                    break
+            if (len(ref_) - len(alt_)) < len_pred:
+                pos_, ref_, alt_ = pos, ref.upper(), alt.upper()
+        chrom_ = chroms[int(chrom)]
+        if fasta.fetch(chrom_, pos_ - 1, pos_ + len(ref_) - 1).upper() != ref_.upper():
+            return []
+        if ref_ == alt_:
+            return []
+
+        pred = list(pred_all)                  # the probabilities as the refinement loop left them
+        if type_pred == "SNP":
+            prob = pred[3][3] * (pred[4][1])
+        elif type_pred == "INS":
+            prob = pred[3][1] * (1 - pred[4][0]) if not ins_no_gap else pred[3][1]
+        else:
+            prob = pred[3][0] * (1 - pred[4][0])
+        return [path, [chrom_, pos_, ref_, alt_, prob, [path, pred]]]
+    except Exception as ex:      # noqa: BLE001  (reference behaviour: log, return None, the caller raises)
+        log.error(traceback.format_exc())
+        log.error(ex)
+        return None
+
+
+def pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, num_threads):
+    """call.py:308-333.  ``true_path[path]`` holds the uint8 [5,32,3] matrix (or a PNG file name).  The records are built
+    in this process when ``num_threads`` <= 1 or the batch is small, otherwise in a pool like the reference."""
+    fasta = open_fasta(ref_file)
+    args = [[path, true_path[path], final_preds[path], chroms, vartype_classes, fasta] for path in final_preds.keys()]
+    if num_threads > 1 and len(args) >= 4096 and isinstance(ref_file, str):
+        for a in args:
+            a[5] = ref_file                    # every worker opens its own reader
+        with multiprocessing.Pool(num_threads) as pool:
+            out = pool.map(pred_vcf_records_path, args, chunksize=256)
+    else:
+        out = [pred_vcf_records_path(a) for a in args]
+    for o in out:
+        if o is None:
+            raise Exception("pred_vcf_records_path failed!")
+    return list(filter(None, out))
+
+
+def pred_vcf_records_none(none_preds, chroms):
+    """call.py:336-354: candidates called NONE whose variant probability is still above 0.005 go to none.vcf."""
+    if hasattr(none_preds, "none_records"):         # call.PredTable: the same filter on whole arrays
+        return none_preds.none_records(chroms)
+    records = {}
+    for path, pred in none_preds.items():
+        chrom, pos, ref, alt, _, _, _, _, _ = path.split(".")
+        if len(ref) == len(alt):
+            prob = pred[3][3] * (pred[4][1])
+        elif len(ref) < len(alt):
+            prob = pred[3][1] * (1 - pred[4][0])
+        else:
+            prob = pred[3][0] * (1 - pred[4][0])
+        if prob > 0.005:
+            records[path] = [chroms[int(chrom)], pos, ref, alt, prob, [path, pred]]     # pos stays the tag's string
+    return records.items()
+
+
+def get_vcf_records(all_vcf_records):
+    """call.py:357-363."""
+    return [all_vcf_records[path][:-1] for path in all_vcf_records if all_vcf_records[path]]
+
+
+def vcf_lines(vcf_records, chroms_order, pass_threshold, lowqual_threshold):
+    """The lines write_vcf emits (call.py:366-387), in order, first occurrence of a repeated line only."""
+    records = sorted((r for r in vcf_records if len(r) > 0), key=lambda x: [chroms_order[x[0]], x[1]])
+    lines, seen = [], set()
+    for chrom_, pos_, ref_, alt_, prob in records:
+        if ref_ == alt_:
+            continue
+        filter_ = "PASS" if prob >= pass_threshold else ("LowQual" if prob >= lowqual_threshold else "REJECT")
+        line = "\t".join([chrom_, str(pos_), ".", ref_, alt_, "{:.4f}".format(np.round(prob2phred(prob), 4)), filter_,
+                          "SCORE={:.4f}".format(np.round(prob, 4)), "GT", "0/1"]) + "\n"
+        if line not in seen:
+            seen.add(line)
+            lines.append(line)
+    return lines
+
+
+def write_vcf(vcf_records, output_vcf, chroms_order, pass_threshold, lowqual_threshold):
+    """call.py:366-387."""
+    with open(output_vcf, "w") as ov:
+        ov.writelines(vcf_lines(vcf_records, chroms_order, pass_threshold, lowqual_threshold))

@@ -1,0 +1,60 @@
+"""GPU: the whole call path -- candidate TSVs + FASTA + checkpoint -> pred.vcf / none.vcf through call_neusomatic
+(call.py:389-554) -- against the files the UNMODIFIED reference wrote for the same inputs on CPU
+(tests/golden/vcf_*.npz, tests/golden/make_golden_vcf.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, vcf_identity
+from oracle import nsnet_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_inputs(tmp_path, name):
+    g = dict(np.load(os.path.join(GOLDEN, "vcf_%s.npz" % name), allow_pickle=False))
+    tags = [str(t) for t in g["tags"]]
+    anns = g.get("anns")
+    split = int(g["split"])
+    tsvs = [str(tmp_path / "candidates_0.tsv"), str(tmp_path / "candidates_1.tsv")]
+    for p, (lo, hi) in zip(tsvs, ((0, split), (split, len(tags)))):
+        with open(p, "w") as f:
+            for i in range(lo, hi):
+                f.write(oracle.encode_tsv_line(i - lo, tags[i], g["matrices"][i], None if anns is None else anns[i]))
+    fa = str(tmp_path / "ref.fa")
+    with open(fa, "w") as f:
+        for k, s in json.loads(str(g["fasta"])).items():
+            f.write(">%s\n" % k)
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + "\n")
+    return g, tsvs, fa
+
+
+# (precision, minimum share of byte-identical pred.vcf lines).  FP32 mode: only last-bit differences of fp32 summation
+# order are left (the reference differs from itself by as much between batch sizes, tests/test_call_host.py).  Default mode
+# (split fp16 + fp8 corrections): probabilities move by up to ~1e-4, i.e. some 4-decimal SCOREs by one unit; the records
+# (chrom, pos, ref, alt), their order and the FILTER column must still be the reference's (vcf_identity asserts that).
+@pytest.mark.parametrize("precision,min_same", [(2, 0.97), (3, 0.80), (0, 0.80)])
+@pytest.mark.parametrize("name", ["std_v014", "std_wex", "ens_v014"])
+def test_call_neusomatic_writes_the_reference_vcf(tmp_path, monkeypatch, name, precision, min_same):
+    from neusomatic_b200.call import call_neusomatic
+    g, tsvs, fa = _write_inputs(tmp_path, name)
+    monkeypatch.setenv("NSC_PRECISION", str(precision))
+    out_dir = str(tmp_path / "out")
+    vcf_path = call_neusomatic(tsvs, fa, out_dir, os.path.join(GOLDEN, name + ".pth"), 2, 100, 2000, 0.7, 0.4,
+                               "anns" in g, True)
+    assert vcf_path == out_dir + "/pred.vcf"
+    same, total = vcf_identity(open(vcf_path).read(), str(g["pred_vcf"]))
+    same_n, total_n = vcf_identity(open(out_dir + "/none.vcf").read(), str(g["none_vcf"]))
+    print("%s precision %d: pred.vcf %d/%d lines identical, none.vcf %d/%d" % (name, precision, same, total, same_n, total_n))
+    assert same >= min_same * total
+    assert total == str(g["pred_vcf"]).count("\n")
+
+
+def test_call_neusomatic_needs_cuda_flag(tmp_path):
+    from neusomatic_b200.call import call_neusomatic
+    with pytest.raises(RuntimeError):
+        call_neusomatic([], "x.fa", str(tmp_path), os.path.join(GOLDEN, "std_v014.pth"), 1, 100, 1000, 0.7, 0.4, False, False)

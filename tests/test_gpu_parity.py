@@ -15,6 +15,9 @@ from neusomatic_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL_PROB, TOL_POS = 2e-3, 1e-3
+# share of 4-decimal probability entries that may differ from the reference's on a golden set in the tensor modes: the
+# measured worst case (profiles/r2_parity_large.json, tools/parity_report.py) plus a margin
+MAX_4DP_MISMATCH = 0.08
 MODES = [0, 2, 3]   # NSC_PREC_* modes that must meet the parity bar: split-fp16 tensor path, fp32 path, fp8-correction tensor path
 
 
@@ -182,7 +185,7 @@ def test_pred_dicts_match_oracle_call_variants(golden, precision):
     # fp32 path: rounding-boundary crossings only; tensor path: fp32-accumulate truncation in the tensor
     # cores moves probabilities by ~1e-4, i.e. about one 4-dp step on unsaturated candidates
     print("%s precision %d: 4-dp probability mismatch rate %.4f" % (name, precision, mism / tot))
-    assert mism / tot < (0.02 if precision == 2 else 0.5)
+    assert mism / tot < (0.02 if precision == 2 else MAX_4DP_MISMATCH)
     sc.engine.close()
 
 
@@ -245,8 +248,45 @@ def test_call_variants_loop_matches_oracle(golden):
     final, none, true_path = call_variants(net, oracle.VARTYPE_CLASSES, loader, None, "t", True)
     f_ref, n_ref = oracle.call_variants(g["o1"], g["o2"], g["o3"], tags)
     assert set(final) == set(f_ref) and set(none) == set(n_ref) and set(true_path) == set(final)
+    nt_np = nt.numpy()
+    for d, d_ref in ((final, f_ref), (none, n_ref)):
+        for k, e in d_ref.items():
+            got = d[k]
+            assert got[0] == e[0] and int(got[2]) == int(e[2]) and type(got[2]) is type(e[2])
+            assert np.asarray(got[1]).shape == (1,) and abs(float(got[1][0]) - float(e[1][0])) <= TOL_POS
+            for j, tol in ((3, TOL_PROB + 1e-4), (4, TOL_PROB + 1e-4), (5, 5e-3), (6, 5e-3)):
+                assert len(got[j]) == 4 and all(type(v) is np.float32 for v in got[j])
+                assert max(abs(float(a) - float(b)) for a, b in zip(got[j], e[j])) <= tol
     for k in final:
-        assert final[k][0] == f_ref[k][0] and true_path[k].shape == (5, 32, 3)
+        np.testing.assert_array_equal(true_path[k], nt_np[tags.index(k), :, :, 0:3])
+
+
+def test_call_variants_writes_the_reference_png_handover(tmp_path, monkeypatch):
+    """Inside the reference's call_neusomatic the directory {out_dir}/matrices_{tag} exists and imageio is installed:
+    true_path then holds PNG file names (call.py:89-95) that the unmodified pred_vcf_records_path can imread."""
+    import sys
+    import types
+    from PIL import Image
+    from neusomatic_b200.network import NeuSomaticNet
+    from neusomatic_b200.call import call_variants, load_checkpoint
+    fake = types.ModuleType("imageio")
+    fake.imwrite = lambda fn, arr: Image.fromarray(np.asarray(arr, np.uint8)).save(fn)
+    fake.imread = lambda fn: np.array(Image.open(fn))
+    monkeypatch.setitem(sys.modules, "imageio", fake)
+    g, ck = load_golden("std_v014")
+    sd, meta = load_checkpoint(ck)
+    x = torch.from_numpy(_assemble(g, ck))
+    nt = torch.from_numpy(oracle.non_transformed(g["matrices"], g["center"]))
+    tags = [str(t) for t in g["tags"]]
+    net = NeuSomaticNet(26).cuda()
+    net.load_state_dict(sd, strict=False)
+    (tmp_path / "matrices_tg").mkdir()
+    loader = [((x, None, None, None, nt), (tags, None))]
+    final, none, true_path = call_variants(net, oracle.VARTYPE_CLASSES, loader, str(tmp_path), "tg", True)
+    assert len(final) > 0 and set(true_path) == set(final)
+    for k, fn in true_path.items():
+        assert fn == "{}/matrices_tg/{}.png".format(tmp_path, k)
+        np.testing.assert_array_equal(fake.imread(fn), nt.numpy()[tags.index(k), :, :, 0:3])
 
 
 def test_call_tsv_end_to_end(tmp_path, golden):

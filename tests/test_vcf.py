@@ -1,0 +1,119 @@
+"""Dictionaries -> VCF stage (neusomatic_b200/vcf.py) against the outputs of the UNMODIFIED reference call.py
+(tests/golden/vcf_*.npz, written by tests/golden/make_golden_vcf.py): record builders, none.vcf filter, sorting,
+de-duplication, QUAL/SCORE formatting -- and the reference's whole call_neusomatic output on synthetic candidates,
+reproduced from the oracle's forward pass."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from neusomatic_b200 import vcf
+from neusomatic_b200.fasta import FastaFile, MemoryFasta
+from oracle import nsnet_oracle as oracle, torch_port
+
+CASES = ["std_v014", "std_wex", "ens_v014"]
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLDEN, "vcf_%s.npz" % name), allow_pickle=False))
+    g["fasta"] = json.loads(str(g["fasta"]))
+    return g
+
+
+def dict_from(g, prefix):
+    """Rebuilds a call_variants dictionary with the reference's element types (np.float32 scalars, [1]-shaped position)."""
+    d = {}
+    for i, path in enumerate(g[prefix + "_paths"]):
+        d[str(path)] = [str(g[prefix + "_type"][i]), np.array([g[prefix + "_pos"][i]], np.float32), np.int64(g[prefix + "_len"][i]),
+                        list(g[prefix + "_p1"][i]), list(g[prefix + "_p3"][i]), list(g[prefix + "_o1"][i]), list(g[prefix + "_o3"][i])]
+    return d
+
+
+def images(g):
+    nt = oracle.non_transformed(g["matrices"], g["center"])
+    return {str(t): nt[i] for i, t in enumerate(g["tags"])}
+
+
+def run_stage(g, final_preds, none_preds):
+    chroms = [str(c) for c in g["chroms"]]
+    order = {c: i for i, c in enumerate(chroms)}
+    fa = MemoryFasta(g["fasta"])
+    img = images(g)
+    recs = dict(vcf.pred_vcf_records(fa, final_preds, img, chroms, oracle.VARTYPE_CLASSES, 1))
+    pred = "".join(vcf.vcf_lines(vcf.get_vcf_records(recs), order, 0.7, 0.4))
+    none = "".join(vcf.vcf_lines(vcf.get_vcf_records(dict(vcf.pred_vcf_records_none(none_preds, chroms))), order, 0.7, 0.4))
+    return pred, none
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forced_dictionaries_give_the_reference_lines(name):
+    g = load(name)
+    forced = dict_from(g, "forced")
+    pred, none = run_stage(g, forced, forced)
+    assert pred == str(g["forced_vcf"])
+    assert none == str(g["forced_none_vcf"])
+    assert pred.count("\n") > 50          # the builders did produce records (SNP, INS and DEL rows)
+    kinds = {(len(l.split("\t")[3]) > 1, len(l.split("\t")[4]) > 1) for l in pred.splitlines()}
+    assert kinds >= {(False, False), (True, False), (False, True)}      # (True, True): multi-base SNP records
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reference_dictionaries_give_the_reference_vcf(name):
+    g = load(name)
+    pred, none = run_stage(g, dict_from(g, "final"), dict_from(g, "none"))
+    assert pred == str(g["pred_vcf"])
+    assert none == str(g["none_vcf"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_forward_reproduces_the_reference_call(name):
+    """oracle forward -> oracle call_variants -> this VCF stage == pred.vcf / none.vcf of the reference's call_neusomatic."""
+    g = load(name)
+    ck = torch.load(os.path.join(GOLDEN, name + ".pth"), map_location="cpu", weights_only=True)
+    x = oracle.assemble_channels(g["matrices"], g["center"], g["tumor_cov"], g["normal_cov"], g.get("anns"), int(ck["coverage_thr"]))
+    o1, o2, o3 = torch_port.forward(torch_port.prepare(ck["state_dict"]), torch.from_numpy(x))
+    final_preds, none_preds = oracle.call_variants(np.asarray(o1), np.asarray(o2), np.asarray(o3), [str(t) for t in g["tags"]])
+    ref_final, ref_none = dict_from(g, "final"), dict_from(g, "none")
+    assert set(final_preds) == set(ref_final) and set(none_preds) == set(ref_none)
+    pred, none = run_stage(g, final_preds, none_preds)
+    assert pred == str(g["pred_vcf"])
+    assert none == str(g["none_vcf"])
+
+
+def test_write_vcf_and_prob2phred(tmp_path):
+    recs = [["chr2", 5, "A", "T", np.float32(0.9997) * np.float32(0.9998)], ["chr1", 9, "G", "GA", np.float32(1.0)],
+            ["chr1", 9, "G", "GA", np.float32(1.0)], ["chr1", 3, "C", "C", np.float32(0.9)], ["chr1", 2, "T", "A", np.float32(0.45)],
+            ["chr1", 1, "T", "G", np.float32(0.0)], []]
+    out = tmp_path / "o.vcf"
+    vcf.write_vcf(recs, str(out), {"chr1": 0, "chr2": 1}, 0.7, 0.4)
+    lines = out.read_text().splitlines()
+    assert lines == ["chr1\t1\t.\tT\tG\t0.0000\tREJECT\tSCORE=0.0000\tGT\t0/1",
+                     "chr1\t2\t.\tT\tA\t2.5964\tLowQual\tSCORE=0.4500\tGT\t0/1",
+                     "chr1\t9\t.\tG\tGA\t100.0000\tPASS\tSCORE=1.0000\tGT\t0/1",
+                     "chr2\t5\t.\tA\tT\t33.0111\tPASS\tSCORE=0.9995\tGT\t0/1"]     # 33.0111: test/NeuSomatic_standalone.vcf:17
+    with pytest.raises(AssertionError):
+        vcf.prob2phred(1.5)
+    assert vcf.get_type("AC", "A") == "DEL" and vcf.get_type("A", "ACT,G") == "INS" and vcf.get_type("A", "G") == "SNP"
+
+
+def test_fasta_reader(tmp_path):
+    seqs = {"chr1": "ACGTACGTACGTAAACCCGGGTTT" * 7, "chrM": "GATTACA"}
+    p = tmp_path / "r.fa"
+    with open(p, "w") as f:
+        for k, s in seqs.items():
+            f.write(">%s some description\n" % k)
+            for i in range(0, len(s), 50):
+                f.write(s[i:i + 50] + "\n")
+    with FastaFile(str(p)) as fa:
+        assert fa.references == ("chr1", "chrM") and fa.lengths == (168, 7)
+        for a, b in ((0, 1), (0, 50), (49, 51), (3, 160), (100, 168), (160, 400), (5, 5)):
+            assert fa.fetch("chr1", a, b) == seqs["chr1"][a:b]
+        assert fa.fetch("chrM", 2, 6) == "TTAC"
+    # a .fai written by samtools has the same five columns
+    with open(str(p) + ".fai", "w") as f:
+        f.write("chr1\t168\t23\t50\t51\nchrM\t7\t%d\t7\t8\n" % (23 + 168 + 4 + 23))
+    with FastaFile(str(p)) as fa:
+        assert fa.fetch("chr1", 49, 120) == seqs["chr1"][49:120] and fa.fetch("chrM", 0, 7) == "GATTACA"
