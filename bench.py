@@ -4,25 +4,33 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2]): synthetic standalone call, C=26 pileup matrices of shape
-26x5x32 built from seeded random uint8[5,32,23] candidates (neusomatic_b200.synth S1) with the
-bundled-layout v0.1.0 standalone checkpoint (tests/golden/std_v010.pth).  One STEP = one pass of
-the hot path (NeuSomaticNet.forward + fused softmax/argmax) over one batch of --batch candidates
-per GPU (default 65536: 1.09 GB of fp32 input, larger than the 126 MB L2); the default
-16 steps score 1M candidates per GPU.
+Workload (BASELINE.json configs[2]): synthetic standalone call, C=26 pileup matrices of shape 26x5x32 built from seeded
+random uint8[5,32,23] candidates (neusomatic_b200.synth S1) with the bundled-layout v0.1.0 standalone checkpoint
+(tests/golden/std_v010.pth).  One STEP = one pass of the hot path (NeuSomaticNet.forward + fused softmax/argmax) over one
+batch of --batch candidates per GPU (default 65536: 1.09 GB of fp32 input, larger than the 126 MB L2); the default 16 steps
+score 1M candidates per GPU.
+
+Timing: a REGION = exactly K steps between two CUDA events on the launching stream, a barrier + synchronize on both
+sides.  A region of the default size lasts ~0.2 s, too short to tell a hiccup of one rank from the steady state, so the
+region is repeated until >= 2 s have been timed (the same number of repeats on every rank); the line reports the MEDIAN
+region (`ms_per_step` = its max over ranks / K), every region (`region_ms`) and the per-rank times of the median region
+(`ms_per_rank`).
 
 Printed JSON (one line, rank 0):
-  value   candidates/s, whole job, inputs resident in HBM (nsc_forward_f32 on device tensors)
-  e2e     candidates/s through the C-ABI host call nsc_score_host_u8 (call.py:68-83 batch step): pinned
-          host uint8 pileup matrices + tag fields in (what the TSV decoder yields, dataloader.py:38-58),
-          host results out, H2D/D2H inside the timed region, channel assembly on the device;
-          e2e_f32 is the same through nsc_score_host_f32 (assembled fp32 [B,C,5,32] matrices in,
-          PCIe-bound at 16.6 KB per candidate)
-  roofline  tensor roofline of the dominant kernel family, timed live with CUDA events
-  cpu_baseline  oracle/torch_port.py (the reference's forward restated on the PyTorch CPU
-          operators the reference itself runs) on a bounded sample, rank 0 / N=1 only
-`--impl reference` times that CPU port alone on the host cores (tier rule: the reference is
-Python over PyTorch CPU kernels; nothing of ours is on that path).
+  value     candidates/s, whole job, inputs resident in HBM (nsc_forward_f32 on device tensors)
+  e2e       candidates/s through the C-ABI host call nsc_score_host_u8 (call.py:68-83 batch step): pinned host uint8 pileup
+            matrices + tag fields in (what the TSV decoder yields, dataloader.py:38-58), host results out, H2D/D2H inside
+            the timed region, channel assembly on the device; e2e_f32: the same through nsc_score_host_f32
+  roofline  tensor roofline of the dominant kernel family (the eight 64->64 convolutions), timed live with CUDA events,
+            against BOTH measured bf16 peaks (sustained = `frac`, burst = `frac_burst`)
+  cpu_baseline  oracle/torch_port.py (the reference's forward restated on the PyTorch CPU operators the reference itself
+            runs) on a bounded sample, rank 0 / N=1 only
+  extra     records measured in the same run with the same build: `ensemble` (BASELINE configs[3], C=119: value + e2e),
+            `train` (configs[4]: one train.py step per GPU + NCCL all-reduce), `gpu_incumbent` (the stock nn.Module in
+            eager PyTorch on the same GPU: fp32 and TF32-allowed, inference and fwd+bwd+SGD -- informational, N=1 only),
+            `e2e_tsv` (a reference-format candidate TSV -> dictionaries through the decode/score/file pipeline, N=1 only)
+`--impl reference` times the CPU port alone on the host cores (tier rule: the reference is Python over PyTorch CPU
+kernels and has no setup.py to install; nothing of ours is on that path).
 """
 from __future__ import annotations
 
@@ -44,11 +52,13 @@ FLOPS_PER_CAND = {26: 2 * 62_384_240, 119: 2 * 65_241_200}      # SURVEY.md Appe
 # dense MACs of the dominant kernel family (the eight 64->64 convolutions), per candidate
 CONV_STACK_MACS = 5_898_240 * 2 + 16_384_000 * 2 + 2_949_120 + 8_192_000 + 1_474_560 + 4_096_000
 # MACs the tensor path actually issues for that family per candidate: kernel rows in the H padding are skipped
-# (13/15, 19/25, 11/15, 7/15, 13/25 of the taps), times 3 products in split mode
+# (13/15, 19/25, 11/15, 7/15, 13/25 of the taps)
 CONV_STACK_EXEC_MACS = 2 * (5_898_240 * 13 // 15 + 16_384_000 * 19 // 25) + 2_949_120 * 11 // 15 + 8_192_000 * 19 // 25 + \
     1_474_560 * 7 // 15 + 4_096_000 * 13 // 25
 MMA_SLOTS = {0: 3, 1: 1, 3: 2}    # fp16-equivalent tcgen05 issue slots per MAC by NSC_PREC_* mode
 CKPT = os.path.join(ROOT, "tests", "golden", "std_v010.pth")
+CKPT_ENS = os.path.join(ROOT, "tests", "golden", "ens_v010.pth")
+MIN_TIMED_MS = 2000.0             # repeat the K-step region until this much has been timed
 
 
 def peaks():
@@ -91,12 +101,13 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for nm, v in zip(names, r[5:9]):
@@ -105,16 +116,19 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_port_rate(C, seconds=12.0, batch=1000, threads=None):
     """Times oracle/torch_port.forward (CPU fp32, all host threads) on a bounded sample."""
     from oracle import nsnet_oracle as oracle, torch_port
     from neusomatic_b200 import synth
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    ck = torch.load(CKPT, map_location="cpu", weights_only=True)
+    ck = torch.load(CKPT if C == 26 else CKPT_ENS, map_location="cpu", weights_only=True)
     p = torch_port.prepare(ck["state_dict"])
     cand = synth.uniform_pileups(batch, seed=1234, ensemble=(C == 119))
     x = torch.from_numpy(oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov,
@@ -127,28 +141,58 @@ def cpu_port_rate(C, seconds=12.0, batch=1000, threads=None):
         el = time.perf_counter() - t0
         if el >= seconds:
             break
-    return done / el, threads, "%d candidates in batches of %d over %.1f s" % (done, batch, el)
+    return done / el, threads, "%d candidates in batches of %d over %.1f s" % (done, batch, el), el
+
+
+def cpu_tsv_rate(path, C, seconds=8.0, batch=1000):
+    """The reference's file -> dictionaries chain restated on the CPU (oracle: TSV line decode, channel assembly, forward,
+    call_variants loop) over the first candidates of `path` for a bounded time: the CPU number beside `e2e_tsv`."""
+    from oracle import nsnet_oracle as oracle, torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    ck = torch.load(CKPT if C == 26 else CKPT_ENS, map_location="cpu", weights_only=True)
+    p = torch_port.prepare(ck["state_dict"])
+    done, t0 = 0, time.perf_counter()
+    with open(path) as f:
+        while time.perf_counter() - t0 < seconds:
+            lines = [f.readline() for _ in range(batch)]
+            lines = [l for l in lines if l]
+            if not lines:
+                break
+            dec = [oracle.decode_tsv_line(l) for l in lines]
+            tags = [d[0] for d in dec]
+            mats = np.stack([d[1] for d in dec])
+            tagf = [oracle.parse_tag(t) for t in tags]
+            anns = np.array([d[2] for d in dec], np.float32) if C == 119 else None
+            x = oracle.assemble_channels(mats, np.array([t[1] for t in tagf]), np.array([t[3] for t in tagf]),
+                                         np.array([t[4] for t in tagf]), anns, int(ck["coverage_thr"]))
+            o1, o2, o3 = torch_port.forward(p, torch.from_numpy(x))
+            oracle.call_variants(np.asarray(o1), np.asarray(o2), np.asarray(o3), tags)
+            done += len(lines)
+    el = time.perf_counter() - t0
+    return done / el, "%d candidates in batches of %d over %.1f s" % (done, batch, el)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     C = 26
-    rates = []
+    rates, secs = [], []
     for _ in range(args.warmup):
         cpu_port_rate(C, seconds=1.0, batch=args.ref_batch)
     t_budget = max(3.0, min(20.0, 120.0 / max(args.steps, 1)))
     sample = ""
     threads = os.cpu_count() or 1
     for _ in range(args.steps):
-        r, threads, sample = cpu_port_rate(C, seconds=t_budget, batch=args.ref_batch)
+        r, threads, sample, el = cpu_port_rate(C, seconds=t_budget, batch=args.ref_batch)
         rates.append(r)
+        secs.append(el)
     v = float(np.mean(rates))
     print(json.dumps({
         "impl": "reference", "metric": "NeuSomaticNet candidates/sec", "value": v, "unit": "candidates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_budget,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic standalone call, C=26 (26x5x32), v0.1.0 standalone checkpoint; CPU sample",
+        "config": {"workload": "synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, v0.1.0 standalone "
+                               "checkpoint, S1 uniform pileups; each step = a bounded CPU sample of that workload",
                    "batch": args.ref_batch},
         "cpu_baseline": {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port",
                          "sample": "oracle/torch_port.py (PyTorch CPU operators, fp32): " + sample},
@@ -156,48 +200,308 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
-def run_train(args, rank, local_rank, world, dev):
-    """BASELINE.json configs[4] (not the headline metric): one train.py optimisation step per bench step on a synthetic
-    batch per GPU; gradients summed over ranks with one NCCL all-reduce of the flat 873 385-float vector."""
-    import torch.distributed as dist
-    from neusomatic_b200 import synth
-    from neusomatic_b200.train import Trainer
-    from oracle import nsnet_oracle as oracle     # input assembly of the synthetic batch only (outside the timed region)
-    B = min(args.batch, 1024)
+# ---------------------------------------------------------------------------------------------------------------------
+# timing helpers
+# ---------------------------------------------------------------------------------------------------------------------
+class Ranks:
+    def __init__(self, rank, world, dev):
+        self.rank, self.world, self.dev = rank, world, dev
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def gather(self, values):
+        """[len(values)] per rank -> [world, len(values)] on every rank."""
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev).reshape(1, -1)
+        if self.world == 1:
+            return t.cpu().numpy()
+        import torch.distributed as dist
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return torch.cat(out, 0).cpu().numpy()
+
+
+def timed_regions(rk, step_fn, steps, warmup, device_events=True, min_ms=MIN_TIMED_MS, max_repeats=40):
+    """Runs `warmup` untimed steps, then K-step regions (barrier + synchronize on both sides, CUDA events on the current
+    stream or the host clock for calls that synchronise themselves) until >= min_ms have been timed.  Returns
+    (median region: max over ranks in ms, [region max over ranks], per-rank ms of the median region)."""
+    for _ in range(warmup):
+        step_fn()
+    per_rank_regions = []
+    repeats = None
+    while repeats is None or len(per_rank_regions) < repeats:
+        rk.barrier()
+        if device_events:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step_fn()
+            e1.record()
+            rk.barrier()
+            ms = e0.elapsed_time(e1)
+        else:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step_fn()
+            torch.cuda.synchronize()
+            ms = 1000.0 * (time.perf_counter() - t0)
+            rk.barrier()
+        per_rank_regions.append(rk.gather([ms])[:, 0])          # [world]
+        if repeats is None:
+            first = float(per_rank_regions[0].max())              # the same number on every rank
+            repeats = int(min(max_repeats, max(1, np.ceil(min_ms / max(first, 1e-3)))))
+    arr = np.stack(per_rank_regions)                              # [repeats, world]
+    region_max = arr.max(1)
+    med = int(np.argsort(region_max)[len(region_max) // 2])
+    return float(region_max[med]), [float(v) for v in region_max], [float(v) for v in arr[med]]
+
+
+def make_inputs(eng, meta, B, ensemble, rank, dev):
+    """S1 candidates, seed = 1234 + rank; a 4096-candidate pool tiled to B.  Host copies are pinned."""
+    from neusomatic_b200 import anns_to_255, synth
+    pool = synth.uniform_pileups(4096, seed=1234 + rank, ensemble=ensemble)
+    reps = (B + 4095) // 4096
+    mat_h = torch.from_numpy(np.tile(pool.matrices, (reps, 1, 1, 1))[:B]).pin_memory()
+    meta_h = torch.from_numpy(np.tile(pool.meta, (reps, 1))[:B].copy()).pin_memory()
+    ann_h = torch.from_numpy(np.tile(anns_to_255(pool.anns), (reps, 1))[:B].copy()).pin_memory() if ensemble else None
+    mat_d, meta_d = mat_h.to(dev), meta_h.to(dev)
+    ann_d = ann_h.to(dev) if ensemble else None
+    x_d = eng.assemble(mat_d, meta_d, ann_d, float(meta["coverage_thr"]))        # fp32 [B,C,5,32] in HBM
+    torch.cuda.synchronize()
+    return mat_h, meta_h, ann_h, x_d
+
+
+def measure_scoring(args, rk, local_rank, ensemble, B, steps, with_f32_host=True, with_profile=True, with_clocks=True):
+    """value (resident), e2e (host u8), e2e_f32, per-kernel profile for one model on this rank's GPU."""
+    from neusomatic_b200 import Engine
+    from neusomatic_b200.call import load_checkpoint
+    C = 119 if ensemble else 26
+    sd, meta = load_checkpoint(CKPT_ENS if ensemble else CKPT)
+    eng = Engine(sd, C, device=local_rank, precision=args.precision)
+    mat_h, meta_h, ann_h, x_d = make_inputs(eng, meta, B, ensemble, rk.rank, rk.dev)
+    thr = float(meta["coverage_thr"])
+    out = {"C": C, "precision": eng.precision, "kernel": eng.kernel_name}
+
+    # ---- value: device-resident inputs; the library's per-kernel event brackets stay on during the timed regions (two
+    # event records per launch on the launching stream), so the roofline's kernel time is measured live, in the timed region
+    for _ in range(args.warmup):
+        eng.forward_f32(x_d, extras=True)
+    sampler = ClockSampler(local_rank) if (with_clocks and rk.rank == 0) else None
+    if with_profile:
+        rk.barrier()
+        eng.get_profile()
+        eng.set_profile(True)
+    l0 = eng.launch_count
+    if sampler:
+        sampler.start()
+    ms, regions, per_rank = timed_regions(rk, lambda: eng.forward_f32(x_d, extras=True), steps, 0)
+    out["clocks"] = sampler.stop() if sampler else None
+    out.update(ms=ms, region_ms=regions, ms_per_rank=per_rank, value=rk.world * B * steps / (ms / 1000.0))
+    out["launches"] = (eng.launch_count - l0) // len(regions)          # launches of ONE K-step region
+    if with_profile:
+        prof = eng.get_profile()
+        eng.set_profile(False)
+        out["prof"] = {k: (v[0] / len(regions), v[1] // len(regions)) for k, v in prof.items()}     # per region
+
+    # ---- e2e: host buffers through the C ABI (the call synchronises: results are in host memory when it returns) -----
+    if not args.no_e2e:
+        host_out = eng._host_out(B, True, pin=True)
+        k = max(2, min(steps, 6))
+        ms_u8, _, _ = timed_regions(rk, lambda: eng.score_host_u8(mat_h, meta_h, ann_h, thr, out=host_out), k, 1,
+                                    device_events=False, min_ms=1000.0)
+        d2h = B * 19 * 4
+        out["e2e"] = {"value": rk.world * B * k / (ms_u8 / 1000.0), "unit": "candidates/s",
+                      "h2d_bytes_per_step": B * (3680 + 12 + (372 if ensemble else 0)), "d2h_bytes_per_step": d2h,
+                      "api": "nsc_score_host_u8 (pinned uint8 [B,5,32,23] + int32 [B,3] in, host results out)"}
+        if with_f32_host:
+            x_h = torch.empty((B, C, 5, 32), dtype=torch.float32).pin_memory()
+            x_h.copy_(x_d)
+            ms_f32, _, _ = timed_regions(rk, lambda: eng.score_host_f32(x_h, out=host_out), k, 1, device_events=False,
+                                         min_ms=1000.0)
+            out["e2e_f32"] = {"value": rk.world * B * k / (ms_f32 / 1000.0), "unit": "candidates/s",
+                              "h2d_bytes_per_step": B * C * 160 * 4, "d2h_bytes_per_step": d2h,
+                              "api": "nsc_score_host_f32 (pinned fp32 [B,C,5,32] in, host results out)"}
+            del x_h
+    eng.close()
+    del x_d
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: train.py step
+# ---------------------------------------------------------------------------------------------------------------------
+def train_inputs(B, rank, dev, local_rank):
+    """Synthetic labelled batch: S2 pileups, channel assembly by the library on the device."""
+    from neusomatic_b200 import Engine, synth
     cand = synth.structured_pileups(B, seed=100 + rank)
-    x = torch.from_numpy(oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)).to(dev)
+    eng = Engine(synth.random_state_dict(26, seed=1), 26, device=local_rank)
+    x = eng.assemble(torch.from_numpy(cand.matrices).to(dev), torch.from_numpy(cand.meta).to(dev), None, 100.0).clone()
+    eng.close()
     vt = torch.tensor([synth.VARTYPE_CLASSES.index(t.split(".")[4]) for t in cand.tags], dtype=torch.int32, device=dev)
     ln = torch.tensor([min(int(t.split(".")[6]), 3) for t in cand.tags], dtype=torch.int32, device=dev)
     ce = torch.from_numpy(cand.center).float().to(dev)
     w1 = torch.tensor([0.2, 0.21, 0.13, 0.16], device=dev)
     w3 = torch.tensor([0.12, 0.2, 0.23, 0.24], device=dev)
+    return x, vt, ce, ln, w1, w3
+
+
+def measure_train(args, rk, local_rank, B, steps):
+    import torch.distributed as dist
+    from neusomatic_b200 import synth
+    from neusomatic_b200.train import Trainer
+    x, vt, ce, ln, w1, w3 = train_inputs(B, rk.rank, rk.dev, local_rank)
     tr = Trainer(synth.random_state_dict(26, seed=11), 26, device=local_rank, max_batch=B)
-    for _ in range(args.warmup):
-        tr.step(x, vt, ce, ln, w1, w3)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        losses = tr.step(x, vt, ce, ln, w1, w3)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    if rank == 0:
-        print(json.dumps({"metric": "NeuSomaticNet train samples/sec (fwd+bwd+SGD)", "value": world * B * args.steps / (ms / 1000.0),
-                          "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "split fp16 x3 on tcgen05 with fp32 accumulate for the 64->64 convolutions (forward, data and weight "
-                                   "gradient); f32 elsewhere (NSC_TRAIN_FP32=1: all f32)", "data": "synthetic",
-                          "config": {"workload": "train.py step (BASELINE.json configs[4]): C=26, SGD lr 0.01 momentum 0.9, "
-                                                 "BatchNorm batch statistics per GPU, one NCCL all-reduce of 873385 floats per step",
-                                     "batch_per_gpu": B}, "loss": float(losses[0])}), flush=True)
+    ms, regions, per_rank = timed_regions(rk, lambda: tr.step(x, vt, ce, ln, w1, w3), steps, max(args.warmup, 3), min_ms=1000.0)
+    out = {"metric": "NeuSomaticNet train samples/sec (fwd+bwd+SGD)", "value": rk.world * B * steps / (ms / 1000.0), "unit": "samples/s",
+           "ms_per_step": ms / steps, "region_ms": regions, "ms_per_rank": per_rank, "batch_per_gpu": B, "loss": float(tr.losses[0]),
+           "allreduce_us": None,
+           "dtype": "split fp16 x3 on tcgen05 with fp32 accumulate for the convolutions (forward, data and weight gradient); f32 elsewhere",
+           "workload": "train.py step (BASELINE.json configs[4]): C=26, SGD lr 0.01 momentum 0.9, BatchNorm batch statistics per GPU, "
+                       "one NCCL all-reduce of %d floats per step" % tr.n}
+    if rk.world > 1:
+        ms_ar, _, _ = timed_regions(rk, lambda: dist.all_reduce(tr.grads), 20, 3, min_ms=200.0)
+        out["allreduce_us"] = 1000.0 * ms_ar / 20
     tr.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU incumbent: the reference architecture as a stock nn.Module in eager PyTorch on the same GPU (network.py:17-78
+# layer list; cuDNN / cuBLAS kernels).  Informational: what `net.cuda()` of call.py:411-413 / train.py delivers.
+# ---------------------------------------------------------------------------------------------------------------------
+def stock_module(C):
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    class Block(nn.Module):
+        def __init__(self, k1, k2, d1, d2, st):
+            super().__init__()
+            self.conv_r1 = nn.Conv2d(64, 64, k1, dilation=d1, padding=(d1 * (k1 - 1)) // 2)
+            self.bn_r1 = nn.BatchNorm2d(64)
+            self.conv_r2 = nn.Conv2d(64, 64, k2, dilation=d2, padding=(d2 * (k2 - 1)) // 2)
+            self.bn_r2 = nn.BatchNorm2d(64)
+            self.pool_r2 = nn.MaxPool2d((1, 3), padding=(0, 1), stride=(1, st))
+
+        def forward(self, x):
+            y = F.relu(self.bn_r1(self.conv_r1(x)))
+            return self.pool_r2(x + self.bn_r2(self.conv_r2(y)))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(C, 64, (1, 3), padding=(0, 1))
+            self.bn1 = nn.BatchNorm2d(64)
+            self.pool1 = nn.MaxPool2d((1, 3), padding=(0, 1), stride=(1, 1))
+            self.res_layers = nn.Sequential(Block(3, 5, 1, 1, 1), Block(3, 5, 1, 1, 2), Block(3, 5, 2, 1, 2), Block(3, 5, 4, 2, 2))
+            self.fc1, self.fc2, self.fc3, self.fc4 = nn.Linear(1280, 240), nn.Linear(240, 4), nn.Linear(240, 1), nn.Linear(240, 4)
+
+        def forward(self, x):
+            x = self.res_layers(self.pool1(F.relu(self.bn1(self.conv1(x)))))
+            x = F.relu(self.fc1(x.reshape(x.shape[0], -1)))
+            return self.fc2(x), self.fc3(x), self.fc4(x)
+    return Net()
+
+
+def measure_incumbent(args, rk, local_rank):
+    import torch.nn.functional as F
+    from neusomatic_b200 import Engine
+    from neusomatic_b200.call import load_checkpoint
+    dev = rk.dev
+    sd, meta = load_checkpoint(CKPT)
+    net = stock_module(26)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(dev).eval()
+    B = 8192
+    eng = Engine(sd, 26, device=local_rank, precision=args.precision)
+    _, _, _, x_d = make_inputs(eng, meta, B, False, 0, dev)
+    ours = [t.float() for t in eng.forward_f32(x_d, extras=True)]
+    eng.close()
+    out = {"batch": B, "what": "stock nn.Module of the same architecture, eager PyTorch %s on the same GPU (cuDNN / cuBLAS), "
+                               "inputs resident" % torch.__version__}
+    for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.no_grad():
+            ms, _, _ = timed_regions(rk, lambda: net(x_d), 8, 3, min_ms=500.0)
+            o1, o2, o3 = net(x_d)
+        p1, p3 = torch.softmax(o1, 1), torch.softmax(o3, 1)
+        out["inference_" + name] = {
+            "value": B * 8 / (ms / 1000.0), "unit": "candidates/s",
+            "vs_this_library": {"max_dprob": float(max((p1 - ours[3]).abs().max(), (p3 - ours[4]).abs().max())),
+                                "max_dpos": float((o2 - ours[1]).abs().max()),
+                                "argmax_flips": int((o1.argmax(1) != ours[5]).sum() + (o3.argmax(1) != ours[6]).sum())}}
+    del x_d
+    # training step: loss.backward() + optim.SGD, batch 1024 (train.py:416-441)
+    x, vt, ce, ln, w1, w3 = train_inputs(1024, 0, dev, local_rank)
+    vt, ln = vt.long(), ln.long()
+    for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        tnet = stock_module(26).to(dev).train()
+        opt = torch.optim.SGD(tnet.parameters(), lr=0.01, momentum=0.9)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            o1, o2, o3 = tnet(x)
+            loss = F.cross_entropy(o1, vt, weight=w1) + F.smooth_l1_loss(o2[:, 0], ce) + F.cross_entropy(o3, ln, weight=w3)
+            loss.backward()
+            opt.step()
+        ms, _, _ = timed_regions(rk, step, 10, 3, min_ms=500.0)
+        out["train_" + name] = {"value": 1024 * 10 / (ms / 1000.0), "unit": "samples/s", "ms_per_step": ms / 10, "batch": 1024}
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# e2e_tsv: reference-format candidate TSV -> dictionaries
+# ---------------------------------------------------------------------------------------------------------------------
+def measure_tsv(args, rk, local_rank, n=131072):
+    import base64
+    import zlib
+    from neusomatic_b200 import synth
+    from neusomatic_b200.call import CandidateScorer, PredTable
+    from neusomatic_b200.vcf import pred_vcf_records_none
+    pool = synth.structured_pileups(4096, seed=4321)
+    td = tempfile.mkdtemp(prefix="nsc_bench_")
+    path = os.path.join(td, "candidates_0.tsv")
+    blobs = [base64.b64encode(zlib.compress(np.ascontiguousarray(pool.matrices[i]))).decode("ascii") for i in range(4096)]
+    with open(path, "w") as f:                      # generate_dataset.py:1569-1581 line format; tags made unique by position
+        for i in range(n):
+            tf = pool.tags[i % 4096].split(".")
+            tf[1] = str(1000 + i)
+            f.write("%d\t1\t%s\t%s\n" % (i, ".".join(tf), blobs[i % 4096]))
+    size = os.path.getsize(path)
+    sc = CandidateScorer(CKPT, device=local_rank, precision=args.precision)
+    threads = os.cpu_count() or 1
+    sc.call_tsv(path, batch=32768, num_threads=threads)       # warm-up: page cache, workspace, pinned slots
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        final_preds, none_preds = sc.call_tsv(path, batch=32768, num_threads=threads)
+        n_none_records = len(dict(pred_vcf_records_none(none_preds, ["chr%d" % i for i in range(30)])))
+        times.append(time.perf_counter() - t0)
+    sc.engine.close()
+    el = float(np.median(times))
+    cpu_rate, cpu_sample = (None, None)
+    if not args.no_cpu_baseline:
+        cpu_rate, cpu_sample = cpu_tsv_rate(path, 26)
+    os.unlink(path)
+    os.rmdir(td)
+    return {"value": n / el, "unit": "candidates/s", "candidates": n, "tsv_bytes": size, "host_threads": threads,
+            "final_preds": len(final_preds), "none_preds": len(none_preds), "none_vcf_records": n_none_records,
+            "what": "CandidateScorer.call_tsv: C++ mmap/base64/inflate decoder -> nsc_score_host_u8 -> PredTable dictionaries + the none.vcf "
+                    "filter on arrays; decode, score and filing overlapped (call.py:504-534 + 336-354)",
+            "cpu_reference_chain": None if cpu_rate is None else {
+                "value": cpu_rate, "unit": "candidates/s", "kind": "port", "cores": threads,
+                "sample": "oracle: TSV line decode + channel assembly + torch_port forward + call_variants loop, " + cpu_sample}}
 
 
 def main():
@@ -211,8 +515,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--train", action="store_true", help="BASELINE configs[4]: train.py step (fwd+bwd+SGD), data-parallel with one NCCL all-reduce")
-    ap.add_argument("--ensemble", action="store_true", help="BASELINE configs[3]: C=119 ensemble model (not the default metric config)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra records (ensemble, train, gpu_incumbent, e2e_tsv)")
+    ap.add_argument("--train", action="store_true", help="BASELINE configs[4] as the line's own metric")
+    ap.add_argument("--ensemble", action="store_true", help="BASELINE configs[3] as the line's own metric (C=119)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -224,131 +529,80 @@ def main():
         return
 
     import torch.distributed as dist
-    from neusomatic_b200 import Engine, synth
-    from neusomatic_b200.call import load_checkpoint
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    rk = Ranks(rank, world, dev)
 
     if args.train:
-        run_train(args, rank, local_rank, world, dev)
+        t = measure_train(args, rk, local_rank, min(args.batch, 1024), args.steps)
+        if rank == 0:
+            print(json.dumps({"metric": t["metric"], "value": t["value"], "unit": t["unit"], "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": t["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": t["dtype"], "data": "synthetic",
+                              "config": {"workload": t["workload"], "batch_per_gpu": t["batch_per_gpu"]}, "loss": t["loss"],
+                              "allreduce_us": t["allreduce_us"], "region_ms": t["region_ms"], "ms_per_rank": t["ms_per_rank"]}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    C = 119 if args.ensemble else 26
-    sd, meta = load_checkpoint(os.path.join(ROOT, "tests", "golden", "ens_v010.pth") if args.ensemble else CKPT)
-    eng = Engine(sd, C, device=local_rank, precision=args.precision)
     B = args.batch
+    m = measure_scoring(args, rk, local_rank, args.ensemble, B, args.steps)
+    C = m["C"]
 
-    # synthetic S1 candidates, seed = 1234 + rank; a 4096-candidate pool tiled to B
-    from neusomatic_b200 import anns_to_255
-    pool = synth.uniform_pileups(4096, seed=1234 + rank, ensemble=args.ensemble)
-    reps = (B + 4095) // 4096
-    mat_h = torch.from_numpy(np.tile(pool.matrices, (reps, 1, 1, 1))[:B]).pin_memory()
-    meta_h = torch.from_numpy(np.tile(pool.meta, (reps, 1))[:B].copy()).pin_memory()
-    ann_h = torch.from_numpy(np.tile(anns_to_255(pool.anns), (reps, 1))[:B].copy()).pin_memory() if args.ensemble else None
-    mat_d, meta_d = mat_h.to(dev), meta_h.to(dev)
-    ann_d = ann_h.to(dev) if args.ensemble else None
-    x_d = eng.assemble(mat_d, meta_d, ann_d, float(meta["coverage_thr"]))        # fp32 [B,C,5,32] in HBM
-    torch.cuda.synchronize()
+    extra = {}
+    if not args.no_extra:
+        if not args.ensemble:
+            e = measure_scoring(args, rk, local_rank, True, min(B, 32768), max(4, args.steps // 2), with_f32_host=False,
+                                with_profile=False, with_clocks=False)
+            extra["ensemble"] = {"value": e["value"], "unit": "candidates/s", "ms_per_step": e["ms"] / max(4, args.steps // 2),
+                                 "batch_per_gpu": min(B, 32768), "e2e": e.get("e2e"), "ms_per_rank": e["ms_per_rank"],
+                                 "workload": "synthetic ensemble call (BASELINE.json configs[3]): C=119, v0.1.0 ensemble checkpoint"}
+        t = measure_train(args, rk, local_rank, 1024, 20)
+        extra["train"] = {k: t[k] for k in ("value", "unit", "ms_per_step", "batch_per_gpu", "allreduce_us", "ms_per_rank", "workload")}
+        if world == 1:
+            extra["gpu_incumbent"] = measure_incumbent(args, rk, local_rank)
+            extra["e2e_tsv"] = measure_tsv(args, rk, local_rank)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- value: device-resident inputs, kernel-only path ---------------------------------------
-    for _ in range(args.warmup):
-        eng.forward_f32(x_d, extras=True)
-    barrier()
-    eng.get_profile()
-    eng.set_profile(True)
-    launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        outs = eng.forward_f32(x_d, extras=True)
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    prof = eng.get_profile()
-    eng.set_profile(False)
-    launches = eng.launch_count - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max / 1000.0)
-
-    # ---- e2e: host buffers through the C ABI -------------------------------------------------------
-    e2e = e2e_u8 = None
-    if not args.no_e2e:
-        x_h = torch.empty((B, C, 5, 32), dtype=torch.float32).pin_memory()
-        x_h.copy_(x_d)
-        host_out = eng._host_out(B, True, pin=True)
-        k = max(2, min(args.steps, 6))
-        res = {}
-        for name in ("f32", "u8"):
-            fn = (lambda: eng.score_host_f32(x_h, out=host_out)) if name == "f32" else \
-                 (lambda: eng.score_host_u8(mat_h, meta_h, ann_h, float(meta["coverage_thr"]), out=host_out))
-            fn()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(k):
-                fn()     # synchronises: results are in host memory when it returns
-            torch.cuda.synchronize()
-            el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(el, op=dist.ReduceOp.MAX)
-            res[name] = world * B * k / float(el.item())
-        d2h = B * 19 * 4
-        e2e = {"value": res["u8"], "unit": "candidates/s", "h2d_bytes_per_step": B * (3680 + 12 + (372 if args.ensemble else 0)),
-               "d2h_bytes_per_step": d2h, "api": "nsc_score_host_u8 (pinned uint8 [B,5,32,23] + int32 [B,3] in, host results out)"}
-        e2e_u8 = {"value": res["f32"], "unit": "candidates/s", "h2d_bytes_per_step": B * C * 160 * 4,
-                  "d2h_bytes_per_step": d2h, "api": "nsc_score_host_f32 (pinned fp32 [B,C,5,32] in, host results out)"}
-
-    # ---- roofline of the dominant kernel family (the eight 64->64 convolutions) -------------------
+    # ---- roofline of the dominant kernel family (the eight 64->64 convolutions) -------------------------------
     pk = peaks()
+    roof = None
+    prof = m.get("prof") or {}
     conv_ms = sum(v[0] for k_, v in prof.items() if k_.startswith("res"))
     conv_launches = sum(v[1] for k_, v in prof.items() if k_.startswith("res"))
     total_ms = sum(v[0] for v in prof.values())
-    roof = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))["dram_bytes_per_launch"]     # ncu capture, 32768-candidate launches
+    traffic, traffic_src = None, None
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))["dram_bytes_per_launch"]     # one ncu --set full capture, 32768-candidate launches
+            traffic_src = "profiles/" + fn
+            break
     if conv_ms > 0:
         cands = B * args.steps
         achieved = cands * 2 * CONV_STACK_MACS / (conv_ms / 1000.0) / 1e12
+        executed = (cands * 2 * CONV_STACK_EXEC_MACS * MMA_SLOTS.get(m["precision"], 1) / (conv_ms / 1000.0) / 1e12
+                    if m["precision"] != 2 else None)
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
-                "kernel": eng.kernel_name, "kernel_launches": conv_launches,
+                "frac": achieved / pk["bf16_sustained"], "peak_burst": pk["bf16_burst"], "frac_burst": achieved / pk["bf16_burst"],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["src"] + " bf16 (sustained = frac, burst = frac_burst)",
+                "kernel": m["kernel"], "kernel_launches": conv_launches,
                 "kernel_ms_per_launch": conv_ms / max(conv_launches, 1),
                 "kernel_share_of_step": conv_ms / total_ms if total_ms else None,
                 "algorithmic_flops_per_candidate": 2 * CONV_STACK_MACS,
-                # tensor-pipe occupancy in fp16-instruction equivalents: 3 per MAC (split-f16), 2 per MAC (split8: one fp16
-                # + two fp8 products, an fp8 instruction covers twice the K of an fp16 one in the same issue slot)
-                "executed_tensor_tflops": cands * 2 * CONV_STACK_EXEC_MACS * MMA_SLOTS.get(eng.precision, 1) /
-                                          (conv_ms / 1000.0) / 1e12 if eng.precision != 2 else None,
-                "executed_frac_of_peak": (cands * 2 * CONV_STACK_EXEC_MACS * MMA_SLOTS.get(eng.precision, 1) /
-                                          (conv_ms / 1000.0) / 1e12 / pk["bf16_sustained"]) if eng.precision != 2 else None,
-                "whole_net_frac": (value / world) * FLOPS_PER_CAND[C] / 1e12 / pk["bf16_sustained"],
+                # informative: tensor-pipe issue slots in fp16-instruction equivalents (3 per MAC split-f16, 2 per MAC with
+                # the fp8 corrections) -- an occupancy figure, not a roofline
+                "executed_tensor_tflops_fp16_slots": executed,
+                "whole_net_frac": (m["value"] / world) * FLOPS_PER_CAND[C] / 1e12 / pk["bf16_sustained"],
+                "whole_net_frac_burst": (m["value"] / world) * FLOPS_PER_CAND[C] / 1e12 / pk["bf16_burst"],
                 "per_kernel_ms": {k_: round(v[0] / args.steps, 4) for k_, v in prof.items()}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r, threads, sample = cpu_port_rate(C, seconds=12.0, batch=args.ref_batch)
+        r, threads, sample, _ = cpu_port_rate(C, seconds=12.0, batch=args.ref_batch)
         cpu = {"value": r, "unit": "candidates/s", "cores": threads, "kind": "port",
                "sample": "oracle/torch_port.py (PyTorch CPU operators, fp32): " + sample}
 
@@ -356,23 +610,25 @@ def main():
         prec_names = {0: "split-f16 (fp16 hi+lo operands, 3 tcgen05 MMAs per MAC, fp32 accumulate)", 1: "f16", 2: "f32",
                       3: "f16 + fp8 corrections (fp16 main product, two e4m3 correction products scaled by 2^15, fp32 accumulate)"}
         print(json.dumps({
-            "metric": "NeuSomaticNet candidates/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "metric": "NeuSomaticNet candidates/sec", "value": m["value"], "unit": "candidates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": prec_names.get(eng.precision, str(eng.precision)), "data": "synthetic",
+            "dtype": prec_names.get(m["precision"], str(m["precision"])), "data": "synthetic",
             "config": {"workload": ("synthetic ensemble call (BASELINE.json configs[3]): C=119, 119x5x32 matrices, v0.1.0 ensemble "
                                     "checkpoint, S1 uniform pileups") if args.ensemble else
                                    ("synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, "
                                     "v0.1.0 standalone checkpoint, S1 uniform pileups"),
                        "batch_per_gpu": B, "candidates_per_step": world * B,
                        "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
-                       "sharding": "contiguous candidate ranges per rank, no collective on the data path"},
-            "e2e": e2e, "e2e_f32": e2e_u8, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "clocks": clocks,
+                       "sharding": "contiguous candidate ranges per rank, no collective on the data path",
+                       "timing": "median of %d regions of %d steps (>= %.0f ms timed), max over ranks per region" % (
+                           len(m["region_ms"]), args.steps, MIN_TIMED_MS)},
+            "region_ms": [round(v, 3) for v in m["region_ms"]], "ms_per_rank": [round(v, 3) for v in m["ms_per_rank"]],
+            "e2e": m.get("e2e"), "e2e_f32": m.get("e2e_f32"), "gpu_launches": m.get("launches"), "roofline": roof,
+            "cpu_baseline": cpu, "clocks": m["clocks"], "extra": extra,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":
