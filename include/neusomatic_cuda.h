@@ -184,6 +184,20 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
                                const int32_t* type_labels, const float* centers, const int32_t* len_labels,
                                const float* w_type_dev, const float* w_len_dev, int64_t B, float bn_momentum,
                                float* grads, float* losses_dev, void* stream);
+/* Data-parallel loss normalisation.  The reference trains under nn.DataParallel, which computes ONE loss over the gathered
+ * global batch (train.py:436-441): both weighted cross entropies divide by the class-weight sum of the global batch and
+ * SmoothL1 by its size.  norm_dev [3] fp32 (device) = (sum of w_type[label], sum of w_len[len_label], candidates) over ALL
+ * ranks makes nsc_train_forward_backward use those normalisers; the per-rank gradients then SUM (not average) to the
+ * gradient of the global loss.  NULL (default): normalise by this batch.  The pointer is read when the step runs. */
+int nsc_trainer_set_loss_norm(nsc_trainer* t, const float* norm_dev);
+/* The same step in two halves, for callers that compute the loss themselves (the reference's loop: outputs = net(x);
+ * loss = criterion(...); loss.backward() -- train.py:426-441): the forward leaves the logits in logits9 [B,9] = (type 4,
+ * position 1, length 4 per candidate) and the activations in the trainer; the backward takes d(loss)/d(logits9) and writes
+ * every parameter gradient.  One forward may be outstanding per trainer; x_dev must be the same tensor in both calls. */
+int nsc_train_forward(nsc_trainer* t, const float* params, float* running, const float* x_dev, int64_t B, float bn_momentum,
+                      float* logits9, void* stream);
+int nsc_train_backward(nsc_trainer* t, const float* params, const float* x_dev, const float* dlogits9, int64_t B,
+                       float* grads, void* stream);
 /* optim.SGD: buf = momentum * buf + grad_scale * grad ; p -= lr * buf   (grad_scale = 1 / world size after a
  * sum all-reduce; momentum buffers start at zero). */
 int nsc_sgd_momentum_update(float* params, float* momentum_buf, const float* grads, int64_t n, float lr,

@@ -46,6 +46,9 @@ SIGNATURES = {
     "nsc_trainer_num_params": (_i64, [_vp]),
     "nsc_trainer_param_slice": (_i32, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "nsc_train_forward_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp]),
+    "nsc_trainer_set_loss_norm": (_i32, [_vp, _vp]),
+    "nsc_train_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp]),
+    "nsc_train_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nsc_sgd_momentum_update": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp]),
     "nsc_trainer_debug_tensor": (_i32, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "nsc_trainer_destroy": (_i32, [_vp]),

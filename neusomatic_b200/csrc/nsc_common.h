@@ -195,6 +195,9 @@ int umma_train_bn_bwd_pack(nsc_model* m, int W, const float* u, const float* sta
                            double inv_m, cudaStream_t s);
 // where the producer of a tensor leaves max |x| (bit pattern of a float): xslot 0..7 = input of the 64 -> 64 layer, -1 = du
 unsigned int* umma_train_amax_slot(nsc_model* m, int xslot);
+// multiplier of a tensor-path layer's folded weights that undoes the accumulator's round-toward-zero shrink (nsc_umma.cu)
+constexpr double kRzKappa = 0.0;
+double rz_compensation(int n_steps, double valid_share);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);

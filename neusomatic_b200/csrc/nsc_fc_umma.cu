@@ -215,10 +215,11 @@ fc_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constan
 int fc_umma_upload_weights(nsc_model* m) {
   const std::vector<float>& w1 = m->params.at("fc1.weight");
   std::vector<uint8_t> pk(2 * 20 * (size_t)kFcWBytes, 0);
+  const double rz = rz_compensation(kFcIn / 16, 1.0);     // 80 main-product steps per output (nsc_umma.cu)
   for (int n = 0; n < kFcHidden; ++n)
     for (int c = 0; c < 64; ++c)
       for (int p = 0; p < 20; ++p) {
-        const float v = w1[(size_t)n * kFcIn + c * 20 + p];
+        const float v = (float)((double)w1[(size_t)n * kFcIn + c * 20 + p] * rz);
         const __half hi = __float2half_rn(v);
         const __half lo = __float2half_rn(v - __half2float(hi));
         const uint32_t off = ptx::swz_offset<128>((uint32_t)n, (uint32_t)(c / 8)) + (c % 8) * 2;

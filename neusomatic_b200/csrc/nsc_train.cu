@@ -58,6 +58,8 @@ struct nsc_trainer {
   // CrossEntropyLoss raises on those); read without a synchronisation at the next entry point
   int* flag_h = nullptr;
   int* flag_d = nullptr;
+  const float* loss_norm = nullptr;   // device [3]: (sum of type weights, sum of length weights, candidates) of the GLOBAL batch, or NULL
+  int64_t fwd_batch = -1;       // batch of the nsc_train_forward whose tensors are in the workspace (-1: none / consumed)
 };
 
 namespace nsc {
@@ -579,8 +581,12 @@ __global__ void loss_weights_kernel(const int32_t* __restrict__ y1, const int32_
 // losses (train.py:436-438) and d(loss)/d(logits).  logits [N][9] = (o1[4], o2[1], o3[4])
 __global__ void loss_kernel(const float* __restrict__ logits, const int32_t* __restrict__ y1, const float* __restrict__ center,
                             const int32_t* __restrict__ y3, const float* __restrict__ w1, const float* __restrict__ w3, int N,
-                            double* __restrict__ acc /*[8]: sum w1, sum w3, l1, l2, l3*/, float* __restrict__ dlogits) {
-  const double sw1 = acc[0], sw3 = acc[1];
+                            double* __restrict__ acc /*[8]: sum w1, sum w3, l1, l2, l3*/, float* __restrict__ dlogits,
+                            const float* __restrict__ norm /* [3] global normalisers or NULL */) {
+  // data-parallel: the reference computes ONE loss over the gathered global batch (nn.DataParallel, train.py:436-441), i.e. the
+  // weighted means are normalised by the weight sums / size of the global batch, not of this rank's shard
+  const double sw1 = norm ? (double)norm[0] : acc[0], sw3 = norm ? (double)norm[1] : acc[1];
+  const double n_total = norm ? (double)norm[2] : (double)N;
   double l1 = 0.0, l2 = 0.0, l3 = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const float* o = logits + (size_t)i * 9;
@@ -603,8 +609,8 @@ __global__ void loss_kernel(const float* __restrict__ logits, const int32_t* __r
     }
     const float diff = o[4] - center[i];
     const float ad = fabsf(diff);
-    l2 += (ad < 1.f ? 0.5 * (double)diff * diff : (double)ad - 0.5) / (double)N;       // SmoothL1Loss, beta = 1, mean
-    d[4] = (ad < 1.f ? diff : (diff > 0.f ? 1.f : -1.f)) / (float)N;
+    l2 += (ad < 1.f ? 0.5 * (double)diff * diff : (double)ad - 0.5) / n_total;       // SmoothL1Loss, beta = 1, mean
+    d[4] = (float)((ad < 1.f ? (double)diff : (diff > 0.f ? 1.0 : -1.0)) / n_total);
   }
   atomicAdd(&acc[2], l1);
   atomicAdd(&acc[3], l2);
@@ -835,28 +841,30 @@ int nsc_trainer_debug_tensor(nsc_trainer* t, const char* name, float** ptr) {
   return NSC_OK;
 }
 
-int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* running, const float* x_dev, const int32_t* type_labels,
-                               const float* centers, const int32_t* len_labels, const float* w_type_dev, const float* w_len_dev,
-                               int64_t B, float bn_momentum, float* grads, float* losses_dev, void* stream) {
-  if (!t || !params || !running || !x_dev || !type_labels || !centers || !len_labels || !w_type_dev || !w_len_dev || !grads) {
-    set_error("NULL argument");
-    return NSC_E_INVALID;
-  }
+}  // extern "C" (reopened below)
+
+namespace nsc {
+
+#define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
+#define NSC_LAUNCH_OK() NSC_CUDA_TRY(cudaGetLastError())
+
+static int train_check(nsc_trainer* t, int64_t B) {
   if (B < 2 || B > t->max_batch) { set_error("batch size %lld outside [2, %lld]", (long long)B, (long long)t->max_batch); return NSC_E_INVALID; }
-  DeviceGuard guard(t->device);
-  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", t->device); return NSC_E_CUDA; }
   if (*(volatile int*)t->flag_h) {
     *t->flag_h = 0;
     set_error("an earlier step was given class labels outside [0,4) (type in DEL,INS,NONE,SNP; length = min(len, 3), "
               "dataloader.py:415); its losses are NaN and its gradients skip those rows");
     return NSC_E_INVALID;
   }
-  cudaStream_t s = (cudaStream_t)stream;
-  const int N = (int)B;
+  return NSC_OK;
+}
+
+// training-mode forward (network.py:66-78 with BatchNorm batch statistics): leaves the logits in t->logits [N][9] and every
+// tensor the backward pass needs in the trainer's workspace
+static int train_forward(nsc_trainer* t, const float* params, float* running, const float* x_dev, int N, float bn_momentum,
+                         cudaStream_t s) {
   const float eps = 1e-5f;
   int rc;
-#define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
-#define NSC_LAUNCH_OK() NSC_CUDA_TRY(cudaGetLastError())
   // ---------------- forward (training mode) ----------------
   // max |x| of every tensor the tensor path consumes is collected by the kernel that produces it (slot li - 1 = input of
   // layer li; -1 = the output gradient du of the layer in backward)
@@ -921,13 +929,16 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   NSC_CUDA_TRY(cudaMemcpyAsync(head_b + 4, params + t->fc_off[5], 4, cudaMemcpyDeviceToDevice, s));
   NSC_CUDA_TRY(cudaMemcpyAsync(head_b + 5, params + t->fc_off[7], 16, cudaMemcpyDeviceToDevice, s));
   NSC_RUN(run_gemm(N, 9, kFcHidden, t->h, kFcHidden, 1, t->head_w, 1, kFcHidden, t->logits, 9, head_b, 0, s));
-  // ---------------- loss ----------------
-  NSC_CUDA_TRY(cudaMemsetAsync(t->red, 0, 8 * sizeof(double), s));
-  loss_weights_kernel<<<8, 256, 0, s>>>(type_labels, len_labels, w_type_dev, w_len_dev, N, t->red, t->flag_d);
-  NSC_LAUNCH_OK();
-  loss_kernel<<<8, 256, 0, s>>>(t->logits, type_labels, centers, len_labels, w_type_dev, w_len_dev, N, t->red, t->dlogits);
-  NSC_LAUNCH_OK();
-  if (losses_dev) { loss_store_kernel<<<1, 32, 0, s>>>(t->red, losses_dev, t->flag_d); NSC_LAUNCH_OK(); }
+  return NSC_OK;
+}
+
+// backward pass from t->dlogits [N][9] = d(loss)/d(o1, o2, o3): every parameter gradient into `grads`
+static int train_backward(nsc_trainer* t, const float* params, const float* x_dev, int N, float* grads, cudaStream_t s) {
+  int rc;
+  const bool fuse_amax = t->tensor_fwd && t->tensor_bwd && t->tensor_wgrad;
+  unsigned int* amax_du = fuse_amax ? umma_train_amax_slot(&t->dummy, -1) : nullptr;
+  const int widths[4] = {32, 32, 16, 8};
+  const float* W1 = params + t->fc_off[0];
   // ---------------- backward: linear layers ----------------
   // d head weights [9][240] = dlogits^T h ; biases = column sums ; dh = dlogits * head_w, masked by ReLU
   NSC_RUN(run_gemm(9, kFcHidden, N, t->dlogits, 1, 9, t->h, kFcHidden, 1, t->head_g, kFcHidden, nullptr, 0, s, t->gpart, t->gpart_floats));
@@ -1006,8 +1017,74 @@ int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* runni
   pool_bwd_kernel<1><<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, g, gz, (int64_t)N * 64 * kH, 32);
   NSC_LAUNCH_OK();
   NSC_RUN(bn_conv_bwd(0, t->u0, gz, t->a0, x_dev, gu));
+  return NSC_OK;
+}
+
 #undef NSC_RUN
 #undef NSC_LAUNCH_OK
+
+}  // namespace nsc
+
+extern "C" {
+
+int nsc_train_forward(nsc_trainer* t, const float* params, float* running, const float* x_dev, int64_t B, float bn_momentum,
+                      float* logits9, void* stream) {
+  if (!t || !params || !running || !x_dev || !logits9) { set_error("NULL argument"); return NSC_E_INVALID; }
+  DeviceGuard guard(t->device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", t->device); return NSC_E_CUDA; }
+  int rc = train_check(t, B);
+  if (rc != NSC_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = train_forward(t, params, running, x_dev, (int)B, bn_momentum, s)) != NSC_OK) return rc;
+  NSC_CUDA_TRY(cudaMemcpyAsync(logits9, t->logits, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  t->fwd_batch = B;
+  return NSC_OK;
+}
+
+int nsc_train_backward(nsc_trainer* t, const float* params, const float* x_dev, const float* dlogits9, int64_t B, float* grads,
+                       void* stream) {
+  if (!t || !params || !x_dev || !dlogits9 || !grads) { set_error("NULL argument"); return NSC_E_INVALID; }
+  if (t->fwd_batch != B) {
+    set_error("nsc_train_backward(B = %lld) does not follow nsc_train_forward of the same batch (last forward: %lld)", (long long)B,
+              (long long)t->fwd_batch);
+    return NSC_E_STATE;
+  }
+  DeviceGuard guard(t->device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", t->device); return NSC_E_CUDA; }
+  cudaStream_t s = (cudaStream_t)stream;
+  NSC_CUDA_TRY(cudaMemcpyAsync(t->dlogits, dlogits9, (size_t)B * 9 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  t->fwd_batch = -1;
+  return train_backward(t, params, x_dev, (int)B, grads, s);
+}
+
+int nsc_train_forward_backward(nsc_trainer* t, const float* params, float* running, const float* x_dev, const int32_t* type_labels,
+                               const float* centers, const int32_t* len_labels, const float* w_type_dev, const float* w_len_dev,
+                               int64_t B, float bn_momentum, float* grads, float* losses_dev, void* stream) {
+  if (!t || !params || !running || !x_dev || !type_labels || !centers || !len_labels || !w_type_dev || !w_len_dev || !grads) {
+    set_error("NULL argument");
+    return NSC_E_INVALID;
+  }
+  DeviceGuard guard(t->device);
+  if (!guard.ok) { set_error("cudaSetDevice(%d) failed", t->device); return NSC_E_CUDA; }
+  int rc = train_check(t, B);
+  if (rc != NSC_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = (int)B;
+  if ((rc = train_forward(t, params, running, x_dev, N, bn_momentum, s)) != NSC_OK) return rc;
+  // ---------------- loss ----------------
+  NSC_CUDA_TRY(cudaMemsetAsync(t->red, 0, 8 * sizeof(double), s));
+  loss_weights_kernel<<<8, 256, 0, s>>>(type_labels, len_labels, w_type_dev, w_len_dev, N, t->red, t->flag_d);
+  NSC_CUDA_TRY(cudaGetLastError());
+  loss_kernel<<<8, 256, 0, s>>>(t->logits, type_labels, centers, len_labels, w_type_dev, w_len_dev, N, t->red, t->dlogits, t->loss_norm);
+  NSC_CUDA_TRY(cudaGetLastError());
+  if (losses_dev) { loss_store_kernel<<<1, 32, 0, s>>>(t->red, losses_dev, t->flag_d); NSC_CUDA_TRY(cudaGetLastError()); }
+  t->fwd_batch = -1;
+  return train_backward(t, params, x_dev, N, grads, s);
+}
+
+int nsc_trainer_set_loss_norm(nsc_trainer* t, const float* norm_dev) {
+  if (!t) { set_error("trainer is NULL"); return NSC_E_INVALID; }
+  t->loss_norm = norm_dev;
   return NSC_OK;
 }
 

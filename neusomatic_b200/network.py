@@ -5,11 +5,14 @@ files load unchanged, with or without a ``module.`` prefix -- call.py:441-460) a
 return structure ``([o1, o2, o3], internal_outs)``.  In eval mode on a CUDA tensor the forward
 pass is ONE call into libneusomatic_cuda (hand-written sm_100a kernels) through the PyTorch
 custom op ``neusomatic_b200::forward_f32``; there is no CPU / eager fallback for inference.
-(Training mode keeps the plain ``nn`` layers so autograd works; the train step is outside this
-round's hot path.)
+In training mode on a CUDA tensor the forward is ``nsc_train_forward`` (training-mode BatchNorm, running statistics
+updated in the module's buffers) behind a ``torch.autograd.Function`` whose backward is ``nsc_train_backward``: the
+reference's loop -- ``outputs, _ = net(inputs); loss = ...; loss.backward(); optimizer.step()`` (train.py:426-441) -- runs
+unmodified on the hand-written kernels, with stock ``torch.optim.SGD`` updating the module's parameters.
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 
 import numpy as np
@@ -17,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .engine import Engine
 
 _ENGINES = {}   # id -> Engine, addressed from inside the custom op by an integer key
@@ -46,6 +50,68 @@ def _(x, engine_key):
     i32 = dict(dtype=torch.int32)
     return [x.new_empty((B, 4)), x.new_empty((B, 1)), x.new_empty((B, 4)), x.new_empty((B, 4)), x.new_empty((B, 4)),
             x.new_empty((B,), **i32), x.new_empty((B,), **i32)]
+
+
+class _TrainState:
+    """One ``nsc_trainer`` handle of the library on one device, sized for batches of up to ``max_batch``."""
+
+    def __init__(self, num_channels, device, max_batch):
+        from .train import BN_LAYERS, param_names
+        self.lib = _lib.load()
+        self.dev = torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.nsc_trainer_create(ctypes.byref(h), device, num_channels, max_batch))
+        self.h, self.max_batch = h, max_batch
+        self.n = int(self.lib.nsc_trainer_num_params(h))
+        self.names, self.bn_layers = param_names(), BN_LAYERS
+        self.slices = []
+        for name in self.names:
+            off, num = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(self.lib.nsc_trainer_param_slice(h, name.encode(), ctypes.byref(off), ctypes.byref(num)))
+            self.slices.append((off.value, num.value))
+        assert all(self.slices[i][0] + self.slices[i][1] == self.slices[i + 1][0] for i in range(len(self.slices) - 1))
+
+    def close(self):
+        if self.h:
+            self.lib.nsc_trainer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _TrainForward(torch.autograd.Function):
+    """outputs = NeuSomaticNet(x) in training mode (network.py:66-78 with batch statistics); backward = the library's full
+    backward pass.  Inputs: x, the flat running-statistics vector (updated in place by the forward), then the module's
+    parameters in named_parameters() order; their gradients come back as slices of one flat vector."""
+
+    @staticmethod
+    def forward(ctx, st, momentum, x, running, *params):
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        assert flat.numel() == st.n
+        B = x.shape[0]
+        logits = torch.empty((B, 9), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(st.lib.nsc_train_forward(st.h, flat.data_ptr(), running.data_ptr(), x.data_ptr(), B, float(momentum),
+                                            logits.data_ptr(), stream))
+        ctx.st, ctx.flat, ctx.x = st, flat, x
+        ctx.shapes = [p.shape for p in params]
+        return logits[:, 0:4].contiguous(), logits[:, 4:5].contiguous(), logits[:, 5:9].contiguous()
+
+    @staticmethod
+    def backward(ctx, g1, g2, g3):
+        st, x = ctx.st, ctx.x
+        B = x.shape[0]
+        z = lambda g, k: torch.zeros((B, k), dtype=torch.float32, device=x.device) if g is None else g.float()
+        dl = torch.cat([z(g1, 4), z(g2, 1), z(g3, 4)], 1).contiguous()
+        grads = torch.empty(st.n, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(st.lib.nsc_train_backward(st.h, ctx.flat.data_ptr(), x.data_ptr(), dl.data_ptr(), B, grads.data_ptr(), stream))
+        out = [grads[off:off + num].view(shape) for (off, num), shape in zip(st.slices, ctx.shapes)]
+        return (None, None, None, None) + tuple(out)
 
 
 class NSBlock(nn.Module):
@@ -85,7 +151,7 @@ class NeuSomaticNet(nn.Module):
         # Shared (by reference) with nn.DataParallel replicas, whose __dict__ is a shallow copy
         # (call.py:417-419): lets a replica find the original parameters and reuse one packed
         # engine per device instead of re-packing on every forward.
-        self._nsc = {"origin": weakref.ref(self), "engines": {}, "precision": None, "internals": False}
+        self._nsc = {"origin": weakref.ref(self), "engines": {}, "precision": None, "internals": False, "trainers": {}}
 
     # -- engine management ------------------------------------------------------------------
     def set_precision(self, precision):
@@ -119,15 +185,40 @@ class NeuSomaticNet(nn.Module):
         return key
 
     # -- forward ------------------------------------------------------------------------------
-    def _forward_layers(self, x):
-        x = self.pool1(F.relu(self.bn1(self.conv1(x))))
-        internal_outs = [x]
-        x = self.res_layers(x)
-        internal_outs.append(x)
-        x2 = x.view(-1, self.fc_dim)
-        x3 = F.relu(self.fc1(x2))
-        internal_outs.extend([x2, x3])
-        return [self.fc2(x3), self.fc3(x3), self.fc4(x3)], internal_outs
+    def _tensor_at(self, dotted):
+        """The tensor behind ``dotted`` on THIS module object: a Parameter / buffer on the original module, the broadcast
+        copy on an nn.DataParallel replica (whose parameters() is empty but whose attributes are set)."""
+        obj = self
+        for part in dotted.split("."):
+            obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+        return obj
+
+    def _forward_train(self, x):
+        """Training-mode forward on the library's kernels (nsc_train_forward / nsc_train_backward behind autograd)."""
+        if not x.is_cuda:
+            raise RuntimeError("neusomatic_b200.NeuSomaticNet trains on CUDA only (sm_100a kernels); no CPU fallback")
+        x = x.contiguous().float()
+        B = x.shape[0]
+        if B < 2:
+            raise ValueError("training-mode BatchNorm needs more than one candidate per batch (as nn.BatchNorm2d does)")
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        st = self._nsc["trainers"].get(idx)
+        if st is None or st.max_batch < B:
+            if st is not None:
+                st.close()
+            st = _TrainState(self.num_channels, idx, max(256, (B + 255) // 256 * 256))
+            self._nsc["trainers"][idx] = st
+        params = [self._tensor_at(n) for n in st.names]
+        bns = [self._tensor_at(n) for n in st.bn_layers]
+        running = torch.cat([t for bn in bns for t in (bn.running_mean.detach().float(), bn.running_var.detach().float())])
+        outs = _TrainForward.apply(st, bns[0].momentum, x, running, *params)
+        with torch.no_grad():           # the forward updated the flat copy: hand the statistics back to the module's buffers
+            for i, bn in enumerate(bns):
+                bn.running_mean.copy_(running[i * 128:i * 128 + 64])
+                bn.running_var.copy_(running[i * 128 + 64:i * 128 + 128])
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+        return list(outs), []
 
     def score(self, x):
         """[o1, o2, o3, softmax(o1), softmax(o3), argmax(o1), argmax(o3)] of a CUDA batch in one library call: what
@@ -141,7 +232,7 @@ class NeuSomaticNet(nn.Module):
 
     def forward(self, x):
         if self.training:
-            return self._forward_layers(x)
+            return self._forward_train(x)
         if not x.is_cuda:
             raise RuntimeError("neusomatic_b200.NeuSomaticNet scores on CUDA only (sm_100a kernels); "
                                "there is no CPU fallback -- move the batch to the GPU")

@@ -117,14 +117,29 @@ class Trainer:
         return self.losses
 
     def step(self, x, labels, centers, len_labels, w_type, w_len, group=None):
-        """One train.py iteration (train.py:426-441); with torch.distributed initialised the gradients are
-        summed over ranks (NCCL) and scaled by 1/world -- the only exchange step of the path."""
+        """One train.py iteration (train.py:426-441); with torch.distributed initialised the per-rank gradients of the
+        GLOBAL loss are summed over ranks (NCCL) -- the only exchange step of the path.  BatchNorm uses the statistics of
+        the rank's own shard and each rank keeps its own running statistics, as the replicas of the reference's
+        nn.DataParallel do (rank 0's are the ones a checkpoint would hold, like device 0's there).  The returned losses
+        are this rank's share of the global loss (their sum over ranks is the reference's loss)."""
         import torch.distributed as dist
-        losses = self.forward_backward(x, labels, centers, len_labels, w_type, w_len)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if multi:
+            # the reference's nn.DataParallel computes one loss over the global batch (train.py:436-441): normalise both
+            # weighted cross entropies and SmoothL1 by the GLOBAL weight sums / batch size (3 floats all-reduced before the
+            # step; the labels are known up front), then SUM the per-rank gradients
+            self._norm = torch.stack([w_type[labels.long()].sum(), w_len[len_labels.long()].sum(),
+                                      torch.tensor(float(x.shape[0]), device=self.dev)]).float()
+            dist.all_reduce(self._norm, op=dist.ReduceOp.SUM, group=group)
+            _lib.check(self.lib.nsc_trainer_set_loss_norm(self.h, self._norm.data_ptr()))
+        try:
+            losses = self.forward_backward(x, labels, centers, len_labels, w_type, w_len)
+        finally:
+            if multi:
+                _lib.check(self.lib.nsc_trainer_set_loss_norm(self.h, None))
         scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if multi:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=group)
-            scale = 1.0 / dist.get_world_size(group)
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         _lib.check(self.lib.nsc_sgd_momentum_update(self.params.data_ptr(), self.mom.data_ptr(), self.grads.data_ptr(), self.n,
                                                     self.lr, self.momentum, scale, stream))

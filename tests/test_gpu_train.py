@@ -159,3 +159,111 @@ def test_ensemble_channels_and_ragged_batch_against_float64_oracle(C, B, mode, m
            if v > (2e-5 if strict_everywhere or k.startswith(("fc", "res_layers.2", "res_layers.3")) else 2e-2)}
     assert not bad, bad
     tr.close()
+
+
+def test_reference_training_loop_runs_unmodified_on_the_module():
+    """train.py:416-441 verbatim in shape -- net.train(); optimizer.zero_grad(); outputs, _ = net(inputs); loss = CE + SmoothL1
+    + CE; loss.backward(); optimizer.step() -- with the drop-in module and stock torch.optim.SGD: the forward / backward
+    run on the library's kernels behind autograd, losses, gradients, parameters and BatchNorm running statistics after two
+    iterations match the unmodified reference (tests/golden/train_std.npz)."""
+    import torch.nn as nn
+    import torch.optim as optim
+    from neusomatic_b200.network import NeuSomaticNet
+    g, x = _golden()
+    sd0 = {k: torch.from_numpy(v) for k, v in synth.random_state_dict(26, seed=11).items()}
+    net = NeuSomaticNet(26)
+    net.load_state_dict(sd0, strict=False)
+    net = net.cuda()
+    net.train()
+    inputs = torch.from_numpy(x).cuda()
+    labels = torch.from_numpy(g["labels"]).long().cuda()
+    var_pos = torch.from_numpy(g["center"]).float().cuda()
+    var_len_labels = torch.from_numpy(g["len_labels"]).long().cuda()
+    criterion_crossentropy = nn.CrossEntropyLoss(torch.from_numpy(g["w_type"]).cuda())
+    criterion_crossentropy2 = nn.CrossEntropyLoss(torch.from_numpy(g["w_len"]).cuda())
+    criterion_smoothl1 = nn.SmoothL1Loss()
+    optimizer = optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+    for step in range(2):
+        optimizer.zero_grad()
+        outputs, _ = net(inputs)
+        [outputs_classification, outputs_pos, outputs_len] = outputs
+        loss = criterion_crossentropy(outputs_classification, labels) + 1 * criterion_smoothl1(
+            outputs_pos.squeeze(1), var_pos) + 1 * criterion_crossentropy2(outputs_len, var_len_labels)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g["loss%d" % step][0], rtol=2e-4)
+        if step == 0:
+            for k in g:
+                if k.startswith("grad."):
+                    got = dict(net.named_parameters())[k[5:]].grad.cpu().numpy()
+                    assert got.shape == g[k].shape
+                    assert np.abs(got - g[k]).max() <= max(1e-2 * float(np.abs(g[k]).max()), 2e-6), k
+        optimizer.step()
+    sd = net.state_dict()
+    for k in g:
+        if k.startswith("final."):
+            np.testing.assert_allclose(sd[k[6:]].cpu().numpy().reshape(g[k].shape), g[k], rtol=2e-3, atol=5e-4)
+    assert int(sd["bn1.num_batches_tracked"]) == 2
+    # and the trained module scores in eval mode through the inference kernels (weights re-packed after the update)
+    net.eval()
+    with torch.no_grad():
+        (o1, o2, o3), _ = net(inputs)
+    r1, _, _ = oracle.forward(oracle.normalize_state_dict({k: v.cpu() for k, v in sd.items()}), x)
+    np.testing.assert_allclose(o1.cpu().numpy(), r1, atol=5e-3)
+
+
+def test_module_rejects_cpu_training_and_single_candidate_batches():
+    from neusomatic_b200.network import NeuSomaticNet
+    net = NeuSomaticNet(26).train()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(4, 26, 5, 32))
+    net = net.cuda()
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 26, 5, 32, device="cuda"))
+
+
+def test_out_of_range_labels_are_flagged_not_read():
+    """A label outside [0,4) must not index the class weights: the step's losses are NaN and the next call fails
+    (the reference's CrossEntropyLoss raises); wrong dtypes are rejected before the raw pointers reach the library."""
+    from neusomatic_b200.train import Trainer
+    from neusomatic_b200._lib import NscError
+    g, x = _golden()
+    tr = Trainer(synth.random_state_dict(26, seed=11), 26, max_batch=64)
+    xin, labels, centers, len_labels, w1, w3 = _cuda_inputs(g, x)
+    with pytest.raises(ValueError):
+        tr.forward_backward(xin, labels.long(), centers, len_labels, w1, w3)            # int64 labels (PyTorch's default)
+    with pytest.raises(ValueError):
+        tr.forward_backward(xin, labels, centers.double(), len_labels, w1, w3)
+    bad = len_labels.clone()
+    bad[3] = 7                                                                              # raw indel length, not min(len, 3)
+    losses = tr.forward_backward(xin, labels, centers, bad, w1, w3).cpu().numpy()
+    assert np.isnan(losses).all()
+    with pytest.raises(NscError):
+        tr.forward_backward(xin, labels, centers, len_labels, w1, w3)
+    losses = tr.forward_backward(xin, labels, centers, len_labels, w1, w3).cpu().numpy()   # the flag is cleared by the report
+    np.testing.assert_allclose(losses, g["loss0"], rtol=1e-4)
+    tr.close()
+
+
+def test_global_loss_normalisation_scales_the_shard_gradients():
+    """nsc_trainer_set_loss_norm: with the normalisers of a (hypothetical) global batch twice this one, every gradient and
+    loss term of the shard is exactly half of the stand-alone step's -- so that shard gradients SUM to the gradient of the
+    reference's single loss over the gathered batch (nn.DataParallel, train.py:436-441)."""
+    from neusomatic_b200 import _lib
+    from neusomatic_b200.train import Trainer
+    g, x = _golden()
+    tr = Trainer(synth.random_state_dict(26, seed=11), 26, max_batch=64)
+    inp = _cuda_inputs(g, x)
+    l0 = tr.forward_backward(*inp).cpu().numpy().copy()
+    g0 = tr.grads.clone()
+    running0 = tr.running.clone()
+    labels, len_labels, w1, w3 = inp[1], inp[3], inp[4], inp[5]
+    norm = torch.stack([2 * w1[labels.long()].sum(), 2 * w3[len_labels.long()].sum(), torch.tensor(2.0 * len(labels), device="cuda")]).float()
+    tr.load_state_dict(synth.random_state_dict(26, seed=11))          # same parameters and running statistics again
+    _lib.check(tr.lib.nsc_trainer_set_loss_norm(tr.h, norm.data_ptr()))
+    l1 = tr.forward_backward(*inp).cpu().numpy().copy()
+    _lib.check(tr.lib.nsc_trainer_set_loss_norm(tr.h, None))
+    np.testing.assert_allclose(l1, 0.5 * l0, rtol=1e-6)
+    scale = float(g0.abs().max())
+    assert float((tr.grads - 0.5 * g0).abs().max()) <= 2e-6 * scale
+    torch.testing.assert_close(tr.running, running0)
+    tr.close()
