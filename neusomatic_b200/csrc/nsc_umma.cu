@@ -1128,7 +1128,8 @@ static int umma_ensure_workspace(nsc_model* m, int64_t need) {
   return NSC_OK;
 }
 
-enum : int { kOutLo = 1, kOutC8 = 2, kOutHiLo = kOutLo };   // which companions of the fp16 hi tensor a layer writes
+enum : int { kOutLo = 1, kOutC8 = 2, kOutHiLo = kOutLo };
+constexpr unsigned kS8LayerMask = 0xffu;   // layers of NSC_PREC_SPLIT8 that take the fp8 corrections (bit l = 64 -> 64 convolution l)   // which companions of the fp16 hi tensor a layer writes
 
 template <class Cfg>
 static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const uint8_t* wpk, const float* bias,
@@ -1244,44 +1245,59 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
   return umma_run(m, n, o, s);
 }
 
-template <bool S8>
-static int umma_run_t(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
+// One forward pass over the packed network input.  `s8` = bit l set: 64 -> 64 convolution l (0 = res_layers.0.conv_r1, 1 =
+// res_layers.0.conv_r2, ... 7 = res_layers.3.conv_r2) computes its two correction products on the fp8 tensor path
+// (NSC_PREC_SPLIT8), bit clear: all three products in fp16 (NSC_PREC_SPLIT16).  A producer writes what its consumers read:
+// the exact fp16 lo part for a residual input or a split-fp16 consumer, the c8 image for an fp8-correction consumer.
+static int umma_run_mask(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s, unsigned s8) {
   int rc;
   UmmaState& u = m->umma;
   const Fp32Weights& w = m->w32;
 #define NSC_RUN(call) do { rc = (call); if (rc != NSC_OK) return rc; } while (0)
+  // layer l as <S8 = true> or <S8 = false> instantiation of the same configuration
+#define NSC_CONV(l, KH, KW, DIL, WW, NK, POOL, KC, GP, slot, in, out, res, relu, fmt)                                                       \
+  do {                                                                                                                                   \
+    if ((s8 >> (l)) & 1u)                                                                                                                \
+      NSC_RUN((launch_umma_conv<ConvCfg<KH, KW, DIL, WW, NK, POOL, false, KC, GP, true>>(m, slot, in, u.wpk8[(l) / 2][(l) % 2],          \
+                                                                                          w.res_b[(l) / 2][(l) % 2], out, nullptr, res, n, \
+                                                                                          relu, s, fmt)));                               \
+    else                                                                                                                                 \
+      NSC_RUN((launch_umma_conv<ConvCfg<KH, KW, DIL, WW, NK, POOL, false, KC, GP, false>>(m, slot, in, u.wpk[(l) / 2][(l) % 2],          \
+                                                                                           w.res_b[(l) / 2][(l) % 2], out, nullptr, res, n, \
+                                                                                           relu, s, fmt)));                              \
+  } while (0)
   uint16_t** X = u.buf[0];   // block input (and residual)
   uint16_t** Y = u.buf[1];   // relu(bn(conv_r1))
   uint16_t** N = u.buf[2];   // pooled block output
-  // what the consumers of a tensor need besides its fp16 hi part: a block input is a residual (exact lo) and, for
-  // NSC_PREC_SPLIT8, an fp8 correction operand (c8); conv_r1's output only feeds conv_r2
-  constexpr int oX = S8 ? (kOutLo | kOutC8) : kOutHiLo, oY = S8 ? kOutC8 : kOutHiLo;
-  uint8_t* const (*wp)[2] = S8 ? u.wpk8 : u.wpk;
+  auto fmt_block_input = [&](int l) { return kOutLo | (((s8 >> l) & 1u) ? kOutC8 : 0); };      // consumers: conv l + the residual of conv l + 1
+  auto fmt_mid = [&](int l) { return ((s8 >> l) & 1u) ? kOutC8 : kOutLo; };                      // consumer: conv l only
+  uint16_t** const none = nullptr;
   // conv1 + BN + ReLU + pool1 (network.py:44-47,67): split-fp16 in every tensor mode (its input is the packed hi/lo image)
-  if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
-  else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
-  else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, oX)));
+  if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
+  else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
+  else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   NSC_RUN(dbg_unpack(m, 0, X, 32, n, s));
   // block 0 (3x3 d1, 5x5 d1, pool stride 1)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false, 32, 1, S8>>(m, 2, X, wp[0][0], w.res_b[0][0], Y, nullptr, nullptr, n, 1, s, oY)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 1, false, 32, 1, S8>>(m, 3, Y, wp[0][1], w.res_b[0][1], N, nullptr, X, n, 0, s, oX)));
+  NSC_CONV(0, 3, 3, 1, 32, 2, 0, 32, 1, 2, X, Y, none, 1, fmt_mid(1));
+  NSC_CONV(1, 5, 5, 1, 32, 2, 1, 32, 1, 3, Y, N, X, 0, fmt_block_input(2));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 1, X, 32, n, s));
   // block 1 (3x3 d1, 5x5 d1, pool stride 2)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 1, 32, 2, 0, false, 32, 1, S8>>(m, 4, X, wp[1][0], w.res_b[1][0], Y, nullptr, nullptr, n, 1, s, oY)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 32, 2, 2, false, 32, 1, S8>>(m, 5, Y, wp[1][1], w.res_b[1][1], N, nullptr, X, n, 0, s, oX)));
+  NSC_CONV(2, 3, 3, 1, 32, 2, 0, 32, 1, 4, X, Y, none, 1, fmt_mid(3));
+  NSC_CONV(3, 5, 5, 1, 32, 2, 2, 32, 1, 5, Y, N, X, 0, fmt_block_input(4));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 2, X, 16, n, s));
   // block 2 (3x3 d2, 5x5 d1, pool stride 2)
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 2, 16, 2, 0, false, 32, 1, S8>>(m, 6, X, wp[2][0], w.res_b[2][0], Y, nullptr, nullptr, n, 1, s, oY)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 1, 16, 2, 2, false, 32, 1, S8>>(m, 7, Y, wp[2][1], w.res_b[2][1], N, nullptr, X, n, 0, s, oX)));
+  NSC_CONV(4, 3, 3, 2, 16, 2, 0, 32, 1, 6, X, Y, none, 1, fmt_mid(5));
+  NSC_CONV(5, 5, 5, 1, 16, 2, 2, 32, 1, 7, Y, N, X, 0, fmt_block_input(6));
   std::swap(X, N);
   NSC_RUN(dbg_unpack(m, 3, X, 8, n, s));
   // block 3 (3x3 d4, 5x5 d2, pool stride 2) -> packed hi/lo [B][5][4][64] for fc1
-  NSC_RUN((launch_umma_conv<ConvCfg<3, 3, 4, 8, 4, 0, false, 16, 2, S8>>(m, 8, X, wp[3][0], w.res_b[3][0], Y, nullptr, nullptr, n, 1, s, oY)));
-  NSC_RUN((launch_umma_conv<ConvCfg<5, 5, 2, 8, 4, 2, false, 16, 2, S8>>(m, 9, Y, wp[3][1], w.res_b[3][1], N, nullptr, X, n, 0, s, kOutHiLo)));
+  NSC_CONV(6, 3, 3, 4, 8, 4, 0, 16, 2, 8, X, Y, none, 1, fmt_mid(7));
+  NSC_CONV(7, 5, 5, 2, 8, 4, 2, 16, 2, 9, Y, N, X, 0, kOutHiLo);
   NSC_RUN(dbg_unpack(m, 4, N, 4, n, s));
   NSC_RUN(fc_umma_forward(m, N, n, o, s));
+#undef NSC_CONV
 #undef NSC_RUN
   return NSC_OK;
 }
@@ -1292,9 +1308,10 @@ static int umma_run(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t s) {
       set_error("folded convolution weights exceed the range of the fp8 correction terms (|w| > 28); use NSC_PREC_SPLIT16");
       return NSC_E_STATE;
     }
-    return umma_run_t<true>(m, n, o, s);
+    const char* e = getenv("NSC_S8_MASK");      // experiments: which layers take the fp8 corrections (default: all eight)
+    return umma_run_mask(m, n, o, s, e ? (unsigned)strtoul(e, nullptr, 0) & 0xffu : kS8LayerMask);
   }
-  return umma_run_t<false>(m, n, o, s);
+  return umma_run_mask(m, n, o, s, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
