@@ -211,16 +211,25 @@ def _score_batch(net, matrices):
     return torch.cat(parts, 0).numpy()
 
 
+# candidates gathered from successive loader batches before one device call: the reference's batch sizes (100 in
+# test/run_test.sh, 1000 by default, call.py:585-586) are one wave of 8-candidate groups or less on 148 SMs and run at the
+# latency of ten dependent layer kernels; the results do not depend on how candidates are batched, so the loop scores
+# them in larger slices
+COALESCE_CANDIDATES = 8192
+
+
 def call_variants(net, vartype_classes, call_loader, out_dir, model_tag, use_cuda):
     """call.py:54-118, same signature and return value ``(final_preds, none_preds, true_path)``.
 
-    ``net`` is a ``neusomatic_b200.network.NeuSomaticNet`` (possibly wrapped in nn.DataParallel).  ``true_path`` maps
-    every non-NONE candidate to its ``non_transformed[:, :, 0:3]`` image.  When the reference's hand-over directory
-    ``{out_dir}/matrices_{model_tag}`` exists and ``imageio`` is installed -- i.e. inside the reference's own
-    call_neusomatic -- the image is written there as a PNG and ``true_path`` holds the file name, exactly as call.py:89-95
-    does, so the unmodified ``pred_vcf_records_path`` (call.py:128 ``imread``) keeps working.  Otherwise ``true_path`` holds
-    the uint8 [5,32,3] array itself, which this package's ``pred_vcf_records_path`` accepts (the PNG is a lossless round
-    trip of exactly these bytes)."""
+    ``net`` is a ``neusomatic_b200.network.NeuSomaticNet`` (possibly wrapped in nn.DataParallel).  Loader batches are
+    copied to the device as they arrive and scored in slices of at least COALESCE_CANDIDATES candidates (one fused library
+    call and one D2H per slice); the dictionaries are filled in loader order, so a repeated tag is overwritten exactly as in
+    the reference.  ``true_path`` maps every non-NONE candidate to its ``non_transformed[:, :, 0:3]`` image.  When the
+    reference's hand-over directory ``{out_dir}/matrices_{model_tag}`` exists and ``imageio`` is installed -- i.e. inside
+    the reference's own call_neusomatic -- the image is written there as a PNG and ``true_path`` holds the file name,
+    exactly as call.py:89-95 does, so the unmodified ``pred_vcf_records_path`` (call.py:128 ``imread``) keeps working.
+    Otherwise ``true_path`` holds the uint8 [5,32,3] array itself, which this package's ``pred_vcf_records_path`` accepts
+    (the PNG is a lossless round trip of exactly these bytes)."""
     if not use_cuda:
         raise RuntimeError("neusomatic_b200 scores on CUDA only")
     net.eval()
@@ -234,23 +243,32 @@ def call_variants(net, vartype_classes, call_loader, out_dir, model_tag, use_cud
                 png_dir = d
             except ImportError:
                 png_dir = None
-    iii = j = 0
-    for data in call_loader:
-        (matrices, labels, var_pos_s, var_len_s, non_transformed_matrices), (paths) = data
-        iii += 1
-        j += len(paths[0])
+    inner = net.module if isinstance(net, torch.nn.DataParallel) else net
+    dev = next(inner.parameters()).device
+    pending, n_pending = [], 0          # (device matrices, paths, non_transformed) of the loader batches not yet scored
+
+    def flush():
+        nonlocal pending, n_pending
+        if not pending:
+            return
+        mats = pending[0][0] if len(pending) == 1 else torch.cat([p[0] for p in pending], 0)
         with torch.no_grad():
-            packed = _score_batch(net, matrices)
-        n_before = len(final_preds)
-        build_pred_dicts(packed[:, 0:4], packed[:, 4:5], packed[:, 5:9], packed[:, 9:13], packed[:, 13:17],
-                         packed[:, 17].astype(np.int64), packed[:, 18].astype(np.int64), paths[0],
-                         vartype_classes, final_preds, none_preds)
-        if len(final_preds) != n_before or png_dir is not None:
-            nt = np.asarray(non_transformed_matrices)
-            for i, path_ in enumerate(paths[0]):
-                path = path_.split("/")[-1]
-                if path not in final_preds:
-                    continue
+            packed = _score_batch(net, mats)
+        lo = 0
+        for _m, paths, nt in pending:
+            hi = lo + len(paths)
+            pk = packed[lo:hi]
+            lo = hi
+            n_before = len(final_preds)
+            build_pred_dicts(pk[:, 0:4], pk[:, 4:5], pk[:, 5:9], pk[:, 9:13], pk[:, 13:17], pk[:, 17].astype(np.int64),
+                             pk[:, 18].astype(np.int64), paths, vartype_classes, final_preds, none_preds)
+            if len(final_preds) == n_before and png_dir is None:
+                continue
+            nt = np.asarray(nt)
+            var = np.nonzero(pk[:, 17].astype(np.int64) != vartype_classes.index("NONE"))[0] if "NONE" in vartype_classes \
+                else np.arange(len(paths))
+            for i in var:
+                path = paths[i].split("/")[-1]
                 if png_dir is not None:
                     file_name = "{}/{}.png".format(png_dir, path)
                     if not os.path.exists(file_name):
@@ -258,8 +276,20 @@ def call_variants(net, vartype_classes, call_loader, out_dir, model_tag, use_cud
                     true_path[path] = file_name
                 elif path not in true_path:
                     true_path[path] = np.array(nt[i, :, :, 0:3])
+        pending, n_pending = [], 0
+
+    iii = j = 0
+    for data in call_loader:
+        (matrices, labels, var_pos_s, var_len_s, non_transformed_matrices), (paths) = data
+        iii += 1
+        j += len(paths[0])
+        pending.append((matrices.to(dev, non_blocking=True), list(paths[0]), non_transformed_matrices))
+        n_pending += len(paths[0])
+        if n_pending >= COALESCE_CANDIDATES:
+            flush()
         if iii % 10 == 0:
             logger.info("Called {} candidates in this batch.".format(j))
+    flush()
     logger.info("Called {} candidates in this batch.".format(j))
     return final_preds, none_preds, true_path
 

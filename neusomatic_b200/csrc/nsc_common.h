@@ -112,7 +112,7 @@ struct UmmaState {
 struct nsc_model {
   int device = 0;
   int C = 26;
-  int precision = NSC_PREC_SPLIT8;                     // library default; falls back to SPLIT16 at finalize if |w| > 28
+  int precision = NSC_PREC_SPLIT16;                    // library default (NSC_PREC_SPLIT8 = opt-in fast mode)
   bool precision_explicit = false;                     // set through nsc_model_set_precision
   bool finalized = false;
   bool normalize_channels = false;                     // checkpoint["normalize_channels"]
@@ -196,7 +196,7 @@ int umma_train_bn_bwd_pack(nsc_model* m, int W, const float* u, const float* sta
 // where the producer of a tensor leaves max |x| (bit pattern of a float): xslot 0..7 = input of the 64 -> 64 layer, -1 = du
 unsigned int* umma_train_amax_slot(nsc_model* m, int xslot);
 // multiplier of a tensor-path layer's folded weights that undoes the accumulator's round-toward-zero shrink (nsc_umma.cu)
-constexpr double kRzKappa = 0.0;
+constexpr double kRzKappa = 1.3;    // tools/rz_kappa_sweep.py: 4-decimal mismatch 5.8 % (0) -> 0.8 % (1.2 .. 1.4) -> 3.3 % (2.0), worst golden set
 double rz_compensation(int n_steps, double valid_share);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);

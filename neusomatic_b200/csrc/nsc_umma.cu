@@ -1046,17 +1046,21 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
       snprintf(bn, sizeof bn, "res_layers.%d.bn_r%d", i, j + 1);
       const int k = j == 0 ? kBlocks[i].k1 : kBlocks[i].k2;
       if ((rc = fold_conv_bn(m, conv, bn, bn_eps, &f)) != NSC_OK) return rc;
+      double rz = 1.0;
       {
         // share of kernel rows inside the 5-row image, averaged over the output rows (the others are never issued)
         const int d = j == 0 ? kBlocks[i].d1 : kBlocks[i].d2, ph = d * (k - 1) / 2;
         int valid = 0;
         for (int h = 0; h < kH; ++h)
           for (int dy = 0; dy < k; ++dy) valid += (h + dy * d - ph >= 0 && h + dy * d - ph < kH) ? 1 : 0;
-        scale_weights(f.w, rz_compensation(k * k * 4, (double)valid / (kH * k)));
+        rz = rz_compensation(k * k * 4, (double)valid / (kH * k));
       }
       const int kc = i == 3 ? 16 : 32;     // the W = 8 layers run two groups per unit on 16-channel phases
-      if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 64 / kc, kc, &max_abs))) != NSC_OK) return rc;
+      // the fp8-correction images stay uncompensated: in that mode the 4-bit correction operands, not the accumulator's
+      // rounding, set the error (tools/rz_kappa_sweep.py: no kappa improves it), so only the split-fp16 image is scaled
       if ((rc = upload_bytes(&u.wpk8[i][j], pack_conv_weights_s8(f.w, k, k, kc))) != NSC_OK) return rc;
+      scale_weights(f.w, rz);
+      if ((rc = upload_bytes(&u.wpk[i][j], pack_conv_weights(f.w, 64, k, k, 64 / kc, kc, &max_abs))) != NSC_OK) return rc;
     }
   u.weights_fit_fp16 = max_abs < 6.0e4f;
   u.weights_fit_fp8 = max_abs <= 28.f;     // e4m3(w * 2^3) and e4m3(w_lo * 2^15) stay below 448

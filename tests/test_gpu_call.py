@@ -37,7 +37,7 @@ def _write_inputs(tmp_path, name):
 # order are left (the reference differs from itself by as much between batch sizes, tests/test_call_host.py).  Default mode
 # (split fp16 + fp8 corrections): probabilities move by up to ~1e-4, i.e. some 4-decimal SCOREs by one unit; the records
 # (chrom, pos, ref, alt), their order and the FILTER column must still be the reference's (vcf_identity asserts that).
-@pytest.mark.parametrize("precision,min_same", [(2, 0.97), (3, 0.75), (0, 0.75)])
+@pytest.mark.parametrize("precision,min_same", [(2, 0.97), (3, 0.75), (0, 0.93)])
 @pytest.mark.parametrize("name", ["std_v014", "std_wex", "ens_v014"])
 def test_call_neusomatic_writes_the_reference_vcf(tmp_path, monkeypatch, name, precision, min_same):
     from neusomatic_b200.call import call_neusomatic

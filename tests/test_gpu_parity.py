@@ -15,9 +15,10 @@ from neusomatic_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL_PROB, TOL_POS = 2e-3, 1e-3
-# share of 4-decimal probability entries that may differ from the reference's on a golden set in the tensor modes: the
-# measured worst case (profiles/r2_parity_large.json, tools/parity_report.py) plus a margin
-MAX_4DP_MISMATCH = 0.08
+# share of 4-decimal probability entries that may differ from the reference's on a golden set, per NSC_PREC_* mode: the
+# measured worst case over the five sets (tools/rz_kappa_sweep.py, tools/parity_report.py: 0.8 % default mode, 5.7 % fp8
+# corrections, 0.13 % CUDA-core fp32) plus a margin
+MAX_4DP_MISMATCH = {0: 0.015, 3: 0.08, 2: 0.005}
 MODES = [0, 2, 3]   # NSC_PREC_* modes that must meet the parity bar: split-fp16 tensor path, fp32 path, fp8-correction tensor path
 
 
@@ -185,7 +186,7 @@ def test_pred_dicts_match_oracle_call_variants(golden, precision):
     # fp32 path: rounding-boundary crossings only; tensor path: fp32-accumulate truncation in the tensor
     # cores moves probabilities by ~1e-4, i.e. about one 4-dp step on unsaturated candidates
     print("%s precision %d: 4-dp probability mismatch rate %.4f" % (name, precision, mism / tot))
-    assert mism / tot < (0.02 if precision == 2 else MAX_4DP_MISMATCH)
+    assert mism / tot < MAX_4DP_MISMATCH[precision]
     sc.engine.close()
 
 

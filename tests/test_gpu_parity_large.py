@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 
 N = 100000
 # per mode: share of 4-decimal probability entries that may differ from the reference's (measured on 2e5 candidates,
-# profiles/r2_parity_large.json, plus a margin): NSC_PREC_SPLIT8 (default), NSC_PREC_SPLIT16, NSC_PREC_FP32
-MAX_MM4 = {3: 0.075, 0: 0.075, 2: 0.006}
+# profiles/r2_parity_large.json, plus a margin): NSC_PREC_SPLIT8 (fast mode), NSC_PREC_SPLIT16 (default), NSC_PREC_FP32
+MAX_MM4 = {3: 0.075, 0: 0.015, 2: 0.006}
 
 
 @pytest.mark.parametrize("family", ["S2", "S3"])
