@@ -101,6 +101,9 @@ struct UmmaState {
   uint16_t* tpk[8][2] = {};             // training: packed (hi, lo) inputs of the eight 64 -> 64 convolutions, kept for the weight gradient
   float* tscl = nullptr;                // training: [8][4] absmax bits / inverse scales of those tensors
   uint8_t* twpk[8][2] = {};             // training: packed weight stages of those layers for this step (forward, data gradient)
+  const uint8_t* u8_mat = nullptr;      // set for the duration of a pass on the uint8 interface: the stem builds its operand from
+  const int32_t* u8_meta = nullptr;     // the stored matrices (csrc/nsc_umma.cu, ConvCfg::U8IN)
+  double u8_thr = 0.0;
   int64_t cap = 0;
   int num_sms = 148;
   bool weights_fit_fp16 = true;

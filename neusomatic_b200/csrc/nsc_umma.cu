@@ -68,9 +68,16 @@ __device__ __forceinline__ void tmem_ld_cpt(uint32_t taddr, uint32_t (&r)[16]) {
 constexpr int kStageBytes = 32768;      // epilogue staging: hi plane + lo plane of one [128 x 64] row tile
 constexpr int kStashBytes = 20480;      // boundary columns carried between the two column blocks (W = 32)
 
-template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_, int KC_ = 32, int GP_ = 1, bool S8_ = false>
+constexpr int kU8CandBytes = kH * kW * kStoredCh;    // 3680: one stored candidate matrix (uint8 [5][32][23])
+constexpr int kU8StageBytes = 8 * kU8CandBytes;      // the eight matrices of a candidate group
+
+template <int KH_, int KW_, int DIL_, int W_, int NK_, int POOL_, bool NCHW_, int KC_ = 32, int GP_ = 1, bool S8_ = false,
+          bool U8IN_ = false>
 struct ConvCfg {
   static constexpr bool S8 = S8_;                        // fp8 correction products (64 input channels only)
+  // the stem on the uint8 interface: the A operand is built in shared memory by two producer warps straight from the stored
+  // candidate matrices (channel assembly of dataloader.py:383-417 + hi/lo split), no packed network input in HBM
+  static constexpr bool U8IN = U8IN_;
   static constexpr int KH = KH_, KW = KW_, DIL = DIL_, W = W_, NK = NK_, POOL = POOL_;
   static constexpr bool NCHW = NCHW_;
   static constexpr int KC = KC_;                         // input channels per phase / weight stage (32 or 16)
@@ -102,8 +109,9 @@ struct ConvCfg {
   // [128 rows][128 B] swizzle-128B tiles (x16 and c8 / lo16): no item phase, no LSU stores
   static constexpr bool TMAOUT = (POOL == 0) && (GP == 1) && (TW == 16) && !NCHW;
   static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
-                                 (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + 256;
+                                 (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + (U8IN ? kU8StageBytes + 2048 : 0) + 256;
   static_assert(SMEM <= 232448 - 1024, "shared memory budget");
+  static_assert(!U8IN || (KH == 1 && NK == 1 && KC == 32 && GP == 1 && W == 32), "the uint8 producer builds the stem's 26 -> 32 channel operand");
 };
 
 // accumulator slot (64 TMEM columns each) of output row h: rows of one dilation chain are adjacent and
@@ -163,6 +171,9 @@ struct UmmaConvArgs {
   int B;
   int relu;
   int split;                 // 1: hi/lo split operands (3 products); 0: single-pass fp16
+  const uint8_t* u8_mat;     // U8IN: stored candidate matrices uint8 [B][5][32][23]
+  const int32_t* u8_meta;    // U8IN: [B][3] = (center, tumor_cov, normal_cov)
+  double u8_thr;             // U8IN: coverage_thr of the checkpoint
   long long* stats;          // optional [grid][8] cycle counters (NSC_UMMA_STATS=1)
   int dbg_skip;              // timing experiments only (NSC_UMMA_SKIP): 1 = no fp8 MMAs, 2 = no fp16 MMAs, 4 = no epilogue body,
                              // 8 / 16 = no A / weight loads, 32 = pooled layers store only the fp16 hi part
@@ -315,13 +326,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   uint8_t* st_hi = w_buf + WS * Cfg::W_STAGE_BYTES;              // 16 KB: [128 rows][128 B], chunk-swizzled
   uint8_t* st_lo = st_hi + 16384;
   uint8_t* stash = st_lo + 16384;                                // [hi|lo][2 cols][5][8 g][8 chunks][16 B]
-  __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2];
+  // U8IN: the group's stored matrices + two 256-entry tables byte -> packed (fp16 hi | fp16 lo << 16) of b / 255 (plain) and
+  // of (b / 255 - 0.5) / 0.5 (channels 0..2), behind everything else
+  uint8_t* u8_stage = stash + (Cfg::STASH ? kStashBytes : 0) + (Cfg::TMAOUT ? kStageBytes : 0);
+  uint32_t* u8_tab = reinterpret_cast<uint32_t*>(u8_stage + kU8StageBytes);
+  __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2 + 1];
+  __shared__ uint32_t u8_cst[8][4];     // per candidate: packed hi|lo of the centre marker value, tumor coverage, normal coverage
+  __shared__ int u8_center[8];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[64];
   const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[3]);
   const uint32_t w_full = smem_u32(&bars[6]), w_empty = smem_u32(&bars[14]);
   const uint32_t acc_full = smem_u32(&bars[22]), shared_free = smem_u32(&bars[23]), all_free = smem_u32(&bars[24]);
+  const uint32_t u8_full = smem_u32(&bars[26]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (Cfg::U8IN && tid < 256) {
+    // byte -> fp32 channel value with the reference's arithmetic (.float().div(255), then (x - 0.5) / 0.5 for channels 0..2:
+    // dataloader.py:25-36, 405-411), split into fp16 hi + lo exactly as pack_nchw_kernel / assemble_pack_kernel do
+    const float f = __fdiv_rn((float)tid, 255.f);
+    const float c = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
+    uint32_t h, l;
+    split2(f, c, h, l);                      // h = (hi(f), hi(c)), l = (lo(f), lo(c))
+    u8_tab[tid] = (h & 0xffffu) | (l << 16);
+    u8_tab[256 + tid] = (h >> 16) | (l & 0xffff0000u);
+  }
 
   if (tid < 64) bias_s[tid] = args.bias[tid];
   if (tid == 0) {
@@ -331,6 +359,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     mbar_init(shared_free, kEpiThreads);
     mbar_init(all_free, kEpiThreads);
     mbar_init(all_free + 8, kEpiThreads);
+    mbar_init(u8_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_hi);
     tma_prefetch_desc(&tmap_lo);
@@ -344,7 +373,81 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   // phases per unit: (lo | hi) x NK channel slices, or for S8 (x_lo8 | x8) x byte slices then NK fp16 slices
   const int nph = Cfg::S8 ? Cfg::NPH : (args.split ? 2 * NK : NK);
 
-  if (warp == 0) {
+  if (Cfg::U8IN && (warp == 0 || warp == 3)) {
+    // ===== A producer on the uint8 interface (64 threads): stage the group's eight stored matrices with one bulk copy, then
+    // build every phase's operand tile in shared memory: row r = (image row, box column, candidate) holds channels 0..31 =
+    // 23 stored channels, the centre marker, the two coverage channels and zeros (dataloader.py:383-411), fp16 hi or lo part,
+    // in the swizzle-64B K-major image the TMA box of the packed path would have produced (columns outside the image: zeros)
+    const int pt = (warp == 0 ? 0 : 32) + lane;
+    uint32_t it = 0, g_it = 0;
+    for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x, ++g_it) {
+      const int n_valid = min(8, args.B - grp * 8);
+      if (pt == 0) {
+        mbar_arrive_expect_tx(u8_full, (uint32_t)(n_valid * kU8CandBytes));
+        bulk_g2s(smem_u32(u8_stage), args.u8_mat + (size_t)grp * kU8StageBytes, (uint32_t)(n_valid * kU8CandBytes), u8_full);
+      }
+      if (pt < 8) {
+        const bool valid = pt < n_valid;
+        const int64_t bb = (int64_t)grp * 8 + pt;
+        u8_center[pt] = valid ? args.u8_meta[bb * 3 + 0] : -1;
+#pragma unroll
+        for (int k = 1; k <= 2; ++k) {
+          const float f = valid ? __fdiv_rn((float)(fmin((double)args.u8_meta[bb * 3 + k], args.u8_thr) / args.u8_thr * 255.0), 255.f) : 0.f;
+          uint32_t h, l;
+          split2(f, 0.f, h, l);
+          u8_cst[pt][k] = (h & 0xffffu) | (l << 16);
+        }
+      }
+      mbar_wait(u8_full, g_it & 1);
+      {
+        // np.max(matrix[:, :, 0]) per candidate (dataloader.py:390): 8 threads per candidate
+        const int g = pt >> 3, l8 = pt & 7;
+        int v = 0;
+        if (g < n_valid)
+          for (int p = l8; p < kH * kW; p += 8) v = max(v, (int)u8_stage[g * kU8CandBytes + p * kStoredCh]);
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, 1));
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        if (l8 == 0) {
+          uint32_t h, l;
+          split2(g < n_valid ? __fdiv_rn((float)v, 255.f) : 0.f, 0.f, h, l);
+          u8_cst[g][0] = (h & 0xffffu) | (l << 16);
+        }
+      }
+      asm volatile("bar.sync 2, 64;" ::: "memory");
+      for (int sub = 0; sub < Cfg::SUBS; ++sub)
+        for (int ph = 0; ph < nph; ++ph, ++it) {
+          const uint32_t buf = it % Cfg::NA;
+          if (it >= Cfg::NA) mbar_wait(a_empty + 8 * buf, ((it / Cfg::NA) - 1) & 1);
+          const int sh = (args.split && ph < NK) ? 16 : 0;          // which half of a table entry: lo part or hi part
+          uint8_t* dst = a_buf + buf * Cfg::A_BYTES;
+          for (int r = pt; r < kH * Cfg::WB * 8; r += 64) {
+            const int g = r & 7, cl = (r >> 3) % Cfg::WB, h = r / (8 * Cfg::WB);
+            const int col = sub * Cfg::TW - Cfg::HALO + cl;
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = 0u;
+            if (col >= 0 && col < W && g < n_valid) {
+              const uint8_t* px = u8_stage + g * kU8CandBytes + (h * kW + col) * kStoredCh;
+              uint32_t e[24];
+#pragma unroll
+              for (int c = 0; c < kStoredCh; ++c) e[c] = (u8_tab[(c < 3 ? 256 : 0) + px[c]] >> sh) & 0xffffu;
+              e[23] = (col == u8_center[g]) ? ((u8_cst[g][0] >> sh) & 0xffffu) : 0u;
+#pragma unroll
+              for (int j = 0; j < 12; ++j) w[j] = e[2 * j] | (e[2 * j + 1] << 16);
+              w[12] = ((u8_cst[g][1] >> sh) & 0xffffu) | (((u8_cst[g][2] >> sh) & 0xffffu) << 16);
+            }
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16)
+              *reinterpret_cast<uint4*>(dst + swz_offset<64>((uint32_t)r, (uint32_t)c16)) =
+                  make_uint4(w[4 * c16], w[4 * c16 + 1], w[4 * c16 + 2], w[4 * c16 + 3]);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 2, 64;" ::: "memory");
+          if (pt == 0) mbar_arrive(a_full + 8 * buf);
+        }
+    }
+  } else if (warp == 0) {
     // ===== A producer: one TMA box per phase =====
     if (elect_one()) {
       uint32_t it = 0;
@@ -1163,6 +1266,9 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
   a.relu = relu;
   a.split = m->precision == NSC_PREC_BF16 ? 0 : 1;
   a.stats = nullptr;
+  a.u8_mat = Cfg::U8IN ? m->umma.u8_mat : nullptr;
+  a.u8_meta = Cfg::U8IN ? m->umma.u8_meta : nullptr;
+  a.u8_thr = m->umma.u8_thr;
   static const int dbg_skip = getenv("NSC_UMMA_SKIP") ? atoi(getenv("NSC_UMMA_SKIP")) : 0;
   a.dbg_skip = dbg_skip;
   if ((dbg_skip & 32) && !Cfg::TMAOUT) { a.out_lo = nullptr; a.out_c8 = nullptr; }   // timing experiment: 2 instead of 6 bytes stored per element
@@ -1245,6 +1351,17 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
   int rc;
   if ((rc = umma_ensure_workspace(m, n)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
+  static const bool no_fused = getenv("NSC_NO_FUSED_STEM") != nullptr;
+  if (u.nk1 == 1 && m->C == kBaseCh && !m->normalize_channels && !no_fused) {
+    // standalone network: the stem reads the stored matrices itself (no packed input in HBM, no separate assembly launch)
+    u.u8_mat = mat;
+    u.u8_meta = meta;
+    u.u8_thr = (double)coverage_thr;
+    rc = umma_run(m, n, o, s);
+    u.u8_mat = nullptr;
+    u.u8_meta = nullptr;
+    return rc;
+  }
   if ((rc = assemble_pack(m, mat, meta, anns255, coverage_thr, n, u.xin[0], u.xin[1], u.nk1 * 32, s)) != NSC_OK) return rc;
   return umma_run(m, n, o, s);
 }
@@ -1277,7 +1394,9 @@ static int umma_run_mask(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t
   auto fmt_mid = [&](int l) { return ((s8 >> l) & 1u) ? kOutC8 : kOutLo; };                      // consumer: conv l only
   uint16_t** const none = nullptr;
   // conv1 + BN + ReLU + pool1 (network.py:44-47,67): split-fp16 in every tensor mode (its input is the packed hi/lo image)
-  if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
+  if (u.nk1 == 1 && u.u8_mat != nullptr)      // uint8 interface: channel assembly + split inside the stem's producer warps
+    NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false, 32, 1, false, true>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
+  else if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   NSC_RUN(dbg_unpack(m, 0, X, 32, n, s));

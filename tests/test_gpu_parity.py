@@ -359,16 +359,20 @@ def test_large_batch_crosses_default_chunk(precision):
     eng.close()
 
 
-def test_default_mode_is_split8_with_fp16_fallback_for_large_weights():
-    """The library default is NSC_PREC_SPLIT8; a checkpoint whose folded weights leave the range of the fp8 correction
-    terms (|w| > 28) silently gets NSC_PREC_SPLIT16, and an explicit request for SPLIT8 on it fails loudly."""
+def test_default_mode_is_split16_and_fast_mode_rejects_large_weights():
+    """The library default is NSC_PREC_SPLIT16 (round-toward-zero compensated); the opt-in fast mode NSC_PREC_SPLIT8 fails
+    loudly on a checkpoint whose folded weights leave the range of its fp8 correction terms (|w| > 28)."""
     from neusomatic_b200 import Engine
     from neusomatic_b200._lib import NscError
     cand = synth.structured_pileups(64, seed=3)
     x = oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)
     sd = synth.random_state_dict(26, seed=2)
     eng = Engine(sd, 26)
+    assert eng.precision == 0
+    eng.close()
+    eng = Engine(sd, 26, precision=3)
     assert eng.precision == 3
+    eng.forward_f32(torch.from_numpy(x).cuda())
     eng.close()
     big = {k: np.array(v, copy=True) for k, v in sd.items()}
     big["res_layers.1.conv_r2.weight"][3, 5, 2, 2] = 300.0
