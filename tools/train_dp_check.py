@@ -1,11 +1,13 @@
 """2+ GPU check of the data-parallel train step (run under torchrun on the GPU box):
-every rank runs nsc_train_forward_backward on its own shard, the flat gradient vector is summed with ONE NCCL
-all-reduce, nsc_sgd_momentum_update applies 1/world.  Checks: (1) all ranks end with identical parameters,
-(2) they equal a single-process update with the average of the per-shard gradients, and prints step throughput."""
+every rank runs nsc_train_forward_backward on its own shard with the loss normalised by the GLOBAL class-weight sums /
+batch size (3 floats all-reduced up front: the reference's nn.DataParallel computes one loss over the gathered batch,
+train.py:436-441), the flat gradient vector is summed with ONE NCCL all-reduce, nsc_sgd_momentum_update applies it.
+Checks: (1) all ranks end with identical parameters, (2) they equal a single-process update with the sum of the per-shard
+gradients of the global loss, (3) the per-rank losses sum to the global loss; prints step throughput."""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from neusomatic_b200 import synth
+from neusomatic_b200 import synth, _lib
 from neusomatic_b200.train import Trainer
 from oracle import nsnet_oracle as oracle
 
@@ -26,24 +28,30 @@ def shard(r):
 w1 = torch.tensor([0.2, 0.21, 0.13, 0.16], device=dev); w3 = torch.tensor([0.12, 0.2, 0.23, 0.24], device=dev)
 tr = Trainer(sd, 26, device=lr_, max_batch=B)
 x, vt, ce, ln = shard(rank)
-tr.step(x, vt, ce, ln, w1, w3)
+losses = tr.step(x, vt, ce, ln, w1, w3).clone()
 torch.cuda.synchronize()
+loss_sum = losses.clone(); dist.all_reduce(loss_sum)
 # (1) identical parameters on every rank
 ref = tr.params.clone(); dist.broadcast(ref, 0)
 assert torch.equal(ref, tr.params), "ranks diverged"
-# (2) equals the average of the per-shard gradients (recomputed locally on rank 0)
+# (2) equals the sum of the per-shard gradients of the global loss (recomputed locally on rank 0)
 if rank == 0:
-    gsum = None
+    shards = [shard(r) for r in range(world)]
+    norm = torch.stack([sum(w1[s[1].long()].sum() for s in shards), sum(w3[s[3].long()].sum() for s in shards),
+                        torch.tensor(float(world * B), device=dev)]).float()
+    gsum, lsum = None, 0.0
     for r in range(world):
         t2 = Trainer(sd, 26, device=lr_, max_batch=B)
-        t2.forward_backward(*shard(r), w1, w3)
+        _lib.check(t2.lib.nsc_trainer_set_loss_norm(t2.h, norm.data_ptr()))
+        lsum = lsum + t2.forward_backward(*shards[r], w1, w3).clone()
         gsum = t2.grads.clone() if gsum is None else gsum + t2.grads
         t2.close()
     t3 = Trainer(sd, 26, device=lr_, max_batch=B)
-    expect = t3.params - 0.01 * (gsum / world)
+    expect = t3.params - 0.01 * gsum
     err = (expect - tr.params).abs().max().item()
-    print("max |param - expected| after the data-parallel step: %.3e" % err)
-    assert err < 1e-6
+    print("max |param - expected| after the data-parallel step: %.3e; global loss %.6f (sum of rank losses %.6f)" % (
+        err, float(lsum[0]), float(loss_sum[0])))
+    assert err < 1e-6 and abs(float(lsum[0]) - float(loss_sum[0])) < 1e-5 * abs(float(lsum[0]))
 # throughput
 for _ in range(3):
     tr.step(x, vt, ce, ln, w1, w3)
