@@ -301,7 +301,7 @@ def measure_scoring(args, rk, local_rank, ensemble, B, steps, with_f32_host=True
     l0 = eng.launch_count
     if sampler:
         sampler.start()
-    ms, regions, per_rank = timed_regions(rk, lambda: eng.forward_f32(x_d, extras=True), steps, 0)
+    ms, regions, per_rank = timed_regions(rk, lambda: eng.forward_f32(x_d, extras=True), steps, 0, min_ms=args.min_timed_ms)
     out["clocks"] = sampler.stop() if sampler else None
     out.update(ms=ms, region_ms=regions, ms_per_rank=per_rank, value=rk.world * B * steps / (ms / 1000.0))
     out["launches"] = (eng.launch_count - l0) // len(regions)          # launches of ONE K-step region
@@ -556,6 +556,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--min-timed-ms", type=float, default=MIN_TIMED_MS, help="repeat the K-step region until this much is timed "
+                    "(0 = one region: profiling runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra records (ensemble, train, gpu_incumbent, e2e_tsv)")
     ap.add_argument("--train", action="store_true", help="BASELINE configs[4] as the line's own metric")
     ap.add_argument("--ensemble", action="store_true", help="BASELINE configs[3] as the line's own metric (C=119)")
@@ -640,7 +642,7 @@ def main():
                        "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
                        "sharding": "contiguous candidate ranges per rank, no collective on the data path",
                        "timing": "median of %d regions of %d steps (>= %.0f ms timed), max over ranks per region" % (
-                           len(m["region_ms"]), args.steps, MIN_TIMED_MS)},
+                           len(m["region_ms"]), args.steps, args.min_timed_ms)},
             "region_ms": [round(v, 3) for v in m["region_ms"]], "ms_per_rank": [round(v, 3) for v in m["ms_per_rank"]],
             "e2e": m.get("e2e"), "e2e_f32": m.get("e2e_f32"), "gpu_launches": m.get("launches"), "roofline": roof,
             "cpu_baseline": cpu, "clocks": m["clocks"], "extra": extra,

@@ -1,12 +1,14 @@
 #!/usr/bin/env python
-"""Turns gpurun_out/{r1_launches.csv, r1_conv_umma.ncu-rep, r1_plain.log} into the tracked summaries under profiles/."""
+"""Turns gpurun_out/{<tag>_launches.csv, <tag>_conv_umma.ncu-rep} into the tracked summaries under profiles/.
+usage: tools/make_profiles.py [tag] [command line that was profiled]"""
 import collections, csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles"); os.makedirs(P, exist_ok=True)
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+cmdline = sys.argv[2] if len(sys.argv) > 2 else "python bench.py --steps 2 --warmup 3 --batch 32768 --no-cpu-baseline --no-e2e"
 
 # 1. launch list: per-kernel totals and shares
-rows = list(csv.DictReader(l for l in open(os.path.join(G, "r1_launches.csv")) if l.startswith('"')))
+rows = list(csv.DictReader(l for l in open(os.path.join(G, tag + "_launches.csv")) if l.startswith('"')))
 agg = collections.OrderedDict()
 for r in rows:
     k = r["Kernel Name"].split("(")[0]
@@ -14,17 +16,17 @@ for r in rows:
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(P, tag + "_launches_summary.md"), "w") as f:
     f.write("# ncu launch list (%s): `ncu --metrics gpu__time_duration.sum --clock-control none` over\n" % tag)
-    f.write("`python bench.py --steps 2 --warmup 3 --batch 32768 --no-cpu-baseline --no-e2e` (first 200 launches; cold-cache,\nserialised: compare SHARES with bench.py's live per-kernel times, not absolutes)\n\n")
+    f.write("`%s` (cold-cache,\nserialised: compare SHARES with bench.py's live per-kernel times, not absolutes)\n\n" % cmdline)
     f.write("| kernel | launches | grid | block | total us | share |\n|---|---|---|---|---|---|\n")
     for k, v in agg.items():
         f.write("| `%s` | %d | %s | %s | %.1f | %.3f |\n" % (k, v[0], v[2], v[3], v[1], v[1] / tot))
     conv = sum(v[1] for k, v in agg.items() if "conv_umma_kernel" in k and "<1, 3" not in k)
     f.write("\nshare of the eight 64->64 convolution launches (the `roofline` kernel family): %.3f\n" % (conv / tot))
 import shutil
-shutil.copy(os.path.join(G, "r1_launches.csv"), os.path.join(P, tag + "_launches.csv"))
+shutil.copy(os.path.join(G, tag + "_launches.csv"), os.path.join(P, tag + "_launches.csv"))
 
 # 2. full capture: selected metrics per profiled launch
-out = subprocess.run(["ncu", "-i", os.path.join(G, "r1_conv_umma.ncu-rep"), "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+out = subprocess.run(["ncu", "-i", os.path.join(G, tag + "_conv_umma.ncu-rep"), "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rr = list(csv.reader(out.splitlines())); hdr, units, data = rr[0], rr[1], rr[2:]
 want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
