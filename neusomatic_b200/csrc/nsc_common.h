@@ -92,6 +92,10 @@ struct Fp32Weights {
 struct UmmaState {
   uint8_t* w1pk = nullptr;              // fc1: [2][20] tiles of [240][64] fp16, swizzle-128B (nsc_fc_umma.cu)
   uint8_t* wpk1 = nullptr;              // conv1: swizzled fp16 hi/lo weight stages (nsc_umma.cu)
+  uint8_t* wpk1_u8 = nullptr;           // conv1 of the ensemble network on the uint8 interface: the 26 position-dependent channels only
+  float* ann_w = nullptr;               // [3][C-26][64] tap-summed conv1 weights of the annotation channels (ann_bias_kernel)
+  float* ann_bias = nullptr;            // [cap][3][64] per-candidate contribution of the annotation channels
+  int64_t ann_bias_cap = 0;
   uint8_t* wpk[4][2] = {};              // res_layers[i].conv_r{1,2}
   uint8_t* wpk8[4][2] = {};             // the same layers for NSC_PREC_SPLIT8 (fp8 correction stages + fp16 stages)
   int nk1 = 1;                          // 32-channel input slices of conv1 (C = 26 -> 1, C = 119 -> 4)

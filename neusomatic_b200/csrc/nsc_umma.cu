@@ -174,6 +174,7 @@ struct UmmaConvArgs {
   const uint8_t* u8_mat;     // U8IN: stored candidate matrices uint8 [B][5][32][23]
   const int32_t* u8_meta;    // U8IN: [B][3] = (center, tumor_cov, normal_cov)
   double u8_thr;             // U8IN: coverage_thr of the checkpoint
+  const float* ann_bias;     // U8IN, ensemble network: [B][3][64] contribution of the annotation channels (ann_bias_kernel) or nullptr
   long long* stats;          // optional [grid][8] cycle counters (NSC_UMMA_STATS=1)
   int dbg_skip;              // timing experiments only (NSC_UMMA_SKIP): 1 = no fp8 MMAs, 2 = no fp16 MMAs, 4 = no epilogue body,
                              // 8 / 16 = no A / weight loads, 32 = pooled layers store only the fp16 hi part
@@ -333,6 +334,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2 + 1];
   __shared__ uint32_t u8_cst[8][4];     // per candidate: packed hi|lo of the centre marker value, tumor coverage, normal coverage
   __shared__ int u8_center[8];
+  // U8IN, ensemble network: the annotation channels' contribution for the unit's 8 candidates x {border column, interior}
+  __shared__ __align__(16) float ann_s[Cfg::U8IN ? 16 : 1][Cfg::U8IN ? 68 : 1];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[64];
   const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[3]);
@@ -415,37 +418,51 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
       }
       asm volatile("bar.sync 2, 64;" ::: "memory");
-      for (int sub = 0; sub < Cfg::SUBS; ++sub)
-        for (int ph = 0; ph < nph; ++ph, ++it) {
-          const uint32_t buf = it % Cfg::NA;
-          if (it >= Cfg::NA) mbar_wait(a_empty + 8 * buf, ((it / Cfg::NA) - 1) & 1);
-          const int sh = (args.split && ph < NK) ? 16 : 0;          // which half of a table entry: lo part or hi part
-          uint8_t* dst = a_buf + buf * Cfg::A_BYTES;
-          for (int r = pt; r < kH * Cfg::WB * 8; r += 64) {
-            const int g = r & 7, cl = (r >> 3) % Cfg::WB, h = r / (8 * Cfg::WB);
-            const int col = sub * Cfg::TW - Cfg::HALO + cl;
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = 0u;
-            if (col >= 0 && col < W && g < n_valid) {
-              const uint8_t* px = u8_stage + g * kU8CandBytes + (h * kW + col) * kStoredCh;
-              uint32_t e[24];
-#pragma unroll
-              for (int c = 0; c < kStoredCh; ++c) e[c] = (u8_tab[(c < 3 ? 256 : 0) + px[c]] >> sh) & 0xffffu;
-              e[23] = (col == u8_center[g]) ? ((u8_cst[g][0] >> sh) & 0xffffu) : 0u;
-#pragma unroll
-              for (int j = 0; j < 12; ++j) w[j] = e[2 * j] | (e[2 * j + 1] << 16);
-              w[12] = ((u8_cst[g][1] >> sh) & 0xffffu) | (((u8_cst[g][2] >> sh) & 0xffffu) << 16);
-            }
-#pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16)
-              *reinterpret_cast<uint4*>(dst + swz_offset<64>((uint32_t)r, (uint32_t)c16)) =
-                  make_uint4(w[4 * c16], w[4 * c16 + 1], w[4 * c16 + 2], w[4 * c16 + 3]);
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 2, 64;" ::: "memory");
-          if (pt == 0) mbar_arrive(a_full + 8 * buf);
+      // one pass over the staged bytes per unit fills BOTH phase buffers (lo part -> the first phase's buffer, hi part -> the
+      // second's; single-pass arithmetic has one phase): a table entry carries both halves, so the byte and table loads are
+      // not repeated per phase.  The stem's MMA work is a fifth of its epilogue, so waiting for both buffers costs nothing.
+      static_assert(Cfg::NA >= 2, "the uint8 producer fills the two phase buffers of a unit together");
+      for (int sub = 0; sub < Cfg::SUBS; ++sub, it += nph) {
+        for (int ph = 0; ph < nph; ++ph) {
+          const uint32_t i2 = it + ph;
+          if (i2 >= Cfg::NA) mbar_wait(a_empty + 8 * (i2 % Cfg::NA), ((i2 / Cfg::NA) - 1) & 1);
         }
+        // split: phase 0 = lo, phase 1 = hi; single pass: phase 0 = hi
+        uint8_t* dst_hi = a_buf + ((it + nph - 1) % Cfg::NA) * Cfg::A_BYTES;
+        uint8_t* dst_lo = a_buf + (it % Cfg::NA) * Cfg::A_BYTES;
+        const bool want_lo = nph == 2;
+        for (int r = pt; r < kH * Cfg::WB * 8; r += 64) {
+          const int g = r & 7, cl = (r >> 3) % Cfg::WB, h = r / (8 * Cfg::WB);
+          const int col = sub * Cfg::TW - Cfg::HALO + cl;
+          uint32_t wh[16], wl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { wh[j] = 0u; wl[j] = 0u; }
+          if (col >= 0 && col < W && g < n_valid) {
+            const uint8_t* px = u8_stage + g * kU8CandBytes + (h * kW + col) * kStoredCh;
+            uint32_t e[24];
+#pragma unroll
+            for (int c = 0; c < kStoredCh; ++c) e[c] = u8_tab[(c < 3 ? 256 : 0) + px[c]];
+            e[23] = (col == u8_center[g]) ? u8_cst[g][0] : 0u;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+              wh[j] = __byte_perm(e[2 * j], e[2 * j + 1], 0x5410);      // (hi of channel 2j, hi of channel 2j + 1)
+              wl[j] = __byte_perm(e[2 * j], e[2 * j + 1], 0x7632);      // (lo, lo)
+            }
+            wh[12] = __byte_perm(u8_cst[g][1], u8_cst[g][2], 0x5410);
+            wl[12] = __byte_perm(u8_cst[g][1], u8_cst[g][2], 0x7632);
+          }
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            const uint32_t off = swz_offset<64>((uint32_t)r, (uint32_t)c16);
+            *reinterpret_cast<uint4*>(dst_hi + off) = make_uint4(wh[4 * c16], wh[4 * c16 + 1], wh[4 * c16 + 2], wh[4 * c16 + 3]);
+            if (want_lo) *reinterpret_cast<uint4*>(dst_lo + off) = make_uint4(wl[4 * c16], wl[4 * c16 + 1], wl[4 * c16 + 2], wl[4 * c16 + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 64;" ::: "memory");
+        if (pt == 0)
+          for (int ph = 0; ph < nph; ++ph) mbar_arrive(a_full + 8 * ((it + ph) % Cfg::NA));
+      }
     }
   } else if (warp == 0) {
     // ===== A producer: one TMA box per phase =====
@@ -670,6 +687,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           else if (!SLIDE) load_res(grp, sub, u_it, 0);
         }
         if (Cfg::NCHW && args.res_nchw != nullptr) load_res_nchw(grp, sub, u_it, 0);
+        if (Cfg::U8IN && args.ann_bias != nullptr) {
+          // rows 0..7: the unit's border column (column 0 of the first block, column 31 of the second: one kernel tap falls
+          // into the zero padding there), rows 8..15: every other column; the previous unit's readers are behind an epi_bar
+          const int i = et >> 4, q4 = (et & 15) * 4, g = i & 7;
+          const int cls = (i < 8) ? (sub == 0 ? 0 : 2) : 1;
+          const int64_t bb = (int64_t)grp * 8 + g;
+          const float4 v = bb < args.B ? __ldg(reinterpret_cast<const float4*>(args.ann_bias + (bb * 3 + cls) * 64 + q4))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(&ann_s[i][q4]) = v;
+          epi_bar();
+        }
         long long t_c = clock64();
         mbar_wait(acc_full, u_it & 1);
         t_full += clock64() - t_c;
@@ -757,6 +785,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             for (int c = 0; c < kCPT / 4; ++c) {
               float4 v = Cfg::NCHW ? make_float4(0.f, 0.f, 0.f, 0.f)    // training: bias follows the output scale
                                    : *reinterpret_cast<const float4*>(bias_s + part * kCPT + c * 4);   // broadcast read
+              if (Cfg::U8IN && args.ann_bias != nullptr) {
+                const int colu = row >> 3;                      // column of this thread's row inside the unit
+                const bool border = (sub == 0) ? (colu == 0) : (colu == Cfg::TW - 1);
+                const float4 ab = *reinterpret_cast<const float4*>(&ann_s[(border ? 0 : 8) + (row & 7)][part * kCPT + c * 4]);
+                v.x += ab.x; v.y += ab.y; v.z += ab.z; v.w += ab.w;
+              }
               v.x += __uint_as_float(r[c * 4 + 0]);
               v.y += __uint_as_float(r[c * 4 + 1]);
               v.z += __uint_as_float(r[c * 4 + 2]);
@@ -956,6 +990,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// The ensemble network's annotation channels on the uint8 interface.  Channels 26.. of a candidate are constant over the
+// 5 x 32 positions (dataloader.py:395-396: matrix[:, :, 26 + i] = a * 255.0), so their share of conv1 (1 x 3, zero padded in
+// W) is a per-candidate vector per output channel -- one for column 0 (the tap at -1 is padding), one for column 31, one for
+// every column between:      out[b][cls][co] = sum_a  fl(anns255[b][a] / 255) * wsum[cls][a][co],
+// wsum = the BN-folded conv1 weights of channel 26 + a summed over the taps inside the image.  93 x 3 MACs per output instead
+// of 96 more input channels through the packed operand (82 KB -> 20 KB of stem input per candidate, no assembly launch).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192)
+ann_bias_kernel(const float* __restrict__ anns255, const float* __restrict__ wsum, float* __restrict__ out, int na, int B) {
+  __shared__ float f[4][128];
+  const int b0 = blockIdx.x * 4;
+  for (int i = threadIdx.x; i < 4 * na; i += 192) {
+    const int j = i / na, a = i - j * na;
+    f[j][a] = (b0 + j < B) ? __fdiv_rn(anns255[(size_t)(b0 + j) * na + a], 255.f) : 0.f;      // .float().div(255)
+  }
+  __syncthreads();
+  const int cls = threadIdx.x >> 6, co = threadIdx.x & 63;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* w = wsum + (size_t)cls * na * 64 + co;
+  for (int a = 0; a < na; ++a) {
+    const float wv = __ldg(w + (size_t)a * 64);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(f[j][a], wv, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (b0 + j < B) out[((size_t)(b0 + j) * 3 + cls) * 64 + co] = acc[j];
+}
+
+// ---------------------------------------------------------------------------------------------
 // layout conversion kernels around the UMMA convolutions
 // ---------------------------------------------------------------------------------------------
 // fp32 NCHW [B,C,5,32] -> packed hi/lo [groups][5][32][8][Cpad] (channels >= C zero); block = (group, h, 32-channel slice)
@@ -1140,6 +1204,30 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
   if ((rc = fold_conv_bn(m, "conv1", "bn1", bn_eps, &f)) != NSC_OK) return rc;
   u.nk1 = (m->C + 31) / 32;
   if (u.nk1 == 3) u.nk1 = 4;
+  if (m->C > kBaseCh) {
+    // uint8 interface of the ensemble network: the tensor part covers the 26 position-dependent channels (their own
+    // 6-step chains), the annotation channels go through ann_bias_kernel (fp32 FMA: no accumulator shrink to compensate)
+    const int na = m->C - kBaseCh;
+    std::vector<float> wsum((size_t)3 * na * 64);
+    for (int co = 0; co < 64; ++co)
+      for (int a = 0; a < na; ++a) {
+        const float* t = &f.w[((size_t)co * m->C + kBaseCh + a) * 3];
+        wsum[((size_t)0 * na + a) * 64 + co] = (float)((double)t[1] + (double)t[2]);                    // column 0: taps 0, +1
+        wsum[((size_t)1 * na + a) * 64 + co] = (float)((double)t[0] + (double)t[1] + (double)t[2]);     // interior
+        wsum[((size_t)2 * na + a) * 64 + co] = (float)((double)t[0] + (double)t[1]);                    // column 31: taps -1, 0
+      }
+    cudaFree(u.ann_w);
+    u.ann_w = nullptr;
+    NSC_CUDA_TRY(cudaMalloc((void**)&u.ann_w, wsum.size() * sizeof(float)));
+    NSC_CUDA_TRY(cudaMemcpy(u.ann_w, wsum.data(), wsum.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> w26((size_t)64 * kBaseCh * 3);
+    for (int co = 0; co < 64; ++co)
+      for (int c = 0; c < kBaseCh; ++c)
+        for (int dx = 0; dx < 3; ++dx) w26[((size_t)co * kBaseCh + c) * 3 + dx] = f.w[((size_t)co * m->C + c) * 3 + dx];
+    scale_weights(w26, rz_compensation(3 * 2, 1.0));
+    float dummy = 0.f;
+    if ((rc = upload_bytes(&u.wpk1_u8, pack_conv_weights(w26, kBaseCh, 1, 3, 1, 32, &dummy))) != NSC_OK) return rc;
+  }
   scale_weights(f.w, rz_compensation(3 * 2 * u.nk1, 1.0));
   if ((rc = upload_bytes(&u.wpk1, pack_conv_weights(f.w, m->C, 1, 3, u.nk1, 32, &max_abs))) != NSC_OK) return rc;
   for (int i = 0; i < 4; ++i)
@@ -1173,6 +1261,10 @@ int umma_upload_weights(nsc_model* m, float bn_eps) {
 void umma_free(nsc_model* m) {
   UmmaState& u = m->umma;
   cudaFree(u.wpk1); u.wpk1 = nullptr;
+  cudaFree(u.wpk1_u8); u.wpk1_u8 = nullptr;
+  cudaFree(u.ann_w); u.ann_w = nullptr;
+  cudaFree(u.ann_bias); u.ann_bias = nullptr;
+  u.ann_bias_cap = 0;
   cudaFree(u.w1pk); u.w1pk = nullptr;
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j) { cudaFree(u.wpk[i][j]); u.wpk[i][j] = nullptr; cudaFree(u.wpk8[i][j]); u.wpk8[i][j] = nullptr; }
@@ -1269,6 +1361,7 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
   a.u8_mat = Cfg::U8IN ? m->umma.u8_mat : nullptr;
   a.u8_meta = Cfg::U8IN ? m->umma.u8_meta : nullptr;
   a.u8_thr = m->umma.u8_thr;
+  a.ann_bias = (Cfg::U8IN && m->C > kBaseCh) ? m->umma.ann_bias : nullptr;
   static const int dbg_skip = getenv("NSC_UMMA_SKIP") ? atoi(getenv("NSC_UMMA_SKIP")) : 0;
   a.dbg_skip = dbg_skip;
   if ((dbg_skip & 32) && !Cfg::TMAOUT) { a.out_lo = nullptr; a.out_c8 = nullptr; }   // timing experiment: 2 instead of 6 bytes stored per element
@@ -1352,8 +1445,23 @@ int umma_forward_chunk_u8(nsc_model* m, const uint8_t* mat, const int32_t* meta,
   if ((rc = umma_ensure_workspace(m, n)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
   static const bool no_fused = getenv("NSC_NO_FUSED_STEM") != nullptr;
-  if (u.nk1 == 1 && m->C == kBaseCh && !m->normalize_channels && !no_fused) {
-    // standalone network: the stem reads the stored matrices itself (no packed input in HBM, no separate assembly launch)
+  if (m->C >= kBaseCh && !m->normalize_channels && !no_fused) {
+    // the stem reads the stored matrices itself (no packed input in HBM, no separate assembly launch); the ensemble network's
+    // annotation channels become a per-candidate bias first
+    if (m->C > kBaseCh) {
+      if (u.ann_bias_cap < n) {
+        NSC_CUDA_TRY(cudaStreamSynchronize(s));
+        cudaFree(u.ann_bias);
+        u.ann_bias = nullptr;
+        u.ann_bias_cap = 0;
+        NSC_CUDA_TRY(cudaMalloc((void**)&u.ann_bias, (size_t)u.cap * 3 * 64 * sizeof(float)));
+        u.ann_bias_cap = u.cap;
+      }
+      ProfScope prof(m, 0, s);
+      ann_bias_kernel<<<(unsigned)((n + 3) / 4), 192, 0, s>>>(anns255, u.ann_w, u.ann_bias, m->C - kBaseCh, (int)n);
+      NSC_CUDA_TRY(cudaGetLastError());
+      m->launches++;
+    }
     u.u8_mat = mat;
     u.u8_meta = meta;
     u.u8_thr = (double)coverage_thr;
@@ -1394,8 +1502,9 @@ static int umma_run_mask(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t
   auto fmt_mid = [&](int l) { return ((s8 >> l) & 1u) ? kOutC8 : kOutLo; };                      // consumer: conv l only
   uint16_t** const none = nullptr;
   // conv1 + BN + ReLU + pool1 (network.py:44-47,67): split-fp16 in every tensor mode (its input is the packed hi/lo image)
-  if (u.nk1 == 1 && u.u8_mat != nullptr)      // uint8 interface: channel assembly + split inside the stem's producer warps
-    NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false, 32, 1, false, true>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
+  if (u.u8_mat != nullptr)      // uint8 interface: channel assembly + split inside the stem's producer warps
+    NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false, 32, 1, false, true>>(m, 1, u.xin, m->C > kBaseCh ? u.wpk1_u8 : u.wpk1, w.conv1_b, X,
+                                                                                     nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 4, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));

@@ -113,9 +113,23 @@ def test_u8_and_host_paths_agree_with_f32_path(golden, precision):
                          None if a255 is None else torch.from_numpy(a255).cuda(), float(ck["coverage_thr"]))
     host_u8 = eng.score_host_u8(g["matrices"], meta, a255, float(ck["coverage_thr"]))
     host_f32 = eng.score_host_f32(x)
-    for other in (dev, host_u8, host_f32):
-        for a, b in zip(ref, other):
+    for a, b in zip(ref, host_f32):
+        np.testing.assert_array_equal(a, b.cpu().numpy())
+    for a, b in zip(dev, host_u8):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    if C == 26 or precision == 2:
+        # standalone network (and the CUDA-core mode): the uint8 interface is the same arithmetic, bit for bit
+        for a, b in zip(ref, dev):
             np.testing.assert_array_equal(a, b.cpu().numpy())
+    else:
+        # ensemble network on the tensor path: the 93 annotation channels are constant over a candidate's positions, and the
+        # uint8 interface adds their share of conv1 as a per-candidate fp32 vector (ann_bias_kernel) instead of running them
+        # through the operand -- same value, different summation order: fp32 noise, far inside the parity bar
+        o = [t.cpu().numpy() for t in dev]
+        assert max(np.abs(o[0] - ref[0]).max(), np.abs(o[2] - ref[2]).max()) <= 3e-4
+        assert np.abs(o[1] - ref[1]).max() <= 1e-4 and max(np.abs(o[3] - ref[3]).max(), np.abs(o[4] - ref[4]).max()) <= 5e-5
+        assert (o[5] == ref[5]).all() and (o[6] == ref[6]).all()
+        _check_outputs(o[0], o[1], o[2], g["o1"], g["o2"], g["o3"], o[3], o[4], o[5], o[6])
     eng.close()
 
 
