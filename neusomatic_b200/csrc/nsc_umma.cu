@@ -109,7 +109,7 @@ struct ConvCfg {
   // [128 rows][128 B] swizzle-128B tiles (x16 and c8 / lo16): no item phase, no LSU stores
   static constexpr bool TMAOUT = (POOL == 0) && (GP == 1) && (TW == 16) && !NCHW;
   static constexpr size_t SMEM = 1024 + NA * (size_t)A_BYTES + (size_t)WS * W_STAGE_BYTES + kStageBytes +
-                                 (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + (U8IN ? kU8StageBytes + 2048 : 0) + 256;
+                                 (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + (U8IN ? kU8StageBytes + 64 : 0) + 256;
   static_assert(SMEM <= 232448 - 1024, "shared memory budget");
   static_assert(!U8IN || (KH == 1 && NK == 1 && KC == 32 && GP == 1 && W == 32), "the uint8 producer builds the stem's 26 -> 32 channel operand");
 };
@@ -327,10 +327,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   uint8_t* st_hi = w_buf + WS * Cfg::W_STAGE_BYTES;              // 16 KB: [128 rows][128 B], chunk-swizzled
   uint8_t* st_lo = st_hi + 16384;
   uint8_t* stash = st_lo + 16384;                                // [hi|lo][2 cols][5][8 g][8 chunks][16 B]
-  // U8IN: the group's stored matrices + two 256-entry tables byte -> packed (fp16 hi | fp16 lo << 16) of b / 255 (plain) and
-  // of (b / 255 - 0.5) / 0.5 (channels 0..2), behind everything else
+  // U8IN: the group's stored matrices, behind everything else
   uint8_t* u8_stage = stash + (Cfg::STASH ? kStashBytes : 0) + (Cfg::TMAOUT ? kStageBytes : 0);
-  uint32_t* u8_tab = reinterpret_cast<uint32_t*>(u8_stage + kU8StageBytes);
   __shared__ __align__(8) uint64_t bars[4 + 2 * 8 + 4 + 2 + 1];
   __shared__ uint32_t u8_cst[8][4];     // per candidate: packed hi|lo of the centre marker value, tumor coverage, normal coverage
   __shared__ int u8_center[8];
@@ -343,17 +341,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   const uint32_t acc_full = smem_u32(&bars[22]), shared_free = smem_u32(&bars[23]), all_free = smem_u32(&bars[24]);
   const uint32_t u8_full = smem_u32(&bars[26]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (Cfg::U8IN && tid < 256) {
-    // byte -> fp32 channel value with the reference's arithmetic (.float().div(255), then (x - 0.5) / 0.5 for channels 0..2:
-    // dataloader.py:25-36, 405-411), split into fp16 hi + lo exactly as pack_nchw_kernel / assemble_pack_kernel do
-    const float f = __fdiv_rn((float)tid, 255.f);
-    const float c = __fdiv_rn(__fsub_rn(f, 0.5f), 0.5f);
-    uint32_t h, l;
-    split2(f, c, h, l);                      // h = (hi(f), hi(c)), l = (lo(f), lo(c))
-    u8_tab[tid] = (h & 0xffffu) | (l << 16);
-    u8_tab[256 + tid] = (h >> 16) | (l & 0xffff0000u);
-  }
-
   if (tid < 64) bias_s[tid] = args.bias[tid];
   if (tid == 0) {
     for (int i = 0; i < Cfg::NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
@@ -438,15 +425,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 #pragma unroll
           for (int j = 0; j < 16; ++j) { wh[j] = 0u; wl[j] = 0u; }
           if (col >= 0 && col < W && g < n_valid) {
-            const uint8_t* px = u8_stage + g * kU8CandBytes + (h * kW + col) * kStoredCh;
-            uint32_t e[24];
+            // the position's 23 stored bytes start at an arbitrary byte address: seven aligned words + funnel shifts instead
+            // of 23 byte loads (the shared-memory pipe is what the stem's epilogue is bound by; this loop must stay off it)
+            const uint32_t a = (uint32_t)(g * kU8CandBytes + (h * kW + col) * kStoredCh);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(u8_stage) + (a >> 2);
+            const uint32_t sh = (a & 3u) * 8u;
+            uint32_t raw[7], al[6];
 #pragma unroll
-            for (int c = 0; c < kStoredCh; ++c) e[c] = u8_tab[(c < 3 ? 256 : 0) + px[c]];
-            e[23] = (col == u8_center[g]) ? u8_cst[g][0] : 0u;
+            for (int k = 0; k < 7; ++k) raw[k] = wp[k];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-              wh[j] = __byte_perm(e[2 * j], e[2 * j + 1], 0x5410);      // (hi of channel 2j, hi of channel 2j + 1)
-              wl[j] = __byte_perm(e[2 * j], e[2 * j + 1], 0x7632);      // (lo, lo)
+            for (int k = 0; k < 6; ++k) al[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+            float v[24];
+#pragma unroll
+            for (int c = 0; c < kStoredCh; ++c) {
+              // fl(b / 255) without a division: q = b * fl(1/255) is within an ulp, one FMA residual step makes it the
+              // correctly rounded quotient for every byte value (checked for all 256 against the reference's .div(255));
+              // channels 0..2: (x - 0.5) / 0.5 == fma(x, 2, -1) bit for bit
+              const float b = (float)((al[c >> 2] >> ((c & 3) * 8)) & 0xffu);
+              const float rcp = 0.00392156885936856269836425781250f;            // fl(1 / 255)
+              const float q = b * rcp;
+              const float f = fmaf(fmaf(-q, 255.f, b), rcp, q);
+              v[c] = c < 3 ? fmaf(f, 2.f, -1.f) : f;
+            }
+#pragma unroll
+            for (int j = 0; j < 11; ++j) split2(v[2 * j], v[2 * j + 1], wh[j], wl[j]);
+            {
+              uint32_t h22, l22;
+              split2(v[22], 0.f, h22, l22);
+              const uint32_t m = (col == u8_center[g]) ? u8_cst[g][0] : 0u;
+              wh[11] = (h22 & 0xffffu) | (m << 16);
+              wl[11] = (l22 & 0xffffu) | (m & 0xffff0000u);
             }
             wh[12] = __byte_perm(u8_cst[g][1], u8_cst[g][2], 0x5410);
             wl[12] = __byte_perm(u8_cst[g][1], u8_cst[g][2], 0x7632);
