@@ -234,6 +234,10 @@ int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t 
 /* lens [n,2] int32 = (len(ref), len(alt)) of the tags of candidates [first, first + n): what call.py:343-350
  * (pred_vcf_records_none) branches on, so that the none.vcf filter can run on whole arrays */
 int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* lens);
+/* Test hook: inflates ONE zlib stream (RFC 1950) of exactly out_len bytes with the decoder's own fast inflate
+ * (csrc/nsc_inflate.h; NSC_E_STATE when it declines the stream and the decoder would fall back to zlib) or, use_zlib != 0,
+ * with zlib itself (NSC_E_INVALID on a malformed stream). */
+int nsc_debug_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len, int use_zlib);
 int nsc_tsv_close(nsc_tsv* t);
 
 #ifdef __cplusplus

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "neusomatic_cuda.h"
+#include "nsc_inflate.h"
 
 namespace nsc {
 void set_error(const char* fmt, ...);
@@ -156,6 +157,10 @@ struct DecodeJob {
 
 void decode_range(DecodeJob* job) {
   std::vector<uint8_t> comp(16384);
+  static const bool fast_inflate = getenv("NSC_TSV_ZLIB") == nullptr;      // NSC_TSV_ZLIB=1: zlib only (A/B, tests)
+  std::vector<nsc::inflate::Tables> dyn_store(1);
+  nsc::inflate::Tables& dyn = dyn_store[0];
+  uint8_t scratch[kMatrixBytes + 64];
   z_stream zs;
   memset(&zs, 0, sizeof zs);
   if (inflateInit(&zs) != Z_OK) { job->failed = 1; return; }
@@ -202,11 +207,15 @@ void decode_range(DecodeJob* job) {
       }
       // image: base64 -> zlib -> uint8[5,32,23]  (dataloader.py:38-39)
       if (ok) {
-        const size_t need = f[3].n * 3 / 4 + 4;
+        const size_t need = f[3].n * 3 / 4 + 4 + 16;          // + the read-ahead slack of the word-wise bit buffer
         if (comp.size() < need) comp.resize(need);
-        const int clen = b64_decode(f[3].p, f[3].n, comp.data(), comp.size());
+        const int clen = b64_decode(f[3].p, f[3].n, comp.data(), comp.size() - 16);
         if (clen < 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: invalid base64", li); }
-        if (ok) {
+        // fast path (nsc_inflate.h) into a private buffer with slack; anything it does not take is left to zlib, whose
+        // verdict on a malformed stream is the reference's (dataloader.py:38-39 zlib.decompress)
+        if (ok && fast_inflate && nsc::inflate::zlib_inflate_exact(comp.data(), (size_t)clen, scratch, kMatrixBytes, &dyn)) {
+          memcpy(job->matrices + (size_t)k * kMatrixBytes, scratch, kMatrixBytes);
+        } else if (ok) {
           inflateReset(&zs);
           zs.next_in = comp.data();
           zs.avail_in = (uInt)clen;
@@ -368,6 +377,33 @@ int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* len
     lens[(i - first) * 2] = rl;
     lens[(i - first) * 2 + 1] = al;
   }
+  return NSC_OK;
+}
+
+int nsc_debug_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len, int use_zlib) {
+  if (!in || !out || in_len < 0 || out_len < 0) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  std::vector<uint8_t> src((size_t)in_len + 16, 0), dst((size_t)out_len + 64);
+  memcpy(src.data(), in, (size_t)in_len);
+  if (!use_zlib) {
+    std::vector<nsc::inflate::Tables> t(1);
+    if (!nsc::inflate::zlib_inflate_exact(src.data(), (size_t)in_len, dst.data(), (size_t)out_len, &t[0])) {
+      nsc::set_error("fast inflate declined the stream");
+      return NSC_E_STATE;
+    }
+  } else {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit(&zs) != Z_OK) { nsc::set_error("inflateInit failed"); return NSC_E_NOMEM; }
+    zs.next_in = src.data();
+    zs.avail_in = (uInt)in_len;
+    zs.next_out = dst.data();
+    zs.avail_out = (uInt)out_len;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = rc == Z_STREAM_END && zs.total_out == (uLong)out_len && zs.avail_in == 0;
+    inflateEnd(&zs);
+    if (!ok) { nsc::set_error("zlib: stream does not hold %lld bytes", (long long)out_len); return NSC_E_INVALID; }
+  }
+  memcpy(out, dst.data(), (size_t)out_len);
   return NSC_OK;
 }
 
