@@ -401,3 +401,26 @@ def test_default_mode_is_split16_and_fast_mode_rejects_large_weights():
     with pytest.raises(NscError):
         eng.forward_f32(torch.from_numpy(x).cuda())
     eng.close()
+
+
+@pytest.mark.parametrize("precision", [0, 3])
+def test_workspace_grows_with_the_batch_and_results_do_not_change(precision):
+    """The packed workspace is sized by the pass that runs (1024 candidates at first) and grown on demand: a small call, a
+    larger one (re-allocation), a small one again and the host-buffer path with changing sizes all give the same rows."""
+    from neusomatic_b200 import Engine, anns_to_255
+    for ens in (False, True):
+        cand = synth.structured_pileups(5000, seed=44, ensemble=ens)
+        sd = synth.random_state_dict(119 if ens else 26, seed=4)
+        eng = Engine(sd, 119 if ens else 26, precision=precision)
+        a255 = anns_to_255(cand.anns)
+        full = [t.numpy().copy() for t in eng.score_host_u8(cand.matrices[:7], cand.meta[:7], None if a255 is None else a255[:7], 100.0)]
+        big = [t.numpy().copy() for t in eng.score_host_u8(cand.matrices, cand.meta, a255, 100.0)]
+        for a, b in zip(full, big):
+            np.testing.assert_array_equal(a, b[:7])
+        md, mt = torch.from_numpy(cand.matrices).cuda(), torch.from_numpy(cand.meta).cuda()
+        ad = None if a255 is None else torch.from_numpy(a255).cuda()
+        for lo, hi in ((0, 3), (100, 2300), (4990, 5000), (0, 5000), (17, 18)):
+            dev = eng.forward_u8(md[lo:hi].contiguous(), mt[lo:hi].contiguous(), None if ad is None else ad[lo:hi].contiguous(), 100.0)
+            for a, b in zip(dev, big):
+                np.testing.assert_array_equal(a.cpu().numpy(), b[lo:hi])
+        eng.close()
