@@ -112,6 +112,7 @@ struct ConvCfg {
                                  (STASH ? kStashBytes : 0) + (TMAOUT ? kStageBytes : 0) + (U8IN ? kU8StageBytes + 64 : 0) + 256;
   static_assert(SMEM <= 232448 - 1024, "shared memory budget");
   static_assert(!U8IN || (KH == 1 && NK == 1 && KC == 32 && GP == 1 && W == 32), "the uint8 producer builds the stem's 26 -> 32 channel operand");
+  static_assert(!U8IN || WS >= 2 * NK * KW, "the stem's weight stages stay resident in the ring's slots");
 };
 
 // accumulator slot (64 TMEM columns each) of output row h: rows of one dilation chain are adjacent and
@@ -363,12 +364,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
   // phases per unit: (lo | hi) x NK channel slices, or for S8 (x_lo8 | x8) x byte slices then NK fp16 slices
   const int nph = Cfg::S8 ? Cfg::NPH : (args.split ? 2 * NK : NK);
 
-  if (Cfg::U8IN && (warp == 0 || warp == 3)) {
+  if (Cfg::U8IN && (warp == 0 || warp == 2 || warp == 3)) {
+    // the stem's weights (six 4 KB stages: {hi, lo} x three taps) stay resident: one load, no ring -- which frees the weight
+    // producer's warp for the operand conversion below (three warps: the conversion, not the MMA, is what a unit waits for)
+    if (warp == 2) {
+      if (elect_one()) {
+        const uint32_t n_st = (args.split ? 2u : 1u) * NK * KW;
+        mbar_arrive_expect_tx(w_full, n_st * Cfg::W_STAGE_BYTES);
+        for (uint32_t st = 0; st < n_st; ++st)
+          bulk_g2s(smem_u32(w_buf + st * Cfg::W_STAGE_BYTES), args.wpk + (size_t)st * Cfg::W_STAGE_BYTES, Cfg::W_STAGE_BYTES, w_full);
+      }
+      __syncwarp();
+    }
     // ===== A producer on the uint8 interface (64 threads): stage the group's eight stored matrices with one bulk copy, then
     // build every phase's operand tile in shared memory: row r = (image row, box column, candidate) holds channels 0..31 =
     // 23 stored channels, the centre marker, the two coverage channels and zeros (dataloader.py:383-411), fp16 hi or lo part,
     // in the swizzle-64B K-major image the TMA box of the packed path would have produced (columns outside the image: zeros)
-    const int pt = (warp == 0 ? 0 : 32) + lane;
+    constexpr int NPT = 96;
+    const int pt = (warp == 0 ? 0 : warp == 2 ? 32 : 64) + lane;
     uint32_t it = 0, g_it = 0;
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x, ++g_it) {
       const int n_valid = min(8, args.B - grp * 8);
@@ -389,7 +402,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
       }
       mbar_wait(u8_full, g_it & 1);
-      {
+      if (pt < 64) {
         // np.max(matrix[:, :, 0]) per candidate (dataloader.py:390): 8 threads per candidate
         const int g = pt >> 3, l8 = pt & 7;
         int v = 0;
@@ -404,7 +417,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           u8_cst[g][0] = (h & 0xffffu) | (l << 16);
         }
       }
-      asm volatile("bar.sync 2, 64;" ::: "memory");
+      asm volatile("bar.sync 2, 96;" ::: "memory");
       // one pass over the staged bytes per unit fills BOTH phase buffers (lo part -> the first phase's buffer, hi part -> the
       // second's; single-pass arithmetic has one phase): a table entry carries both halves, so the byte and table loads are
       // not repeated per phase.  The stem's MMA work is a fifth of its epilogue, so waiting for both buffers costs nothing.
@@ -418,7 +431,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         uint8_t* dst_hi = a_buf + ((it + nph - 1) % Cfg::NA) * Cfg::A_BYTES;
         uint8_t* dst_lo = a_buf + (it % Cfg::NA) * Cfg::A_BYTES;
         const bool want_lo = nph == 2;
-        for (int r = pt; r < kH * Cfg::WB * 8; r += 64) {
+        for (int r = pt; r < kH * Cfg::WB * 8; r += NPT) {
           const int g = r & 7, cl = (r >> 3) % Cfg::WB, h = r / (8 * Cfg::WB);
           const int col = sub * Cfg::TW - Cfg::HALO + cl;
           uint32_t wh[16], wl[16];
@@ -467,7 +480,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           }
         }
         fence_proxy_async_smem();
-        asm volatile("bar.sync 2, 64;" ::: "memory");
+        asm volatile("bar.sync 2, 96;" ::: "memory");
         if (pt == 0)
           for (int ph = 0; ph < nph; ++ph) mbar_arrive(a_full + 8 * ((it + ph) % Cfg::NA));
       }
@@ -553,9 +566,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const int nsel = (!Cfg::S8 && args.split && ph >= NK) ? 2 : 1;
             for (int si = 0; si < nsel; ++si)
               for (int dx = 0; dx < KW; ++dx, ++w_it) {
-                const uint32_t st = w_it % WS;
+                // U8IN: resident stages, addressed by (weight part, tap); otherwise the ring slot the producer filled
+                const uint32_t st = Cfg::U8IN ? (uint32_t)(((nsel == 2 ? 1 - si : 0) * NK + (ph % NK)) * KW + dx) : w_it % WS;
                 t_c = clock64();
-                mbar_wait(w_full + 8 * st, (w_it / WS) & 1);
+                if (!Cfg::U8IN) mbar_wait(w_full + 8 * st, (w_it / WS) & 1);
+                else if (w_it == 0) mbar_wait(w_full, 0);
                 t_w += clock64() - t_c;
                 tc_fence_after_sync();
                 const uint32_t w_base = smem_u32(w_buf + st * Cfg::W_STAGE_BYTES);
@@ -584,7 +599,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 } else {
                   issue_rows<Cfg, 0, f8>(acc0, a_base, w_base, wl0, 0x1fu, 0, 4);
                 }
-                umma_commit(w_empty + 8 * st);
+                if (!Cfg::U8IN) umma_commit(w_empty + 8 * st);
                 first_stage = false;
               }
             umma_commit(a_empty + 8 * buf);
