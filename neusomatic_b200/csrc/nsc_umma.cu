@@ -436,45 +436,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         uint8_t* dst_hi = a_buf + ((it + nph - 1) % Cfg::NA) * Cfg::A_BYTES;
         uint8_t* dst_lo = a_buf + (it % Cfg::NA) * Cfg::A_BYTES;
         const bool want_lo = nph == 2;
-        if (from_f32) {
-          // fp32 NCHW source: an item = (image row, aligned block of 4 columns, candidate, octet of channels): eight 16-byte
-          // loads x[b][8q .. 8q+7][h][4 columns] give one 16-byte operand chunk for each of 4 positions.  Lane order
-          // (octet, block parity, candidate): neighbouring lanes take the two halves of every 32-byte sector.
-          const int cb0 = sub * Cfg::TW - 4;                    // first aligned block starts 2 columns left of the box
-          for (int itx = pt; itx < kH * 6 * 8 * 4; itx += NPT) {
-            const int q = itx & 3, jb = ((itx >> 2) & 1) | (((itx >> 6) % 3) << 1), g = (itx >> 3) & 7;
-            const int h = itx / 192;
-            const int colb = cb0 + 4 * jb;
-            const bool inimg = colb >= 0 && colb < W && g < n_valid;
-            const float* xb = args.x_f32 + ((((int64_t)grp * 8 + g) * args.c_in + q * 8) * kH + h) * kW + colb;
-            float4 v[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              v[c] = (inimg && q * 8 + c < args.c_in) ? __ldg(reinterpret_cast<const float4*>(xb + (int64_t)c * (kH * kW)))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int cl = 4 * jb - 2 + t;                    // box column of this position
-              if (cl < 0 || cl >= Cfg::WB) continue;
-              const float* f = reinterpret_cast<const float*>(v) + t;
-              uint4 hq, lq;
-              split2(f[0], f[4], hq.x, lq.x);
-              split2(f[8], f[12], hq.y, lq.y);
-              split2(f[16], f[20], hq.z, lq.z);
-              split2(f[24], f[28], hq.w, lq.w);
-              const uint32_t off = swz_offset<64>((uint32_t)((h * Cfg::WB + cl) * 8 + g), (uint32_t)q);
-              *reinterpret_cast<uint4*>(dst_hi + off) = hq;
-              if (want_lo) *reinterpret_cast<uint4*>(dst_lo + off) = lq;
-            }
-          }
-        } else
         for (int r = pt; r < kH * Cfg::WB * 8; r += NPT) {
           const int g = r & 7, cl = (r >> 3) % Cfg::WB, h = r / (8 * Cfg::WB);
           const int col = sub * Cfg::TW - Cfg::HALO + cl;
           uint32_t wh[16], wl[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { wh[j] = 0u; wl[j] = 0u; }
-          if (col >= 0 && col < W && g < n_valid) {
+          if (from_f32) {
+            if (col >= 0 && col < W && g < n_valid) {
+              // x[b][c][h][col], c = 0 .. c_in-1: c_in independent 4-byte loads 640 bytes apart (a warp's lanes are 8 candidates
+              // x 4 adjacent columns: eight half-used 32-byte sectors per instruction; the other half is the neighbouring
+              // lanes' next iteration and comes out of L2)
+              const float* xb = args.x_f32 + (((int64_t)grp * 8 + g) * args.c_in * kH + h) * kW + col;
+              float v[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = c < args.c_in ? __ldg(xb + (int64_t)c * (kH * kW)) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], wh[j], wl[j]);
+            }
+          } else if (col >= 0 && col < W && g < n_valid) {
             // the position's 23 stored bytes start at an arbitrary byte address: seven aligned words + funnel shifts instead
             // of 23 byte loads (the shared-memory pipe is what the stem's epilogue is bound by; this loop must stay off it)
             const uint32_t a = (uint32_t)(g * kU8CandBytes + (h * kW + col) * kStoredCh);
