@@ -108,7 +108,6 @@ struct UmmaState {
   const uint8_t* u8_mat = nullptr;      // set for the duration of a pass on the uint8 interface: the stem builds its operand from
   const int32_t* u8_meta = nullptr;     // the stored matrices (csrc/nsc_umma.cu, ConvCfg::U8IN)
   double u8_thr = 0.0;
-  const float* x_f32 = nullptr;         // ... or from the fp32 NCHW batch of the module interface (<= 32 channels)
   int64_t cap = 0;
   int num_sms = 148;
   bool weights_fit_fp16 = true;

@@ -175,8 +175,6 @@ struct UmmaConvArgs {
   const uint8_t* u8_mat;     // U8IN: stored candidate matrices uint8 [B][5][32][23]
   const int32_t* u8_meta;    // U8IN: [B][3] = (center, tumor_cov, normal_cov)
   double u8_thr;             // U8IN: coverage_thr of the checkpoint
-  const float* x_f32;        // U8IN kernel on the fp32 module interface: [B][c_in][5][32] NCHW (c_in <= 32), instead of u8_mat
-  int c_in;
   const float* ann_bias;     // U8IN, ensemble network: [B][3][64] contribution of the annotation channels (ann_bias_kernel) or nullptr
   long long* stats;          // optional [grid][8] cycle counters (NSC_UMMA_STATS=1)
   int dbg_skip;              // timing experiments only (NSC_UMMA_SKIP): 1 = no fp8 MMAs, 2 = no fp16 MMAs, 4 = no epilogue body,
@@ -387,8 +385,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     uint32_t it = 0, g_it = 0;
     for (int grp = blockIdx.x; grp < args.n_groups; grp += gridDim.x, ++g_it) {
       const int n_valid = min(8, args.B - grp * 8);
-      const bool from_f32 = args.x_f32 != nullptr;      // fp32 module interface: channels straight from the NCHW batch
-      if (!from_f32) {
       if (pt == 0) {
         mbar_arrive_expect_tx(u8_full, (uint32_t)(n_valid * kU8CandBytes));
         bulk_g2s(smem_u32(u8_stage), args.u8_mat + (size_t)grp * kU8StageBytes, (uint32_t)(n_valid * kU8CandBytes), u8_full);
@@ -422,7 +418,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         }
       }
       asm volatile("bar.sync 2, 96;" ::: "memory");
-      }
       // one pass over the staged bytes per unit fills BOTH phase buffers (lo part -> the first phase's buffer, hi part -> the
       // second's; single-pass arithmetic has one phase): a table entry carries both halves, so the byte and table loads are
       // not repeated per phase.  The stem's MMA work is a fifth of its epilogue, so waiting for both buffers costs nothing.
@@ -442,19 +437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
           uint32_t wh[16], wl[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { wh[j] = 0u; wl[j] = 0u; }
-          if (from_f32) {
-            if (col >= 0 && col < W && g < n_valid) {
-              // x[b][c][h][col], c = 0 .. c_in-1: c_in independent 4-byte loads 640 bytes apart (a warp's lanes are 8 candidates
-              // x 4 adjacent columns: eight half-used 32-byte sectors per instruction; the other half is the neighbouring
-              // lanes' next iteration and comes out of L2)
-              const float* xb = args.x_f32 + (((int64_t)grp * 8 + g) * args.c_in * kH + h) * kW + col;
-              float v[32];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) v[c] = c < args.c_in ? __ldg(xb + (int64_t)c * (kH * kW)) : 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], wh[j], wl[j]);
-            }
-          } else if (col >= 0 && col < W && g < n_valid) {
+          if (col >= 0 && col < W && g < n_valid) {
             // the position's 23 stored bytes start at an arbitrary byte address: seven aligned words + funnel shifts instead
             // of 23 byte loads (the shared-memory pipe is what the stem's epilogue is bound by; this loop must stay off it)
             const uint32_t a = (uint32_t)(g * kU8CandBytes + (h * kW + col) * kStoredCh);
@@ -1401,9 +1384,7 @@ static int launch_umma_conv(nsc_model* m, int slot, uint16_t* const in[3], const
   a.u8_mat = Cfg::U8IN ? m->umma.u8_mat : nullptr;
   a.u8_meta = Cfg::U8IN ? m->umma.u8_meta : nullptr;
   a.u8_thr = m->umma.u8_thr;
-  a.x_f32 = Cfg::U8IN ? m->umma.x_f32 : nullptr;
-  a.c_in = m->C;
-  a.ann_bias = (Cfg::U8IN && m->C > kBaseCh && m->umma.x_f32 == nullptr) ? m->umma.ann_bias : nullptr;
+  a.ann_bias = (Cfg::U8IN && m->C > kBaseCh) ? m->umma.ann_bias : nullptr;
   static const int dbg_skip = getenv("NSC_UMMA_SKIP") ? atoi(getenv("NSC_UMMA_SKIP")) : 0;
   a.dbg_skip = dbg_skip;
   if ((dbg_skip & 32) && !Cfg::TMAOUT) { a.out_lo = nullptr; a.out_c8 = nullptr; }   // timing experiment: 2 instead of 6 bytes stored per element
@@ -1470,14 +1451,6 @@ int umma_forward_chunk(nsc_model* m, const float* x, int64_t n, const Outputs& o
   int rc;
   if ((rc = umma_ensure_workspace(m, n)) != NSC_OK) return rc;
   UmmaState& u = m->umma;
-  static const bool no_fused = getenv("NSC_NO_FUSED_STEM") != nullptr;
-  if (u.nk1 == 1 && !no_fused) {
-    // up to 32 input channels: the stem's producer warps read the fp32 batch themselves (no packed copy of the input)
-    u.x_f32 = x;
-    rc = umma_run(m, n, o, s);
-    u.x_f32 = nullptr;
-    return rc;
-  }
   {
     ProfScope prof(m, 11, s);
     pack_nchw_kernel<<<(unsigned)(((n + 7) / 8) * kH * u.nk1), 256, 0, s>>>(x, u.xin[0], u.xin[1], (int)n, m->C, u.nk1 * 32);
@@ -1552,8 +1525,8 @@ static int umma_run_mask(nsc_model* m, int64_t n, const Outputs& o, cudaStream_t
   auto fmt_mid = [&](int l) { return ((s8 >> l) & 1u) ? kOutC8 : kOutLo; };                      // consumer: conv l only
   uint16_t** const none = nullptr;
   // conv1 + BN + ReLU + pool1 (network.py:44-47,67): split-fp16 in every tensor mode (its input is the packed hi/lo image)
-  if (u.u8_mat != nullptr || u.x_f32 != nullptr)      // channel assembly / fp32 load + split inside the stem's producer warps
-    NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false, 32, 1, false, true>>(m, 1, u.xin, (m->C > kBaseCh && u.u8_mat != nullptr) ? u.wpk1_u8 : u.wpk1, w.conv1_b, X,
+  if (u.u8_mat != nullptr)      // uint8 interface: channel assembly + split inside the stem's producer warps
+    NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false, 32, 1, false, true>>(m, 1, u.xin, m->C > kBaseCh ? u.wpk1_u8 : u.wpk1, w.conv1_b, X,
                                                                                      nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else if (u.nk1 == 1) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 1, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
   else if (u.nk1 == 2) NSC_RUN((launch_umma_conv<ConvCfg<1, 3, 1, 32, 2, 1, false>>(m, 1, u.xin, u.wpk1, w.conv1_b, X, nullptr, nullptr, n, 1, s, fmt_block_input(0))));
