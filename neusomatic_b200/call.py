@@ -465,7 +465,16 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
         if not slices:
             return
         cap = max(s[2] for s in slices)
-        slots = [_Slot(cap, num_anns) for _ in range(min(len(slices), 2 + len(scorers)))]
+        n_slots = min(len(slices), 2 + len(scorers))
+        # pinned slot buffers are kept on the first scorer between calls (cudaHostAlloc of a few hundred MB is slow)
+        cache = getattr(scorers[0], "_slot_cache", None)
+        if cache is None or cache[0] < cap or len(cache[1]) < n_slots or cache[2] != num_anns:
+            cache = (cap, [_Slot(cap, num_anns) for _ in range(n_slots)], num_anns)
+            try:
+                scorers[0]._slot_cache = cache
+            except AttributeError:
+                pass
+        slots = cache[1][:n_slots]
 
         def decode(k, wait_for):
             if wait_for is not None:

@@ -424,3 +424,28 @@ def test_workspace_grows_with_the_batch_and_results_do_not_change(precision):
             for a, b in zip(dev, big):
                 np.testing.assert_array_equal(a.cpu().numpy(), b[lo:hi])
         eng.close()
+
+
+def test_call_variants_under_dataparallel(golden):
+    """call.py:417-419 wraps the module in nn.DataParallel when several GPUs are visible: call_variants then splits every
+    coalesced slice over the module's devices (one engine per device) and returns the same dictionaries."""
+    from neusomatic_b200.network import NeuSomaticNet
+    from neusomatic_b200.call import call_variants, load_checkpoint
+    name, g, ck = golden
+    sd, meta = load_checkpoint(ck)
+    x = torch.from_numpy(_assemble(g, ck))
+    nt = torch.from_numpy(oracle.non_transformed(g["matrices"], g["center"]))
+    tags = [str(t) for t in g["tags"]]
+    net = NeuSomaticNet(x.shape[1]).cuda()
+    net.load_state_dict(sd, strict=False)
+    bs = 40
+    loader = [((x[i:i + bs], None, None, None, nt[i:i + bs]), (tags[i:i + bs], None)) for i in range(0, len(tags), bs)]
+    f1, n1, t1 = call_variants(net, oracle.VARTYPE_CLASSES, loader, None, "t", True)
+    f2, n2, t2 = call_variants(torch.nn.DataParallel(net), oracle.VARTYPE_CLASSES, loader, None, "t", True)
+    assert list(f1.keys()) == list(f2.keys()) and list(n1.keys()) == list(n2.keys()) and set(t1) == set(t2)
+    for d1, d2 in ((f1, f2), (n1, n2)):
+        for k in d1:
+            a, b = d1[k], d2[k]
+            assert a[0] == b[0] and int(a[2]) == int(b[2]) and a[1][0] == b[1][0]
+            for j in (3, 4, 5, 6):
+                assert [float(v) for v in a[j]] == [float(v) for v in b[j]]
