@@ -484,21 +484,23 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             t = tsvs[path]
             t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
                                  "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
-            return t.tags(f0, n), t.allele_lens(f0, n)
+            return None
 
         def score(k, fdec):
-            tags, lens = fdec.result()
+            fdec.result()
             n = slices[k][2]
             slot = slots[k % len(slots)]
             sc = scorers[k % len(scorers)]
             outs = [None if t is None else t[:n] for t in slot.out]
             sc.engine.score_host_u8(slot.matrices[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
                                     sc.coverage_thr, extras=True, out=outs)
-            return tags, lens, outs
+            return outs
 
         def file_slice(k, fsc):
-            tags, lens, outs = fsc.result()
-            n = slices[k][2]
+            # the tag strings and allele lengths are read here, off the decoder thread: the decode stage is the slowest
+            path, f0, n = slices[k]
+            tags, lens = tsvs[path].tags(f0, n), tsvs[path].allele_lens(f0, n)
+            outs = fsc.result()
             slot = slots[k % len(slots)]
             names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
             r = {nm: t.numpy() for nm, t in zip(names, outs)}

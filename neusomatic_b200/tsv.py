@@ -35,10 +35,14 @@ class CandidateTSV:
         if n == 0:
             return []
         need = C.c_int64()
-        _lib.check(self.lib.nsc_tsv_tags(self.h, first, n, None, 0, C.byref(need)))
-        buf = C.create_string_buffer(need.value)
-        _lib.check(self.lib.nsc_tsv_tags(self.h, first, n, buf, need.value, C.byref(need)))
-        return buf.raw[:need.value - 1].decode().split("\n")
+        cap = 96 * n + 64                                  # one pass for ordinary tags (~40 bytes); sized exactly otherwise
+        buf = np.empty(cap, np.uint8)
+        rc = self.lib.nsc_tsv_tags(self.h, first, n, buf.ctypes.data, cap, C.byref(need))
+        if rc != 0 and need.value > cap:
+            buf = np.empty(need.value, np.uint8)
+            rc = self.lib.nsc_tsv_tags(self.h, first, n, buf.ctypes.data, need.value, C.byref(need))
+        _lib.check(rc)
+        return buf[:need.value - 1].tobytes().decode().split("\n")
 
     def allele_lens(self, first=0, n=None):
         """int32 [n,2] = (len(ref), len(alt)) of the candidates' tags (what the none.vcf filter branches on, call.py:343-350)."""
