@@ -174,10 +174,23 @@ def cpu_tsv_rate(path, C, seconds=8.0, batch=1000):
     return done / el, "%d candidates in batches of %d over %.1f s" % (done, batch, el)
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line; identical for both arms (the reference arm times a bounded sample of it)."""
+    C = 119 if getattr(args, "ensemble", False) else 26
+    B = args.batch
+    return {"workload": ("synthetic ensemble call (BASELINE.json configs[3]): C=119, 119x5x32 matrices, v0.1.0 ensemble "
+                         "checkpoint, S1 uniform pileups") if C == 119 else
+                        ("synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, "
+                         "v0.1.0 standalone checkpoint, S1 uniform pileups"),
+            "batch_per_gpu": B, "candidates_per_step": world * B,
+            "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
+            "sharding": "contiguous candidate ranges per rank, no collective on the data path"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    C = 26
+    C = 119 if args.ensemble else 26
     rates, secs = [], []
     for _ in range(args.warmup):
         cpu_port_rate(C, seconds=1.0, batch=args.ref_batch)
@@ -193,9 +206,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "NeuSomaticNet candidates/sec", "value": v, "unit": "candidates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, v0.1.0 standalone "
-                               "checkpoint, S1 uniform pileups; each step = a bounded CPU sample of that workload",
-                   "batch": args.ref_batch},
+        "config": workload_config(args, max(args.gpus, 1)),
+        "timing": "each step = a bounded CPU sample of the workload, scored %d candidates at a time" % args.ref_batch,
         "cpu_baseline": {"value": v, "unit": "candidates/s", "cores": threads, "kind": "port",
                          "sample": "oracle/torch_port.py (PyTorch CPU operators, fp32): " + sample},
         "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -636,15 +648,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": prec_names.get(m["precision"], str(m["precision"])), "data": "synthetic",
-            "config": {"workload": ("synthetic ensemble call (BASELINE.json configs[3]): C=119, 119x5x32 matrices, v0.1.0 ensemble "
-                                    "checkpoint, S1 uniform pileups") if args.ensemble else
-                                   ("synthetic standalone call (BASELINE.json configs[2]): C=26, 26x5x32 matrices, "
-                                    "v0.1.0 standalone checkpoint, S1 uniform pileups"),
-                       "batch_per_gpu": B, "candidates_per_step": world * B,
-                       "l2_policy": "inputs larger than L2 (%.2f GB fp32 per step per GPU)" % (B * C * 640 / 1e9),
-                       "sharding": "contiguous candidate ranges per rank, no collective on the data path",
-                       "timing": "median of %d regions of %d steps (>= %.0f ms timed), max over ranks per region" % (
-                           len(m["region_ms"]), args.steps, args.min_timed_ms)},
+            "config": workload_config(args, world),
+            "timing": "median of %d regions of %d steps (>= %.0f ms timed), max over ranks per region" % (
+                len(m["region_ms"]), args.steps, args.min_timed_ms),
             "region_ms": [round(v, 3) for v in m["region_ms"]], "ms_per_rank": [round(v, 3) for v in m["ms_per_rank"]],
             "e2e": m.get("e2e"), "e2e_f32": m.get("e2e_f32"), "gpu_launches": m.get("launches"), "roofline": roof,
             "cpu_baseline": cpu, "clocks": m["clocks"], "extra": extra,
