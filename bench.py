@@ -478,7 +478,7 @@ def measure_incumbent(args, rk, local_rank):
 # ---------------------------------------------------------------------------------------------------------------------
 # e2e_tsv: reference-format candidate TSV -> dictionaries
 # ---------------------------------------------------------------------------------------------------------------------
-def measure_tsv(args, rk, local_rank, n=131072):
+def measure_tsv(args, rk, local_rank, n=524288):
     import base64
     import zlib
     from neusomatic_b200 import synth
@@ -496,15 +496,31 @@ def measure_tsv(args, rk, local_rank, n=131072):
     size = os.path.getsize(path)
     sc = CandidateScorer(CKPT, device=local_rank, precision=args.precision)
     threads = os.cpu_count() or 1
-    sc.call_tsv(path, batch=32768, num_threads=threads)       # warm-up: page cache, workspace, pinned slots
-    times = []
-    for _ in range(3):
-        t0 = time.perf_counter()
-        final_preds, none_preds = sc.call_tsv(path, batch=32768, num_threads=threads)
-        n_none_records = len(dict(pred_vcf_records_none(none_preds, ["chr%d" % i for i in range(30)])))
-        times.append(time.perf_counter() - t0)
+    chroms = ["chr%d" % i for i in range(30)]
+
+    def run_mode(host_decode):
+        os.environ["NSC_TSV_HOST_DECODE"] = "1" if host_decode else "0"
+        sc.call_tsv(path, batch=32768, num_threads=threads)       # warm-up: page cache, workspace, pinned slots
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fp, npred = sc.call_tsv(path, batch=32768, num_threads=threads)
+            nrec = len(dict(pred_vcf_records_none(npred, chroms)))
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), fp, npred, nrec
+
+    el_host, _, _, _ = run_mode(True)
+    times = None
+    el, final_preds, none_preds, n_none_records = run_mode(False)
+    # device time of the inflate kernel itself (event brackets of the library), one more pass
+    sc.engine.set_profile(True)
+    sc.engine.get_profile()
+    sc.call_tsv(path, batch=32768, num_threads=threads)
+    prof = sc.engine.get_profile()
+    sc.engine.set_profile(False)
+    os.environ.pop("NSC_TSV_HOST_DECODE", None)
     sc.engine.close()
-    el = float(np.median(times))
+    infl_ms = prof.get("inflate_b64", (0.0, 0))[0]
     cpu_rate, cpu_sample = (None, None)
     if not args.no_cpu_baseline:
         cpu_rate, cpu_sample = cpu_tsv_rate(path, 26)
@@ -512,8 +528,14 @@ def measure_tsv(args, rk, local_rank, n=131072):
     os.rmdir(td)
     return {"value": n / el, "unit": "candidates/s", "candidates": n, "tsv_bytes": size, "host_threads": threads,
             "final_preds": len(final_preds), "none_preds": len(none_preds), "none_vcf_records": n_none_records,
-            "what": "CandidateScorer.call_tsv: C++ mmap/base64/inflate decoder -> nsc_score_host_u8 -> PredTable dictionaries + the none.vcf "
-                    "filter on arrays; decode, score and filing overlapped (call.py:504-534 + 336-354)",
+            "what": "CandidateScorer.call_tsv: C++ line splitter / tag parser -> nsc_score_host_b64 (base64 + zlib inflate on the device, "
+                    "then the network) -> PredTable dictionaries + the none.vcf filter on arrays; stage, score and filing overlapped "
+                    "(call.py:504-534 + 336-354)",
+            "h2d_bytes_per_candidate": size / n,
+            "inflate_kernel": {"ms_per_pass": infl_ms, "candidates_per_s": (n / (infl_ms * 1e-3)) if infl_ms > 0 else None,
+                               "output_GBps": (n * 3680 / (infl_ms * 1e-3) / 1e9) if infl_ms > 0 else None},
+            "host_inflate": {"value": n / el_host, "unit": "candidates/s",
+                             "what": "the same call with NSC_TSV_HOST_DECODE=1: inflate on the host threads -> nsc_score_host_u8"},
             "cpu_reference_chain": None if cpu_rate is None else {
                 "value": cpu_rate, "unit": "candidates/s", "kind": "port", "cores": threads,
                 "sample": "oracle: TSV line decode + channel assembly + torch_port forward + call_variants loop, " + cpu_sample}}

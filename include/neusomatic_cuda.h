@@ -132,6 +132,19 @@ int nsc_score_host_u8(nsc_model* m, const uint8_t* matrices_host, const int32_t*
                       float* type_logits, float* pos, float* len_logits,
                       float* type_prob, float* len_prob,
                       int32_t* type_argmax, int32_t* len_argmax);
+/* The same batch step fed with the TSV's own image fields: extract_zlib (dataloader.py:38-39,
+ * zlib.decompress(base64.b64decode(field))) runs ON THE DEVICE, so a candidate crosses PCIe as ~1.3 KB of text.
+ * text_host: bytes holding the fields (nsc_tsv_stage copies the file's lines there verbatim; pinned memory keeps the
+ * copies asynchronous); spans_host [B][2] uint32 = (offset in text_host, characters) of every candidate's
+ * base64(zlib(uint8[5,32,23])) field; meta / anns255 / outputs as in nsc_score_host_u8.  A field the device decoder
+ * declines (malformed or unusual stream) is decoded by zlib on the host before its slice is scored: results never depend
+ * on where a candidate was inflated, and a field zlib rejects fails the call (NSC_E_INVALID) like the reference's worker.
+ * host_decoded (optional): how many candidates of this call went that way. */
+int nsc_score_host_b64(nsc_model* m, const uint8_t* text_host, int64_t text_bytes, const uint32_t* spans_host,
+                       const int32_t* meta_host, const float* anns255_host, float coverage_thr, int64_t B,
+                       float* type_logits, float* pos, float* len_logits,
+                       float* type_prob, float* len_prob,
+                       int32_t* type_argmax, int32_t* len_argmax, int64_t* host_decoded);
 
 /* Test / profiling hooks (no reference equivalent; network.py:78 returns internal_outs that
  * every caller discards).  Copies an internal activation of the LAST forward chunk to a
@@ -226,6 +239,15 @@ int64_t nsc_tsv_count(const nsc_tsv* t);
  * text in nsc_last_error) on malformed lines, like the reference's worker returning None. */
 int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* matrices, int32_t* meta,
                    float* anns255, int32_t* labels, int num_threads);
+/* Staging for nsc_score_host_b64 -- everything of nsc_tsv_decode except the inflate: the lines of candidates
+ * [first, first + n) are copied verbatim to text (text_cap >= nsc_tsv_range_bytes(t, first, n) + 16), spans [n,2] uint32
+ * receive (offset in text, characters) of each image field, meta / anns255 / labels as above. */
+int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* text, int64_t text_cap, uint32_t* spans,
+                  int32_t* meta, float* anns255, int32_t* labels, int num_threads);
+/* bytes of the lines of candidates [first, first + n) (-1: range out of bounds) */
+int64_t nsc_tsv_range_bytes(const nsc_tsv* t, int64_t first, int64_t n);
+/* matrices [n,5,32,23] of the listed candidates only (the images call.py:89-95 keeps for the called variants) */
+int nsc_tsv_decode_rows(nsc_tsv* t, const int64_t* rows, int64_t n, uint8_t* matrices, int num_threads);
 /* pointer into the mapped file + length of candidate i's tag (field 3 of the line; not NUL-terminated) */
 int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len);
 /* tags of candidates [first, first + n), each followed by '\n', copied into buf (cap bytes); *needed = bytes required
@@ -238,6 +260,11 @@ int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* len
  * (csrc/nsc_inflate.h; NSC_E_STATE when it declines the stream and the decoder would fall back to zlib) or, use_zlib != 0,
  * with zlib itself (NSC_E_INVALID on a malformed stream). */
 int nsc_debug_inflate(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_len, int use_zlib);
+/* Test hook: the device decoder of nsc_score_host_b64 alone -- base64 + zlib inflate of n image fields on `device`;
+ * matrices_host [n,3680] (rows of declined candidates are zero), declined_host [n] = 1 where the device decoder left the
+ * candidate to the host. */
+int nsc_debug_inflate_b64(int device, const uint8_t* text_host, int64_t text_bytes, const uint32_t* spans_host, int64_t n,
+                          uint8_t* matrices_host, int32_t* declined_host);
 int nsc_tsv_close(nsc_tsv* t);
 
 #ifdef __cplusplus

@@ -34,6 +34,7 @@ SIGNATURES = {
     "nsc_forward_u8": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64] + _OUT7 + [_vp]),
     "nsc_score_host_f32": (_i32, [_vp, _vp, _i64] + _OUT7),
     "nsc_score_host_u8": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64] + _OUT7),
+    "nsc_score_host_b64": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _f32, _i64] + _OUT7 + [C.POINTER(_i64)]),
     "nsc_debug_internal": (_i32, [_vp, _i32, _vp, _i64, _vp]),
     "nsc_debug_assemble": (_i32, [_vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp]),
     "nsc_model_set_profile": (_i32, [_vp, _i32]),
@@ -55,10 +56,14 @@ SIGNATURES = {
     "nsc_tsv_open": (_i32, [C.POINTER(_vp), C.c_char_p]),
     "nsc_tsv_count": (_i64, [_vp]),
     "nsc_tsv_decode": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32]),
+    "nsc_tsv_stage": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32]),
+    "nsc_tsv_range_bytes": (_i64, [_vp, _i64, _i64]),
+    "nsc_tsv_decode_rows": (_i32, [_vp, _vp, _i64, _vp, _i32]),
     "nsc_tsv_tag": (_i32, [_vp, _i64, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "nsc_tsv_tags": (_i32, [_vp, _i64, _i64, _vp, _i64, C.POINTER(_i64)]),
     "nsc_tsv_allele_lens": (_i32, [_vp, _i64, _i64, _vp]),
     "nsc_debug_inflate": (_i32, [_vp, _i64, _vp, _i64, _i32]),
+    "nsc_debug_inflate_b64": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nsc_tsv_close": (_i32, [_vp]),
 }
 

@@ -429,7 +429,10 @@ def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds,
     final_preds.add(vt, *[np.asarray(r[c])[var] for c in cols], lens=None if lens is None else lens[var])
     none_preds.add([tags[i] for i in non], *[np.asarray(r[c])[non] for c in cols], lens=None if lens is None else lens[non])
     if true_path is not None:
-        img = non_transformed_images(np.asarray(matrices)[var], np.asarray(center)[var])
+        # ``matrices`` may be a function of the row indices (the device-inflate pipeline keeps no decoded matrices on the host:
+        # only the called variants' images are decoded here)
+        mv = matrices(var) if callable(matrices) else np.asarray(matrices)[var]
+        img = non_transformed_images(mv, np.asarray(center)[var])
         for t, im in zip(vt, img):
             true_path[t] = im
 
@@ -437,11 +440,17 @@ def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds,
 class _Slot:
     """Pinned host buffers of one in-flight slice: decoder output = scorer input, and the scorer's host results."""
 
-    def __init__(self, n, num_anns):
+    def __init__(self, n, num_anns, text_bytes=0):
         pin = torch.cuda.is_available()
         mk = lambda shape, dt: (torch.empty(shape, dtype=dt).pin_memory() if pin else torch.empty(shape, dtype=dt))
         self.n = n
-        self.matrices = mk((n, 5, 32, 23), torch.uint8)
+        self.text_bytes = text_bytes
+        if text_bytes:        # device inflate: the slice's lines as they are in the file + (offset, characters) of each image field
+            self.text = mk((text_bytes,), torch.uint8)
+            self.spans = mk((n, 2), torch.int32)         # read as uint32 by the library
+            self.matrices = None
+        else:
+            self.matrices = mk((n, 5, 32, 23), torch.uint8)
         self.meta = mk((n, 3), torch.int32)
         self.anns = mk((n, num_anns), torch.float32) if num_anns else None
         self.out = Engine._host_out(n, True, pin)
@@ -451,9 +460,14 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
     """Decode -> score -> file, overlapped.  ``pieces`` = [(tsv path, first candidate, count or None)]; slices of at most
     ``batch`` candidates go round-robin to ``scorers`` (one per GPU: the path shards by candidate, no collective).  One
     decoder thread (the C++ decoder fans out over ``num_threads`` itself), one scoring thread per GPU and one filing
-    thread; the ctypes calls release the GIL, so only the filing stage competes for it."""
+    thread; the ctypes calls release the GIL, so only the filing stage competes for it.
+
+    By default the image fields are inflated ON THE DEVICE (``nsc_tsv_stage`` -> ``nsc_score_host_b64``,
+    csrc/nsc_inflate_gpu.cu): the host stage only splits lines and parses tags.  ``NSC_TSV_HOST_DECODE=1`` keeps the
+    inflate on the host threads (``nsc_tsv_decode`` -> ``nsc_score_host_u8``); the results are the same bytes."""
     from .tsv import CandidateTSV
     num_anns = scorers[0].C - 26
+    device_inflate = os.environ.get("NSC_TSV_HOST_DECODE", "0") in ("", "0")
     tsvs, slices = {}, []
     try:
         for path, first, count in pieces:
@@ -466,10 +480,15 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             return
         cap = max(s[2] for s in slices)
         n_slots = min(len(slices), 2 + len(scorers))
+        text_cap = 0
+        if device_inflate:
+            text_cap = max(tsvs[p].range_bytes(f0, n) for p, f0, n in slices) + 64
         # pinned slot buffers are kept on the first scorer between calls (cudaHostAlloc of a few hundred MB is slow)
         cache = getattr(scorers[0], "_slot_cache", None)
-        if cache is None or cache[0] < cap or len(cache[1]) < n_slots or cache[2] != num_anns:
-            cache = (cap, [_Slot(cap, num_anns) for _ in range(n_slots)], num_anns)
+        if (cache is None or cache[0] < cap or len(cache[1]) < n_slots or cache[2] != num_anns or
+                (cache[1][0].text_bytes < text_cap) or (cache[1][0].text_bytes > 0) != device_inflate):
+            text_cap += text_cap // 8
+            cache = (cap, [_Slot(cap, num_anns, text_cap) for _ in range(n_slots)], num_anns)
             try:
                 scorers[0]._slot_cache = cache
             except AttributeError:
@@ -482,16 +501,23 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             path, f0, n = slices[k]
             slot = slots[k % len(slots)]
             t = tsvs[path]
+            if device_inflate:
+                t.stage(f0, n, slot.text, slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n])
+                return t.range_bytes(f0, n)
             t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
                                  "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
             return None
 
         def score(k, fdec):
-            fdec.result()
+            nbytes = fdec.result()
             n = slices[k][2]
             slot = slots[k % len(slots)]
             sc = scorers[k % len(scorers)]
             outs = [None if t is None else t[:n] for t in slot.out]
+            if device_inflate:
+                sc.engine.score_host_b64(slot.text[:nbytes], slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
+                                         sc.coverage_thr, extras=True, out=outs)
+                return outs
             sc.engine.score_host_u8(slot.matrices[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
                                     sc.coverage_thr, extras=True, out=outs)
             return outs
@@ -504,8 +530,8 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             slot = slots[k % len(slots)]
             names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
             r = {nm: t.numpy() for nm, t in zip(names, outs)}
-            _split_into_tables(r, tags, lens, slot.matrices[:n].numpy(), slot.meta[:n, 0].numpy(), final_preds, none_preds,
-                               true_path)
+            mats = (lambda rows: tsvs[path].decode_rows(f0 + np.asarray(rows, np.int64))) if device_inflate else slot.matrices[:n].numpy()
+            _split_into_tables(r, tags, lens, mats, slot.meta[:n, 0].numpy(), final_preds, none_preds, true_path)
 
         TPE = concurrent.futures.ThreadPoolExecutor
         with TPE(1) as dec_ex, TPE(1) as file_ex:

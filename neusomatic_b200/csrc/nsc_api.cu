@@ -364,11 +364,20 @@ int nsc_forward_u8(nsc_model* m, const uint8_t* matrices_dev, const int32_t* met
 }
 
 // --- host-buffer scoring: H2D / compute / D2H on three internal streams, two slots -----------
-static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t* meta_host, const float* anns_host,
-                      float coverage_thr, int64_t B, const Outputs& oh) {
+// kind: 0 = fp32 network input, 1 = stored uint8 matrices, 2 = the TSV's base64(zlib(matrix)) text fields (in_host = text,
+// spans [B][2] = (offset, characters) of each candidate's field): inflated on the device, candidates the device decoder
+// declines are decoded by zlib on the host and patched in before the slice is scored
+static int score_host(nsc_model* m, int kind, const void* in_host, const int32_t* meta_host, const float* anns_host,
+                      float coverage_thr, int64_t B, const Outputs& oh, const uint32_t* spans = nullptr, int64_t text_bytes = 0) {
+  const bool u8 = kind != 0, b64 = kind == 2;
   int rc = check_ready(m, B);
   if (rc != NSC_OK) return rc;
   if (B == 0) return NSC_OK;
+  if (b64) {
+    if (spans == nullptr || text_bytes <= 0 || text_bytes > 0xffffffffll) { set_error("spans is NULL / text_bytes out of range"); return NSC_E_INVALID; }
+    for (int64_t i = 0; i < B; ++i)
+      if ((int64_t)spans[2 * i] + (int64_t)spans[2 * i + 1] > text_bytes) { set_error("candidate %lld: span outside the text", (long long)i); return NSC_E_INVALID; }
+  }
   if (in_host == nullptr || !oh.type_logits || !oh.pos || !oh.len_logits) { set_error("NULL input / logits pointer"); return NSC_E_INVALID; }
   if (u8) {
     if (meta_host == nullptr) { set_error("meta_host is NULL"); return NSC_E_INVALID; }
@@ -409,14 +418,49 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
     for (int i = 0; i < 2; ++i) NSC_CUDA_TRY(cudaMalloc(&m->hstage_out[i], out_per * cap));
     m->hstage_out_cap = cap;
   }
+  // the first slice is small: its host-to-device copy is the only one no kernel overlaps
+  const int64_t first = std::min<int64_t>(cap, 4096);
+  if (b64) {
+    // text range of every slice (candidates of a slice need not be in file order, but they are expected to be close)
+    size_t need = 0;
+    int64_t it = 0, n_prev = 0;
+    for (int64_t i = 0; i < B; i += n_prev, ++it) {
+      const int64_t n = std::min<int64_t>(it == 0 ? first : cap, B - i);
+      n_prev = n;
+      uint32_t lo = 0xffffffffu, hi = 0;
+      for (int64_t k = i; k < i + n; ++k) { lo = std::min(lo, spans[2 * k]); hi = std::max(hi, spans[2 * k] + spans[2 * k + 1]); }
+      need = std::max(need, (size_t)(hi - lo));
+    }
+    need += 64;
+    if (need > ((size_t)1 << 30)) { set_error("a slice of %lld candidates spans %zu bytes of text: stage the candidates in order", (long long)cap, need); return NSC_E_INVALID; }
+    if (m->ztext_bytes < need) {
+      NSC_CUDA_TRY(cudaDeviceSynchronize());
+      m->ztext_bytes = 0;
+      for (int i = 0; i < 2; ++i) { cudaFree(m->ztext[i]); m->ztext[i] = nullptr; }
+      need += need / 4;
+      for (int i = 0; i < 2; ++i) NSC_CUDA_TRY(cudaMalloc((void**)&m->ztext[i], need));
+      m->ztext_bytes = need;
+    }
+    if (m->zcap < cap) {
+      NSC_CUDA_TRY(cudaDeviceSynchronize());
+      m->zcap = 0;
+      for (int i = 0; i < 2; ++i) { cudaFree(m->zspans[i]); cudaFree(m->zdecl[i]); m->zspans[i] = nullptr; m->zdecl[i] = nullptr; }
+      if (m->zdecl_host) { cudaFreeHost(m->zdecl_host); m->zdecl_host = nullptr; }
+      for (int i = 0; i < 2; ++i) {
+        NSC_CUDA_TRY(cudaMalloc((void**)&m->zspans[i], (size_t)cap * 2 * sizeof(uint32_t)));
+        NSC_CUDA_TRY(cudaMalloc((void**)&m->zdecl[i], (size_t)(cap + 1) * sizeof(int)));
+        if (!m->zevent[i]) NSC_CUDA_TRY(cudaEventCreateWithFlags(&m->zevent[i], cudaEventDisableTiming));
+      }
+      NSC_CUDA_TRY(cudaMallocHost((void**)&m->zdecl_host, (size_t)2 * (cap + 1) * sizeof(int)));
+      m->zcap = cap;
+    }
+  }
   cudaStream_t s_in = m->hstream[0], s_cmp = m->hstream[1], s_out = m->hstream[2];
   if ((rc = ws_acquire(m, s_cmp)) != NSC_OK) return rc;
   cudaEvent_t* in_ready = &m->hevent[0];
   cudaEvent_t* in_free = &m->hevent[2];
   cudaEvent_t* out_ready = &m->hevent[4];
   cudaEvent_t* out_free = &m->hevent[6];
-  // the first slice is small: its host-to-device copy is the only one no kernel overlaps
-  const int64_t first = std::min<int64_t>(cap, 4096);
   // the slices are enqueued by a lambda so that EVERY failure leaves through the same exit: the copies into the caller's
   // host buffers that are already in flight are waited for and the workspace event is recorded before the error returns
   auto enqueue = [&]() -> int {
@@ -429,7 +473,44 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
       char* dmeta = din + ((in_per * cap + 255) / 256) * 256;
       char* dann = dmeta + ((meta_per * cap + 255) / 256) * 256;
       if (it >= 2) NSC_CUDA_TRY(cudaStreamWaitEvent(s_in, in_free[slot], 0));
-      NSC_CUDA_TRY(cudaMemcpyAsync(din, (const char*)in_host + i * in_per, in_per * n, cudaMemcpyHostToDevice, s_in));
+      if (b64) {
+        uint32_t lo = 0xffffffffu, hi = 0;
+        for (int64_t k = i; k < i + n; ++k) { lo = std::min(lo, spans[2 * k]); hi = std::max(hi, spans[2 * k] + spans[2 * k + 1]); }
+        NSC_CUDA_TRY(cudaMemcpyAsync(m->ztext[slot], (const char*)in_host + lo, hi - lo, cudaMemcpyHostToDevice, s_in));
+        NSC_CUDA_TRY(cudaMemcpyAsync(m->zspans[slot], spans + 2 * i, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s_in));
+        {
+          ProfScope prof(m, 13, s_in);
+          rc = inflate_b64_launch(m->ztext[slot], m->zspans[slot], lo, n, (uint8_t*)din, m->zdecl[slot], s_in);
+        }
+        if (rc != NSC_OK) return rc;
+        m->launches++;
+        int* dh = m->zdecl_host + (size_t)slot * (m->zcap + 1);
+        NSC_CUDA_TRY(cudaMemcpyAsync(dh, m->zdecl[slot], sizeof(int), cudaMemcpyDeviceToHost, s_in));
+        NSC_CUDA_TRY(cudaEventRecord(m->zevent[slot], s_in));
+        NSC_CUDA_TRY(cudaEventSynchronize(m->zevent[slot]));
+        const int nd = dh[0];
+        if (nd < 0 || nd > n) { set_error("device decoder: corrupt declined count %d", nd); return NSC_E_STATE; }
+        if (nd > 0) {
+          // the host decoder's verdict on what the device decoder declined: the bytes, or the reference's error
+          NSC_CUDA_TRY(cudaMemcpyAsync(dh + 1, m->zdecl[slot] + 1, (size_t)nd * sizeof(int), cudaMemcpyDeviceToHost, s_in));
+          NSC_CUDA_TRY(cudaStreamSynchronize(s_in));
+          std::vector<uint8_t> mat((size_t)kH * kW * kStoredCh);
+          for (int d = 0; d < nd; ++d) {
+            const int k = dh[1 + d];
+            if (k < 0 || k >= n) { set_error("device decoder: corrupt declined index %d", k); return NSC_E_STATE; }
+            char msg[160];
+            if (!tsv_inflate_field((const char*)in_host + spans[2 * (i + k)], spans[2 * (i + k) + 1], mat.data(), msg, sizeof msg)) {
+              set_error("candidate %lld: %s", (long long)(i + k), msg);
+              return NSC_E_INVALID;
+            }
+            NSC_CUDA_TRY(cudaMemcpyAsync(din + (size_t)k * in_per, mat.data(), in_per, cudaMemcpyHostToDevice, s_in));
+            NSC_CUDA_TRY(cudaStreamSynchronize(s_in));      // `mat` is reused
+          }
+          m->z_host_decoded += nd;
+        }
+      } else {
+        NSC_CUDA_TRY(cudaMemcpyAsync(din, (const char*)in_host + i * in_per, in_per * n, cudaMemcpyHostToDevice, s_in));
+      }
       if (u8) {
         NSC_CUDA_TRY(cudaMemcpyAsync(dmeta, meta_host + i * 3, meta_per * n, cudaMemcpyHostToDevice, s_in));
         if (ann_per) NSC_CUDA_TRY(cudaMemcpyAsync(dann, anns_host + i * na, ann_per * n, cudaMemcpyHostToDevice, s_in));
@@ -477,14 +558,24 @@ static int score_host(nsc_model* m, bool u8, const void* in_host, const int32_t*
 int nsc_score_host_f32(nsc_model* m, const float* x_host, int64_t B, float* type_logits, float* pos, float* len_logits,
                        float* type_prob, float* len_prob, int32_t* type_argmax, int32_t* len_argmax) {
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
-  return score_host(m, false, x_host, nullptr, nullptr, 0.f, B, o);
+  return score_host(m, 0, x_host, nullptr, nullptr, 0.f, B, o);
 }
 
 int nsc_score_host_u8(nsc_model* m, const uint8_t* matrices_host, const int32_t* meta_host, const float* anns255_host,
                       float coverage_thr, int64_t B, float* type_logits, float* pos, float* len_logits,
                       float* type_prob, float* len_prob, int32_t* type_argmax, int32_t* len_argmax) {
   Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
-  return score_host(m, true, matrices_host, meta_host, anns255_host, coverage_thr, B, o);
+  return score_host(m, 1, matrices_host, meta_host, anns255_host, coverage_thr, B, o);
+}
+
+int nsc_score_host_b64(nsc_model* m, const uint8_t* text_host, int64_t text_bytes, const uint32_t* spans_host, const int32_t* meta_host,
+                       const float* anns255_host, float coverage_thr, int64_t B, float* type_logits, float* pos, float* len_logits,
+                       float* type_prob, float* len_prob, int32_t* type_argmax, int32_t* len_argmax, int64_t* host_decoded) {
+  Outputs o{type_logits, pos, len_logits, type_prob, len_prob, type_argmax, len_argmax};
+  const int64_t before = m ? m->z_host_decoded : 0;
+  const int rc = score_host(m, 2, text_host, meta_host, anns255_host, coverage_thr, B, o, spans_host, text_bytes);
+  if (host_decoded) *host_decoded = m ? m->z_host_decoded - before : 0;
+  return rc;
 }
 
 int nsc_debug_internal(nsc_model* m, int which, float* out_dev, int64_t n, void* stream) {
@@ -535,7 +626,7 @@ int nsc_model_get_profile(nsc_model* m, double* ms, int64_t* launches) {
 const char* nsc_profile_slot_name(int slot) {
   static const char* names[NSC_PROF_SLOTS] = {
       "assemble", "conv1", "res0.conv_r1", "res0.conv_r2", "res1.conv_r1", "res1.conv_r2", "res2.conv_r1",
-      "res2.conv_r2", "res3.conv_r1", "res3.conv_r2", "fc_heads", "pack_input", "pool", "", "", ""};
+      "res2.conv_r2", "res3.conv_r1", "res3.conv_r2", "fc_heads", "pack_input", "pool", "inflate_b64", "", ""};
   return (slot >= 0 && slot < NSC_PROF_SLOTS) ? names[slot] : "";
 }
 
@@ -557,6 +648,13 @@ int nsc_model_destroy(nsc_model* m) {
   umma_free(m);
   free_workspace(m);
   for (int i = 0; i < 2; ++i) { cudaFree(m->hstage_in[i]); cudaFree(m->hstage_out[i]); }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(m->ztext[i]);
+    cudaFree(m->zspans[i]);
+    cudaFree(m->zdecl[i]);
+    if (m->zevent[i]) cudaEventDestroy(m->zevent[i]);
+  }
+  if (m->zdecl_host) cudaFreeHost(m->zdecl_host);
   for (int i = 0; i < 3; ++i) if (m->hstream[i]) cudaStreamDestroy(m->hstream[i]);
   for (int i = 0; i < 8; ++i) if (m->hevent[i]) cudaEventDestroy(m->hevent[i]);
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);

@@ -143,6 +143,16 @@ struct nsc_model {
   void* hstage_out[2] = {nullptr, nullptr};
   size_t hstage_in_bytes = 0;
   int64_t hstage_out_cap = 0;
+  // device decode of the TSV's base64 / zlib fields (nsc_score_host_b64): per slot the slice's text, its spans and the list of
+  // candidates the device decoder declined; the count of the list comes back through pinned host memory
+  uint8_t* ztext[2] = {nullptr, nullptr};
+  size_t ztext_bytes = 0;
+  uint32_t* zspans[2] = {nullptr, nullptr};
+  int* zdecl[2] = {nullptr, nullptr};
+  int64_t zcap = 0;
+  int* zdecl_host = nullptr;                                // pinned [2][zcap + 1]
+  cudaEvent_t zevent[2] = {nullptr, nullptr};
+  int64_t z_host_decoded = 0;                               // candidates handed to zlib on the host so far
   // orders successive uses of the (single) workspace across streams: every entry point waits for it on
   // its stream before touching the workspace and records it when its work is enqueued
   cudaEvent_t ws_event = nullptr;
@@ -208,6 +218,11 @@ double rz_compensation(int n_steps, double valid_share);
 // nsc_fc_umma.cu
 int fc_umma_upload_weights(nsc_model* m);
 int fc_umma_forward(nsc_model* m, uint16_t* const x[2], int64_t n, const Outputs& o, cudaStream_t s);
+// nsc_inflate_gpu.cu: base64 + zlib inflate of a slice of candidate matrices on the device (declined[0] = how many
+// candidates it left to the host, declined[1..] = which)
+int inflate_b64_launch(uint8_t* text, const uint32_t* spans, uint32_t origin, int64_t n, uint8_t* out, int* declined, cudaStream_t s);
+// nsc_tsv.cpp: the host decoder of one base64 field (dataloader.py:38-39); false + msg when it is not a 3680-byte zlib stream
+bool tsv_inflate_field(const char* p, size_t n, uint8_t* out, char* msg, size_t msg_cap);
 // nsc_assemble.cu
 int assemble_channels(nsc_model* m, const uint8_t* mat, const int32_t* meta, const float* anns255,
                       float coverage_thr, int64_t n, float* x_out, cudaStream_t s);

@@ -47,7 +47,14 @@ inline bool next_field(const char*& p, const char* end, Field* f) {
   while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
   if (p >= end) return false;
   const char* s = p;
-  while (p < end && *p != ' ' && *p != '\t' && *p != '\r') ++p;
+  // the end of the field = the first of the three separators; memchr, because the image field is ~1.3 KB
+  const char* e = (const char*)memchr(p, '\t', (size_t)(end - p));
+  if (!e) e = end;
+  const char* q = (const char*)memchr(p, ' ', (size_t)(e - p));
+  if (q) e = q;
+  q = (const char*)memchr(p, '\r', (size_t)(e - p));
+  if (q) e = q;
+  p = e;
   f->p = s;
   f->n = (size_t)(p - s);
   return true;
@@ -150,6 +157,11 @@ struct DecodeJob {
   int32_t* meta;
   float* anns255;
   int32_t* labels;
+  const int64_t* rows = nullptr;     // candidate indices instead of the range [first, first + n)
+  bool images = true;                // inflate the image fields (false: tags / annotations only)
+  uint8_t* text = nullptr;           // staging for the device decoder: the lines are copied here verbatim ...
+  size_t text_base = 0;              // ... text[0] = file offset text_base ...
+  uint32_t* spans = nullptr;         // ... and [n][2] = (offset in text, characters) of every image field
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
   std::string err;
@@ -169,7 +181,7 @@ void decode_range(DecodeJob* job) {
     if (k0 >= job->n || job->failed.load()) break;
     const int64_t k1 = std::min<int64_t>(job->n, k0 + 64);
     for (int64_t k = k0; k < k1; ++k) {
-      const size_t li = (size_t)(job->first + k);
+      const size_t li = (size_t)(job->rows ? job->rows[k] : job->first + k);
       const char* p = job->t->data + job->t->line_start[li];
       const char* end = job->t->data + job->t->line_start[li + 1];
       while (end > p && (end[-1] == '\n' || end[-1] == '\r')) --end;
@@ -205,8 +217,15 @@ void decode_range(DecodeJob* job) {
           else if (type_idx < 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: unknown variant type in tag", li); }
         }
       }
+      if (ok && job->text) {
+        // staging: the whole line travels (one copy, no scatter); the device decoder finds the image field through its span
+        const size_t l0 = job->t->line_start[li], l1 = job->t->line_start[li + 1];
+        memcpy(job->text + (l0 - job->text_base), job->t->data + l0, l1 - l0);
+        job->spans[2 * k] = (uint32_t)((size_t)(f[3].p - job->t->data) - job->text_base);
+        job->spans[2 * k + 1] = (uint32_t)f[3].n;
+      }
       // image: base64 -> zlib -> uint8[5,32,23]  (dataloader.py:38-39)
-      if (ok) {
+      if (ok && job->images) {
         const size_t need = f[3].n * 3 / 4 + 4 + 16;          // + the read-ahead slack of the word-wise bit buffer
         if (comp.size() < need) comp.resize(need);
         const int clen = b64_decode(f[3].p, f[3].n, comp.data(), comp.size() - 16);
@@ -228,7 +247,7 @@ void decode_range(DecodeJob* job) {
           }
         }
       }
-      if (ok) {
+      if (ok && job->meta) {
         job->meta[k * 3 + 0] = (int32_t)center;
         job->meta[k * 3 + 1] = (int32_t)tcov;
         job->meta[k * 3 + 2] = (int32_t)ncov;
@@ -263,6 +282,42 @@ void decode_range(DecodeJob* job) {
   inflateEnd(&zs);
 }
 
+}  // namespace
+
+namespace nsc {
+// One image field on the host, zlib's verdict (what the device decoder's declined candidates get): base64 -> zlib -> 3680 bytes
+bool tsv_inflate_field(const char* p, size_t n, uint8_t* out, char* msg, size_t msg_cap) {
+  std::vector<uint8_t> comp(n * 3 / 4 + 4 + 16);
+  const int clen = b64_decode(p, n, comp.data(), comp.size() - 16);
+  if (clen < 0) { snprintf(msg, msg_cap, "invalid base64"); return false; }
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit(&zs) != Z_OK) { snprintf(msg, msg_cap, "inflateInit failed"); return false; }
+  std::vector<uint8_t> tmp(kMatrixBytes + 8);
+  zs.next_in = comp.data();
+  zs.avail_in = (uInt)clen;
+  zs.next_out = tmp.data();
+  zs.avail_out = kMatrixBytes;
+  const int rc = ::inflate(&zs, Z_FINISH);
+  const bool ok = rc == Z_STREAM_END && zs.total_out == (uLong)kMatrixBytes;
+  inflateEnd(&zs);
+  if (!ok) { snprintf(msg, msg_cap, "zlib stream does not hold %d bytes", kMatrixBytes); return false; }
+  memcpy(out, tmp.data(), kMatrixBytes);
+  return true;
+}
+}  // namespace nsc
+
+namespace {
+int run_job(DecodeJob& job, int64_t n, int num_threads) {
+  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min<int>(nt, (int)((n + 63) / 64)));
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) th.emplace_back(decode_range, &job);
+  decode_range(&job);
+  for (auto& x : th) x.join();
+  if (job.failed.load()) { nsc::set_error("%s", job.err.empty() ? "TSV decode failed" : job.err.c_str()); return NSC_E_INVALID; }
+  return NSC_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -307,14 +362,42 @@ int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* 
   DecodeJob job;
   job.t = t; job.first = first; job.n = n; job.num_anns = num_anns;
   job.matrices = matrices; job.meta = meta; job.anns255 = anns255; job.labels = labels;
-  int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min<int>(nt, (int)((n + 63) / 64)));
-  std::vector<std::thread> th;
-  for (int i = 1; i < nt; ++i) th.emplace_back(decode_range, &job);
-  decode_range(&job);
-  for (auto& x : th) x.join();
-  if (job.failed.load()) { nsc::set_error("%s", job.err.empty() ? "TSV decode failed" : job.err.c_str()); return NSC_E_INVALID; }
-  return NSC_OK;
+  return run_job(job, n, num_threads);
+}
+
+int nsc_tsv_decode_rows(nsc_tsv* t, const int64_t* rows, int64_t n, uint8_t* matrices, int num_threads) {
+  if (!t || n < 0 || (n > 0 && (!rows || !matrices))) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  const int64_t count = nsc_tsv_count(t);
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= count) { nsc::set_error("candidate index %lld out of bounds", (long long)rows[i]); return NSC_E_INVALID; }
+  if (n == 0) return NSC_OK;
+  DecodeJob job;
+  job.t = t; job.first = 0; job.n = n; job.num_anns = 0;
+  job.matrices = matrices; job.meta = nullptr; job.anns255 = nullptr; job.labels = nullptr;
+  job.rows = rows;
+  return run_job(job, n, num_threads);
+}
+
+int64_t nsc_tsv_range_bytes(const nsc_tsv* t, int64_t first, int64_t n) {
+  if (!t || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) return -1;
+  return (int64_t)(t->line_start[(size_t)(first + n)] - t->line_start[(size_t)first]);
+}
+
+int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* text, int64_t text_cap, uint32_t* spans, int32_t* meta,
+                  float* anns255, int32_t* labels, int num_threads) {
+  if (!t || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("candidate range out of bounds"); return NSC_E_INVALID; }
+  if (n == 0) return NSC_OK;
+  if (!text || !spans || !meta || num_anns < 0 || (num_anns > 0 && !anns255)) { nsc::set_error("NULL output buffer"); return NSC_E_INVALID; }
+  const int64_t bytes = nsc_tsv_range_bytes(t, first, n);
+  if (bytes > text_cap || bytes > 0xffffffffll) { nsc::set_error("text buffer too small: %lld of %lld bytes", (long long)text_cap, (long long)bytes); return NSC_E_INVALID; }
+  DecodeJob job;
+  job.t = t; job.first = first; job.n = n; job.num_anns = num_anns;
+  job.matrices = nullptr; job.meta = meta; job.anns255 = anns255; job.labels = labels;
+  job.images = false;
+  job.text = text;
+  job.text_base = t->line_start[(size_t)first];
+  job.spans = spans;
+  return run_job(job, n, num_threads);
 }
 
 int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len) {

@@ -7,6 +7,8 @@ pinned torch CPU tensors (host buffers).  PyTorch is only the allocator and the 
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -136,6 +138,17 @@ class Engine:
         _lib.check(self.lib.nsc_score_host_u8(self.h, _lib.ptr(matrices), _lib.ptr(meta), _lib.ptr(anns255),
                                               float(coverage_thr), B, *[_lib.ptr(t) for t in outs]))
         return outs
+
+    def score_host_b64(self, text, spans, meta, anns255, coverage_thr, extras=True, out=None):
+        """The batch step from the TSV's own image fields (base64(zlib(matrix)) text; ``CandidateTSV.stage`` fills ``text``
+        and ``spans``): inflated on the device.  Returns (outs, host_decoded)."""
+        B = spans.shape[0]
+        outs = out if out is not None else self._host_out(B, extras, pin=False)
+        nhost = C.c_int64(0)
+        _lib.check(self.lib.nsc_score_host_b64(self.h, _lib.ptr(text), int(text.numel() if hasattr(text, "numel") else text.size),
+                                               _lib.ptr(spans), _lib.ptr(meta), _lib.ptr(anns255), float(coverage_thr), B,
+                                               *[_lib.ptr(t) for t in outs], C.byref(nhost)))
+        return outs, int(nhost.value)
 
     # -- per-kernel timing ------------------------------------------------------------------------
     def set_profile(self, on):

@@ -76,6 +76,27 @@ class CandidateTSV:
         c.labels = labels
         return c
 
+    def range_bytes(self, first=0, n=None):
+        """Bytes of the lines of candidates [first, first + n): the text a staged slice needs (+ 16 of slack)."""
+        n = len(self) - first if n is None else n
+        return int(self.lib.nsc_tsv_range_bytes(self.h, first, n))
+
+    def stage(self, first, n, text, spans, meta, anns255=None, labels=None):
+        """Everything of ``decode`` except the inflate, for ``Engine.score_host_b64``: copies the lines verbatim into ``text``
+        (uint8, >= range_bytes + 16), fills ``spans`` [n,2] uint32 (offset, characters of each image field), ``meta`` [n,3]
+        and ``anns255``."""
+        cap = int(text.numel() if hasattr(text, "numel") else text.size)
+        _lib.check(self.lib.nsc_tsv_stage(self.h, first, n, self.num_anns, _lib.ptr(text), cap, _lib.ptr(spans), _lib.ptr(meta),
+                                          _lib.ptr(anns255) if self.num_anns else None, _lib.ptr(labels), self.num_threads))
+
+    def decode_rows(self, rows):
+        """uint8 [len(rows),5,32,23]: the matrices of the listed candidates only."""
+        rows = np.ascontiguousarray(rows, np.int64)
+        m = np.empty((len(rows), 5, 32, 23), np.uint8)
+        if len(rows):
+            _lib.check(self.lib.nsc_tsv_decode_rows(self.h, rows.ctypes.data, len(rows), m.ctypes.data, self.num_threads))
+        return m
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.nsc_tsv_close(self.h)

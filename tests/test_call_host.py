@@ -114,14 +114,28 @@ class _OracleEngine:
         return out
 
 
+    def score_host_b64(self, text, spans, meta, anns255, coverage_thr, extras=True, out=None):
+        """The staged text of nsc_tsv_stage, inflated the reference's way (dataloader.py:38-39)."""
+        import base64
+        import zlib
+        raw = text.numpy().tobytes()
+        sp = spans.numpy().view(np.uint32)
+        m = np.stack([np.frombuffer(zlib.decompress(base64.b64decode(raw[o:o + n])), np.uint8).reshape(5, 32, 23) for o, n in sp])
+        return self.score_host_u8(torch.from_numpy(m), meta, anns255, coverage_thr, extras, out), 0
+
+
 class _OracleScorer:
     def __init__(self, ck, C):
         self.engine, self.C, self.coverage_thr = _OracleEngine(ck), C, float(ck["coverage_thr"])
 
 
+@pytest.mark.parametrize("host_decode", ["0", "1"])
 @pytest.mark.parametrize("name", ["std_v014", "std_wex"])
-def test_pipeline_reproduces_the_reference_vcf(tmp_path, built, name):
-    """Two reference-format TSVs -> C++ decoder -> (oracle scorer) -> PredTables -> VCF stage == the reference's files."""
+def test_pipeline_reproduces_the_reference_vcf(tmp_path, built, name, host_decode, monkeypatch):
+    """Two reference-format TSVs -> C++ decoder -> (oracle scorer) -> PredTables -> VCF stage == the reference's files.
+    host_decode 0: the staging form of the decoder (lines copied verbatim + spans of the image fields; the stand-in inflates
+    them with zlib where the product inflates them on the device); 1: the host-inflate form."""
+    monkeypatch.setenv("NSC_TSV_HOST_DECODE", host_decode)
     g = dict(np.load(os.path.join(GOLDEN, "vcf_%s.npz" % name), allow_pickle=False))
     ck = torch.load(os.path.join(GOLDEN, name + ".pth"), map_location="cpu", weights_only=True)
     tags = [str(t) for t in g["tags"]]
