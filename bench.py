@@ -507,11 +507,11 @@ def measure_tsv(args, rk, local_rank, n=524288):
             fp, npred = sc.call_tsv(path, batch=32768, num_threads=threads)
             nrec = len(dict(pred_vcf_records_none(npred, chroms)))
             ts.append(time.perf_counter() - t0)
-        return float(np.median(ts)), fp, npred, nrec
+        from neusomatic_b200.call import PIPELINE_TIMES
+        return float(np.median(ts)), fp, npred, nrec, {k: round(v, 4) for k, v in PIPELINE_TIMES.items()}
 
-    el_host, _, _, _ = run_mode(True)
-    times = None
-    el, final_preds, none_preds, n_none_records = run_mode(False)
+    el_host, _, _, _, stages_host = run_mode(True)
+    el, final_preds, none_preds, n_none_records, stages = run_mode(False)
     # device time of the inflate kernel itself (event brackets of the library), one more pass
     sc.engine.set_profile(True)
     sc.engine.get_profile()
@@ -532,9 +532,10 @@ def measure_tsv(args, rk, local_rank, n=524288):
                     "then the network) -> PredTable dictionaries + the none.vcf filter on arrays; stage, score and filing overlapped "
                     "(call.py:504-534 + 336-354)",
             "h2d_bytes_per_candidate": size / n,
+            "seconds": el, "stage_busy_seconds": stages,
             "inflate_kernel": {"ms_per_pass": infl_ms, "candidates_per_s": (n / (infl_ms * 1e-3)) if infl_ms > 0 else None,
                                "output_GBps": (n * 3680 / (infl_ms * 1e-3) / 1e9) if infl_ms > 0 else None},
-            "host_inflate": {"value": n / el_host, "unit": "candidates/s",
+            "host_inflate": {"value": n / el_host, "unit": "candidates/s", "seconds": el_host, "stage_busy_seconds": stages_host,
                              "what": "the same call with NSC_TSV_HOST_DECODE=1: inflate on the host threads -> nsc_score_host_u8"},
             "cpu_reference_chain": None if cpu_rate is None else {
                 "value": cpu_rate, "unit": "candidates/s", "kind": "port", "cores": threads,

@@ -256,6 +256,9 @@ int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t 
 /* lens [n,2] int32 = (len(ref), len(alt)) of the tags of candidates [first, first + n): what call.py:343-350
  * (pred_vcf_records_none) branches on, so that the none.vcf filter can run on whole arrays */
 int nsc_tsv_allele_lens(const nsc_tsv* t, int64_t first, int64_t n, int32_t* lens);
+/* both of the above in one pass over the lines (the filing stage of the call pipeline); the tags are copied without their
+ * directory part (path_.split("/")[-1], call.py:88) */
+int nsc_tsv_tags_lens(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t cap, int64_t* needed, int32_t* lens);
 /* Test hook: inflates ONE zlib stream (RFC 1950) of exactly out_len bytes with the decoder's own fast inflate
  * (csrc/nsc_inflate.h; NSC_E_STATE when it declines the stream and the decoder would fall back to zlib) or, use_zlib != 0,
  * with zlib itself (NSC_E_INVALID on a malformed stream). */

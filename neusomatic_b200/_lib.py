@@ -62,6 +62,7 @@ SIGNATURES = {
     "nsc_tsv_tag": (_i32, [_vp, _i64, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "nsc_tsv_tags": (_i32, [_vp, _i64, _i64, _vp, _i64, C.POINTER(_i64)]),
     "nsc_tsv_allele_lens": (_i32, [_vp, _i64, _i64, _vp]),
+    "nsc_tsv_tags_lens": (_i32, [_vp, _i64, _i64, _vp, _i64, C.POINTER(_i64), _vp]),
     "nsc_debug_inflate": (_i32, [_vp, _i64, _vp, _i64, _i32]),
     "nsc_debug_inflate_b64": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nsc_tsv_close": (_i32, [_vp]),

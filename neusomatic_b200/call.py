@@ -25,6 +25,7 @@ import concurrent.futures
 import gc
 import logging
 import os
+import time
 
 import numpy as np
 import torch
@@ -127,7 +128,11 @@ class PredTable(collections.abc.Mapping):
         if len(paths) == 0:
             return
         f32 = lambda a: np.asarray(a, np.float32)
+        base = len(self._paths)
         self._paths.extend(paths)
+        if self._indexed == base:            # keep the tag -> row index current (a later duplicate replaces the earlier row)
+            self._index.update(zip(paths, range(base, base + len(paths))))
+            self._indexed = base + len(paths)
         self._parts.append((np.asarray(a1, np.int64), f32(o2).reshape(len(paths), -1), np.asarray(a3, np.int64),
                             np.round(f32(p1), 4), np.round(f32(p3), 4), np.round(f32(o1), 4), np.round(f32(o3), 4),
                             None if lens is None else np.asarray(lens, np.int32)))
@@ -469,10 +474,15 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
     num_anns = scorers[0].C - 26
     device_inflate = os.environ.get("NSC_TSV_HOST_DECODE", "0") in ("", "0")
     tsvs, slices = {}, []
+    times = {"open": 0.0, "decode": 0.0, "tags": 0.0, "score": 0.0, "file": 0.0, "total": 0.0}      # busy seconds per stage (PIPELINE_TIMES)
+    t_begin = time.perf_counter()
+
     try:
         for path, first, count in pieces:
             if path not in tsvs:
+                t0 = time.perf_counter()
                 tsvs[path] = CandidateTSV(path, num_anns=num_anns, num_threads=num_threads)
+                times["open"] += time.perf_counter() - t0
             n = len(tsvs[path]) - first if count is None else count
             for f0 in range(first, first + n, batch):
                 slices.append((path, f0, min(batch, first + n - f0)))
@@ -501,12 +511,16 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             path, f0, n = slices[k]
             slot = slots[k % len(slots)]
             t = tsvs[path]
-            if device_inflate:
-                t.stage(f0, n, slot.text, slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n])
-                return t.range_bytes(f0, n)
-            t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
-                                 "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
-            return None
+            t0 = time.perf_counter()
+            try:
+                if device_inflate:
+                    t.stage(f0, n, slot.text, slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n])
+                    return t.range_bytes(f0, n)
+                t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
+                                     "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
+                return None
+            finally:
+                times["decode"] += time.perf_counter() - t0
 
         def score(k, fdec):
             nbytes = fdec.result()
@@ -514,27 +528,42 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             slot = slots[k % len(slots)]
             sc = scorers[k % len(scorers)]
             outs = [None if t is None else t[:n] for t in slot.out]
+            t0 = time.perf_counter()
             if device_inflate:
                 sc.engine.score_host_b64(slot.text[:nbytes], slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
                                          sc.coverage_thr, extras=True, out=outs)
-                return outs
-            sc.engine.score_host_u8(slot.matrices[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
-                                    sc.coverage_thr, extras=True, out=outs)
+            else:
+                sc.engine.score_host_u8(slot.matrices[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
+                                        sc.coverage_thr, extras=True, out=outs)
+            times["score"] += time.perf_counter() - t0
             return outs
 
-        def file_slice(k, fsc):
-            # the tag strings and allele lengths are read here, off the decoder thread: the decode stage is the slowest
+        def read_tags(k, wait_for):
+            # the tag strings (the dictionaries' keys) and allele lengths of a slice, on a thread of their own: one C pass over
+            # the lines (GIL released) and one split
+            if wait_for is not None:
+                wait_for.result()
             path, f0, n = slices[k]
-            tags, lens = tsvs[path].tags(f0, n), tsvs[path].allele_lens(f0, n)
+            t0 = time.perf_counter()
+            try:
+                return tsvs[path].tags_lens(f0, n)
+            finally:
+                times["tags"] += time.perf_counter() - t0
+
+        def file_slice(k, fsc, ftags):
+            path, f0, n = slices[k]
+            tags, lens = ftags.result()
             outs = fsc.result()
+            t0 = time.perf_counter()
             slot = slots[k % len(slots)]
             names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
             r = {nm: t.numpy() for nm, t in zip(names, outs)}
             mats = (lambda rows: tsvs[path].decode_rows(f0 + np.asarray(rows, np.int64))) if device_inflate else slot.matrices[:n].numpy()
             _split_into_tables(r, tags, lens, mats, slot.meta[:n, 0].numpy(), final_preds, none_preds, true_path)
+            times["file"] += time.perf_counter() - t0
 
         TPE = concurrent.futures.ThreadPoolExecutor
-        with TPE(1) as dec_ex, TPE(1) as file_ex:
+        with TPE(1) as dec_ex, TPE(1) as file_ex, TPE(1) as tag_ex:
             sc_ex = [TPE(1) for _ in scorers]
             try:
                 filed = []
@@ -542,7 +571,8 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
                     wait_for = filed[k - len(slots)] if k >= len(slots) else None
                     fd = dec_ex.submit(decode, k, wait_for)
                     fs = sc_ex[k % len(scorers)].submit(score, k, fd)
-                    filed.append(file_ex.submit(file_slice, k, fs))
+                    ft = tag_ex.submit(read_tags, k, wait_for)
+                    filed.append(file_ex.submit(file_slice, k, fs, ft))
                 for f in filed:
                     f.result()
             finally:
@@ -551,6 +581,12 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
     finally:
         for t in tsvs.values():
             t.close()
+        times["total"] = time.perf_counter() - t_begin
+        PIPELINE_TIMES.clear()
+        PIPELINE_TIMES.update(times)
+
+
+PIPELINE_TIMES = {}      # busy seconds per stage of the last run_tsv_pipeline call (waits for the neighbouring stages excluded)
 
 
 def plan_call_groups(counts, max_load_candidates):

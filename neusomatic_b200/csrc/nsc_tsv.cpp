@@ -17,6 +17,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -44,15 +45,18 @@ struct Field { const char* p; size_t n; };
 
 // split on runs of whitespace (python str.split() semantics used by dataloader.py:44)
 inline bool next_field(const char*& p, const char* end, Field* f) {
-  while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+  while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
   if (p >= end) return false;
   const char* s = p;
-  // the end of the field = the first of the three separators; memchr, because the image field is ~1.3 KB
+  // the end of the field = the first separator (a line's range runs to the start of the next non-blank line, so it may hold
+  // newlines of blank lines); memchr, because the image field is ~1.3 KB
   const char* e = (const char*)memchr(p, '\t', (size_t)(end - p));
   if (!e) e = end;
   const char* q = (const char*)memchr(p, ' ', (size_t)(e - p));
   if (q) e = q;
   q = (const char*)memchr(p, '\r', (size_t)(e - p));
+  if (q) e = q;
+  q = (const char*)memchr(p, '\n', (size_t)(e - p));
   if (q) e = q;
   p = e;
   f->p = s;
@@ -338,15 +342,41 @@ int nsc_tsv_open(nsc_tsv** out, const char* path) {
     t->data = (const char*)p;
     madvise(p, t->size, MADV_SEQUENTIAL);
   }
-  size_t pos = 0;
-  while (pos < t->size) {
-    const char* nl = (const char*)memchr(t->data + pos, '\n', t->size - pos);
-    const size_t e = nl ? (size_t)(nl - t->data) + 1 : t->size;
-    bool blank = true;
-    for (size_t i = pos; i < e && blank; ++i) blank = t->data[i] == '\n' || t->data[i] == '\r' || t->data[i] == ' ' || t->data[i] == '\t';
-    if (!blank) t->line_start.push_back(pos);
-    pos = e;
+  // line index: the file is cut into pieces at arbitrary offsets, each piece's thread lists the non-blank lines that START in
+  // it (a line starts at 0 or after a '\n'), and the lists are joined in order
+  const size_t piece = (size_t)32 << 20;
+  const int np = (int)std::max<size_t>(1, (t->size + piece - 1) / piece);
+  std::vector<std::vector<size_t>> found((size_t)np);
+  auto scan = [&](int pi) {
+    const size_t lo = (size_t)pi * piece, hi = std::min(t->size, lo + piece);
+    size_t pos = lo;
+    if (lo > 0 && t->data[lo - 1] != '\n') {          // inside a line that started in an earlier piece
+      const char* nl = (const char*)memchr(t->data + lo, '\n', t->size - lo);
+      pos = nl ? (size_t)(nl - t->data) + 1 : t->size;
+    }
+    std::vector<size_t>& v = found[(size_t)pi];
+    while (pos < hi) {
+      const char* nl = (const char*)memchr(t->data + pos, '\n', t->size - pos);
+      const size_t e = nl ? (size_t)(nl - t->data) + 1 : t->size;
+      bool blank = true;
+      for (size_t i = pos; i < e && blank; ++i) blank = t->data[i] == '\n' || t->data[i] == '\r' || t->data[i] == ' ' || t->data[i] == '\t';
+      if (!blank) v.push_back(pos);
+      pos = e;
+    }
+  };
+  {
+    const int nt = std::max(1, std::min<int>(np, (int)std::thread::hardware_concurrency()));
+    std::atomic<int> next{0};
+    auto worker = [&]() { for (int pi = next.fetch_add(1); pi < np; pi = next.fetch_add(1)) scan(pi); };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(worker);
+    worker();
+    for (auto& x : th) x.join();
   }
+  size_t total = 0;
+  for (auto& v : found) total += v.size();
+  t->line_start.reserve(total + 1);
+  for (auto& v : found) t->line_start.insert(t->line_start.end(), v.begin(), v.end());
   t->line_start.push_back(t->size);
   *out = t;
   return NSC_OK;
@@ -426,6 +456,45 @@ int nsc_tsv_tags(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t 
       buf[o + f.n] = '\n';
     }
     o += (int64_t)f.n + 1;
+  }
+  *needed = o;
+  if (buf != nullptr && o > cap) { nsc::set_error("tag buffer too small: %lld of %lld bytes", (long long)cap, (long long)o); return NSC_E_INVALID; }
+  return NSC_OK;
+}
+
+int nsc_tsv_tags_lens(const nsc_tsv* t, int64_t first, int64_t n, char* buf, int64_t cap, int64_t* needed, int32_t* lens) {
+  if (!t || !needed || !lens || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("bad argument"); return NSC_E_INVALID; }
+  int64_t o = 0;
+  for (int64_t i = first; i < first + n; ++i) {
+    const char* p = t->data + t->line_start[(size_t)i];
+    const char* end = t->data + t->line_start[(size_t)i + 1];
+    Field f;
+    for (int k = 0; k < 3; ++k)
+      if (!next_field(p, end, &f)) { nsc::set_error("line %lld: no tag field", (long long)i); return NSC_E_INVALID; }
+    const char* tb = f.p;
+    const char* te = f.p + f.n;
+    for (const char* q = te; q > tb; --q)
+      if (q[-1] == '/') { tb = q; break; }          // path_.split("/")[-1]
+    const int64_t tn = (int64_t)(te - tb);
+    if (buf != nullptr && o + tn + 1 <= cap) {
+      memcpy(buf + o, tb, (size_t)tn);
+      buf[o + tn] = '\n';
+    }
+    o += tn + 1;
+    int field = 0;
+    const char* fs = tb;
+    int32_t rl = -1, al = -1;
+    for (const char* q = tb; q <= te; ++q) {
+      if (q == te || *q == '.') {
+        if (field == 2) rl = (int32_t)(q - fs);
+        if (field == 3) { al = (int32_t)(q - fs); break; }
+        ++field;
+        fs = q + 1;
+      }
+    }
+    if (rl < 0 || al < 0) { nsc::set_error("line %lld: tag does not have 9 fields", (long long)i); return NSC_E_INVALID; }
+    lens[(i - first) * 2] = rl;
+    lens[(i - first) * 2 + 1] = al;
   }
   *needed = o;
   if (buf != nullptr && o > cap) { nsc::set_error("tag buffer too small: %lld of %lld bytes", (long long)cap, (long long)o); return NSC_E_INVALID; }

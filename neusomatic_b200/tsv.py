@@ -44,6 +44,22 @@ class CandidateTSV:
         _lib.check(rc)
         return buf[:need.value - 1].tobytes().decode().split("\n")
 
+    def tags_lens(self, first=0, n=None):
+        """(tags without their directory part, int32 [n,2] allele lengths) in one pass over the lines."""
+        n = len(self) - first if n is None else n
+        lens = np.empty((n, 2), np.int32)
+        if n == 0:
+            return [], lens
+        need = C.c_int64()
+        cap = 96 * n + 64
+        buf = np.empty(cap, np.uint8)
+        rc = self.lib.nsc_tsv_tags_lens(self.h, first, n, buf.ctypes.data, cap, C.byref(need), lens.ctypes.data)
+        if rc != 0 and need.value > cap:
+            buf = np.empty(need.value, np.uint8)
+            rc = self.lib.nsc_tsv_tags_lens(self.h, first, n, buf.ctypes.data, need.value, C.byref(need), lens.ctypes.data)
+        _lib.check(rc)
+        return buf[:need.value - 1].tobytes().decode().split("\n"), lens
+
     def allele_lens(self, first=0, n=None):
         """int32 [n,2] = (len(ref), len(alt)) of the candidates' tags (what the none.vcf filter branches on, call.py:343-350)."""
         n = len(self) - first if n is None else n

@@ -134,3 +134,72 @@ def test_empty_and_malformed_files(tmp_path, built):
             t.decode()
     with pytest.raises(NscError):
         CandidateTSV(str(tmp_path / "missing.tsv"))
+
+
+def test_tags_lens_one_pass_equals_the_two_calls(tmp_path, built):
+    from neusomatic_b200.tsv import CandidateTSV
+    cand = synth.structured_pileups(64, seed=10)
+    p = str(tmp_path / "t.tsv")
+    with open(p, "w") as f:
+        for i in range(64):
+            tag = ("work/dataset/" if i % 3 == 0 else "") + cand.tags[i]            # path_.split("/")[-1], call.py:88
+            f.write(oracle.encode_tsv_line(i, tag, cand.matrices[i]))
+    t = CandidateTSV(p)
+    tags, lens = t.tags_lens()
+    assert tags == list(cand.tags)
+    np.testing.assert_array_equal(lens, t.allele_lens())
+    np.testing.assert_array_equal(lens, [[len(x.split(".")[2]), len(x.split(".")[3])] for x in cand.tags])
+    tags, lens = t.tags_lens(7, 5)
+    assert tags == list(cand.tags[7:12]) and lens.shape == (5, 2)
+    assert t.tags_lens(3, 0)[0] == []
+    t.close()
+
+
+def test_line_index_across_pieces_and_staging(tmp_path, built):
+    """The line index is built piecewise by threads (32 MB pieces): a file of several pieces with blank lines, CRLF endings
+    and no final newline indexes like a sequential scan; nsc_tsv_stage copies the lines verbatim and its spans delimit the
+    image fields; nsc_tsv_decode_rows returns the listed candidates' matrices."""
+    import base64
+    import zlib
+    from neusomatic_b200.tsv import CandidateTSV
+    cand = synth.structured_pileups(256, seed=12)
+    lines = [oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i]) for i in range(256)]
+    n = 70000                                                   # ~ 90 MB: three pieces
+    p = str(tmp_path / "big.tsv")
+    with open(p, "w", newline="") as f:
+        for i in range(n):
+            ln = lines[i % 256]
+            if i % 1000 == 17:
+                f.write("\n   \t\n")                            # blank lines are skipped (dataloader.py: `if not line.strip()`)
+            if i % 5000 == 3:
+                ln = ln[:-1] + "\r\n"
+            if i == n - 1:
+                ln = ln[:-1]                                    # no newline at the end of the file
+            f.write(ln)
+    t = CandidateTSV(p, num_threads=4)
+    assert len(t) == n
+    for first in (0, 24000, 26000, 50000, n - 300):             # around the piece boundaries and at both ends
+        got = t.decode(first, 300)
+        want = cand.matrices[(first + np.arange(300)) % 256]
+        np.testing.assert_array_equal(got.matrices, want)
+        assert got.tags == [cand.tags[(first + i) % 256] for i in range(300)]
+    first, m = 4990, 1200
+    text = np.zeros(t.range_bytes(first, m) + 16, np.uint8)
+    spans, meta = np.zeros((m, 2), np.uint32), np.zeros((m, 3), np.int32)
+    t.stage(first, m, text, spans, meta)
+    raw = open(p, "rb").read()
+    start = raw.index(lines[first % 256].encode()[:40])
+    assert text[:t.range_bytes(first, m)].tobytes() in raw
+    for k in (0, 1, 13, 555, m - 1):
+        o, ln = int(spans[k, 0]), int(spans[k, 1])
+        mat = np.frombuffer(zlib.decompress(base64.b64decode(text[o:o + ln].tobytes())), np.uint8).reshape(5, 32, 23)
+        np.testing.assert_array_equal(mat, cand.matrices[(first + k) % 256])
+        i = (first + k) % 256
+        assert list(meta[k]) == [cand.center[i], cand.tumor_cov[i], cand.normal_cov[i]]
+    rows = np.array([5, 69999, 25000, 5, 31234], np.int64)
+    np.testing.assert_array_equal(t.decode_rows(rows), cand.matrices[rows % 256])
+    with pytest.raises(Exception):
+        t.decode_rows([n])
+    with pytest.raises(Exception):
+        t.stage(0, 10, np.zeros(100, np.uint8), spans, meta)   # text buffer too small
+    t.close()
