@@ -513,8 +513,9 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             t = tsvs[path]
             t0 = time.perf_counter()
             try:
-                if device_inflate:
-                    t.stage(f0, n, slot.text, slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n])
+                if device_inflate:        # the staging threads gather the tag strings and allele lengths in the same pass
+                    slot.tags = t.stage(f0, n, slot.text, slot.spans[:n], slot.meta[:n], None if slot.anns is None else slot.anns[:n],
+                                        with_tags=True)
                     return t.range_bytes(f0, n)
                 t.decode(f0, n, out={"matrices": slot.matrices[:n].numpy(), "meta": slot.meta[:n].numpy(),
                                      "anns255": None if slot.anns is None else slot.anns[:n].numpy()}, with_tags=False)
@@ -541,6 +542,8 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
         def read_tags(k, wait_for):
             # the tag strings (the dictionaries' keys) and allele lengths of a slice, on a thread of their own: one C pass over
             # the lines (GIL released) and one split
+            if device_inflate:
+                return None                      # came with the staging pass (slot.tags)
             if wait_for is not None:
                 wait_for.result()
             path, f0, n = slices[k]
@@ -552,8 +555,9 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
 
         def file_slice(k, fsc, ftags):
             path, f0, n = slices[k]
-            tags, lens = ftags.result()
-            outs = fsc.result()
+            tl = ftags.result()
+            outs = fsc.result()                  # (after the slice's decode stage: slot.tags is this slice's)
+            tags, lens = tl if tl is not None else slots[k % len(slots)].tags
             t0 = time.perf_counter()
             slot = slots[k % len(slots)]
             names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]

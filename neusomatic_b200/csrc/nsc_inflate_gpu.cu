@@ -24,10 +24,10 @@
 namespace nsc {
 namespace {
 
-constexpr int kZWarps = 8;                        // candidates per CTA
+constexpr int kZWarps = 10;                       // candidates per CTA (3 CTAs = 30 warps per SM: shared memory is the limit)
 constexpr int kZOut = kH * kW * kStoredCh;        // 3680
-constexpr int kZOutPad = 3712;
-constexpr int kLitBits = 10, kDistBits = 9, kPreBits = 7;
+constexpr int kZOutPad = 3680;
+constexpr int kLitBits = 10, kDistBits = 8, kPreBits = 7;
 constexpr uint32_t kFull = 0xffffffffu;
 
 __constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -48,23 +48,33 @@ struct __align__(16) ZWarp {
   uint8_t prelen[32];
 };
 
+// Bit reader: two 32-bit words of the stream in registers, the next one prefetched, a bit position into the first; the next
+// 32 bits are one funnel shift away.  At most 32 bits may be consumed between two calls of norm().
 struct Bits {
-  uint64_t buf;
-  int bits;
-  uint32_t wi, nw;
+  uint32_t w0, w1, wn;
+  uint32_t pos;                 // bits of w0 already consumed (< 32 after norm)
+  uint32_t wi, nw;              // index of the word in wn, words of the stream
   const uint32_t* in;
 };
-
-__device__ __forceinline__ void refill(Bits& b) {
-  if (b.bits <= 32) {
-    const uint32_t w = b.wi < b.nw ? b.in[b.wi] : 0u;
+__device__ __forceinline__ uint32_t zword(const Bits& b, uint32_t i) { return i < b.nw ? b.in[i] : 0u; }
+__device__ __forceinline__ void zseek(Bits& b, uint32_t word, uint32_t bit) {
+  b.w0 = zword(b, word);
+  b.w1 = zword(b, word + 1);
+  b.wn = zword(b, word + 2);
+  b.wi = word + 2;
+  b.pos = bit;
+}
+__device__ __forceinline__ void norm(Bits& b) {
+  if (b.pos >= 32u) {
+    b.pos -= 32u;
+    b.w0 = b.w1;
+    b.w1 = b.wn;
     ++b.wi;
-    b.buf |= (uint64_t)w << b.bits;
-    b.bits += 32;
+    b.wn = zword(b, b.wi);      // consumed two refills from now: its latency is off the decoding chain
   }
 }
-__device__ __forceinline__ uint32_t peek(const Bits& b, int n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
-__device__ __forceinline__ void drop(Bits& b, int n) { b.buf >>= n; b.bits -= n; }
+__device__ __forceinline__ uint32_t window(const Bits& b) { return __funnelshift_r(b.w0, b.w1, b.pos); }
+__device__ __forceinline__ uint32_t zbitpos(const Bits& b) { return (b.wi - 2u) * 32u + b.pos; }
 
 __device__ __forceinline__ int sextet(uint32_t c) {
   int v = -1;
@@ -131,7 +141,7 @@ __device__ int build_tables(const uint8_t* lens, int n, E* tab, uint16_t* sorted
 }
 
 // bit-by-bit canonical decoding (codes longer than the look-up table); -1 = no such code
-__device__ __forceinline__ int walk(uint64_t buf, const uint16_t* cnt, const uint16_t* sorted, int* len) {
+__device__ __forceinline__ int walk(uint32_t buf, const uint16_t* cnt, const uint16_t* sorted, int* len) {
   int code = 0, first = 0, index = 0;
   for (int l = 1; l <= 15; ++l) {
     code |= (int)(buf & 1);
@@ -196,40 +206,39 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
   }
   int op = 0;
   Bits b;
-  b.buf = 0;
-  b.bits = 0;
-  b.wi = 0;
   b.nw = (clen + 3) >> 2;
   b.in = reinterpret_cast<const uint32_t*>(bin);
+  b.w0 = b.w1 = b.wn = 0;
+  b.wi = 2;
+  b.pos = 0;
   if (ok) {
-    refill(b);
-    const uint32_t cmf = peek(b, 8), flg = (uint32_t)(b.buf >> 8) & 255u;
-    drop(b, 16);
+    zseek(b, 0, 0);
+    const uint32_t w = window(b), cmf = w & 255u, flg = (w >> 8) & 255u;
+    b.pos += 16;
     if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u)) ok = false;
   }
   bool last = false;
   while (ok && !last) {
-    refill(b);
-    last = peek(b, 1) != 0;
-    const uint32_t type = (uint32_t)(b.buf >> 1) & 3u;
-    drop(b, 3);
+    norm(b);
+    uint32_t w = window(b);
+    last = (w & 1u) != 0;
+    const uint32_t type = (w >> 1) & 3u;
+    b.pos += 3;
     if (type == 0) {
       // stored block: to the byte boundary, LEN / NLEN, raw bytes
-      drop(b, b.bits & 7);
-      refill(b);
-      const uint32_t len = peek(b, 16), nlen = (uint32_t)(b.buf >> 16) & 0xffffu;
-      drop(b, 32);
-      const uint32_t p = (b.wi * 32u - (uint32_t)b.bits) >> 3;
+      b.pos = (b.pos + 7u) & ~7u;
+      norm(b);
+      w = window(b);
+      const uint32_t len = w & 0xffffu, nlen = w >> 16;
+      b.pos += 32;
+      norm(b);
+      const uint32_t p = zbitpos(b) >> 3;
       if ((len ^ nlen) != 0xffffu || p + len + 4 > clen || (uint32_t)op + len > (uint32_t)kZOut) { ok = false; break; }
       __syncwarp();
       for (uint32_t j = lane; j < len; j += 32) z.out[op + j] = bin[p + j];
       op += (int)len;
       const uint32_t q = p + len;
-      b.wi = q >> 2;
-      b.buf = 0;
-      b.bits = 0;
-      refill(b);
-      drop(b, (int)(q & 3u) * 8);
+      zseek(b, q >> 2, (q & 3u) * 8u);
       continue;
     }
     if (type == 3) { ok = false; break; }
@@ -240,28 +249,32 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
       build_tables<uint16_t, kLitBits, 4>(z.lens, 288, z.lit, z.lit_sorted, z.cnt[0], lane);
       build_tables<uint16_t, kDistBits, 4>(z.lens + 288, 32, z.dist, z.dist_sorted, z.cnt[1], lane);
     } else {
-      const uint32_t hlit = peek(b, 5) + 257u, hdist = ((uint32_t)(b.buf >> 5) & 31u) + 1u, hclen = ((uint32_t)(b.buf >> 10) & 15u) + 4u;
-      drop(b, 14);
+      norm(b);
+      w = window(b);
+      const uint32_t hlit = (w & 31u) + 257u, hdist = ((w >> 5) & 31u) + 1u, hclen = ((w >> 10) & 15u) + 4u;
+      b.pos += 14;
       if (hlit > 286u || hdist > 30u) { ok = false; break; }
       if (lane < 19) z.prelen[lane] = 0;
       __syncwarp();
       for (uint32_t i = 0; i < hclen; ++i) {
-        refill(b);
-        if (lane == 0) z.prelen[c_order[i]] = (uint8_t)peek(b, 3);
-        drop(b, 3);
+        norm(b);
+        if (lane == 0) z.prelen[c_order[i]] = (uint8_t)(window(b) & 7u);
+        b.pos += 3;
       }
       __syncwarp();
       if (build_tables<uint8_t, kPreBits, 3>(z.prelen, 19, z.pre, z.dist_sorted, z.cnt[1], lane) != 0) { ok = false; break; }
       const uint32_t total = hlit + hdist;
       uint32_t nl = 0, prev = 0;
       while (nl < total) {
-        refill(b);
-        const uint32_t e = z.pre[peek(b, kPreBits)];
-        const int l = (int)(e & 7u);
+        norm(b);
+        w = window(b);
+        const uint32_t e = z.pre[w & ((1u << kPreBits) - 1u)];
+        const uint32_t l = e & 7u;
         if (l == 0) { ok = false; break; }
-        drop(b, l);
+        w >>= l;
         const uint32_t sym = e >> 3;
         if (sym < 16u) {
+          b.pos += l;
           if (lane == 0) z.lens[nl] = (uint8_t)sym;
           prev = sym;
           ++nl;
@@ -270,14 +283,14 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
           if (sym == 16u) {
             if (nl == 0) { ok = false; break; }
             val = prev;
-            rep = 3u + peek(b, 2);
-            drop(b, 2);
+            rep = 3u + (w & 3u);
+            b.pos += l + 2;
           } else if (sym == 17u) {
-            rep = 3u + peek(b, 3);
-            drop(b, 3);
+            rep = 3u + (w & 7u);
+            b.pos += l + 3;
           } else {
-            rep = 11u + peek(b, 7);
-            drop(b, 7);
+            rep = 11u + (w & 127u);
+            b.pos += l + 7;
           }
           if (nl + rep > total) { ok = false; break; }
           for (uint32_t j = lane; j < rep; j += 32) z.lens[nl + j] = (uint8_t)val;
@@ -295,15 +308,18 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
     }
     // ---- symbols ----------------------------------------------------------------------------------------------------------
     for (;;) {
-      if (b.wi > b.nw + 2) { ok = false; break; }          // ran past the input
-      refill(b);
-      uint32_t e = z.lit[peek(b, kLitBits)];
+      if (b.pos >= 32u) {
+        norm(b);
+        if (b.wi > b.nw + 4) { ok = false; break; }          // ran past the input
+      }
+      w = window(b);
+      uint32_t e = z.lit[w & ((1u << kLitBits) - 1u)];
       int l = (int)(e & 15u), sym = (int)(e >> 4);
       if (l == 0) {
-        sym = walk(b.buf, z.cnt[0], z.lit_sorted, &l);
+        sym = walk(w, z.cnt[0], z.lit_sorted, &l);
         if (sym < 0) { ok = false; break; }
       }
-      drop(b, l);
+      b.pos += (uint32_t)l;
       if (sym < 256) {
         if (op >= kZOut) { ok = false; break; }
         if (lane == 0) z.out[op] = (uint8_t)sym;
@@ -313,22 +329,24 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
       if (sym == 256) break;
       sym -= 257;
       if (sym > 28 || no_dist) { ok = false; break; }
+      w >>= l;
       int eb = c_lext[sym];
-      const int len = c_lbase[sym] + (int)peek(b, eb);
-      drop(b, eb);
-      refill(b);
-      e = z.dist[peek(b, kDistBits)];
+      const int len = c_lbase[sym] + (int)(w & ((1u << eb) - 1u));
+      b.pos += (uint32_t)eb;
+      norm(b);
+      w = window(b);
+      e = z.dist[w & ((1u << kDistBits) - 1u)];
       l = (int)(e & 15u);
       int ds = (int)(e >> 4);
       if (l == 0) {
-        ds = walk(b.buf, z.cnt[1], z.dist_sorted, &l);
+        ds = walk(w, z.cnt[1], z.dist_sorted, &l);
         if (ds < 0) { ok = false; break; }
       }
-      drop(b, l);
       if (ds > 29) { ok = false; break; }
+      w >>= l;
       eb = c_dext[ds];
-      const int dist = c_dbase[ds] + (int)peek(b, eb);
-      drop(b, eb);
+      const int dist = c_dbase[ds] + (int)(w & ((1u << eb) - 1u));
+      b.pos += (uint32_t)(l + eb);
       if (dist > op || op + len > kZOut) { ok = false; break; }
       __syncwarp();
       const int from = op - dist;
@@ -346,7 +364,8 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
   __syncwarp();
   if (ok) {
     // nothing but the Adler-32 trailer may be left, and it has to match
-    const uint32_t p = (b.wi * 32u - (uint32_t)b.bits + 7u) >> 3;
+    norm(b);
+    const uint32_t p = (zbitpos(b) + 7u) >> 3;
     if (op != kZOut || p + 4 != clen) ok = false;
     if (ok) {
       const uint32_t want = ((uint32_t)bin[p] << 24) | ((uint32_t)bin[p + 1] << 16) | ((uint32_t)bin[p + 2] << 8) | (uint32_t)bin[p + 3];

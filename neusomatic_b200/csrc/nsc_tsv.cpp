@@ -166,6 +166,8 @@ struct DecodeJob {
   uint8_t* text = nullptr;           // staging for the device decoder: the lines are copied here verbatim ...
   size_t text_base = 0;              // ... text[0] = file offset text_base ...
   uint32_t* spans = nullptr;         // ... and [n][2] = (offset in text, characters) of every image field
+  std::vector<std::string>* tag_blocks = nullptr;   // per block of 64 candidates: the tags, each followed by '\n' (no directory part)
+  int32_t* tag_lens = nullptr;       // [n][2] = (len(ref), len(alt)) of the tags
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
   std::string err;
@@ -219,6 +221,15 @@ void decode_range(DecodeJob* job) {
           if (!ok) snprintf(msg, sizeof msg, "line %zu: non-integer tag field", li);
           // type_class_dict[tag.split(".")[4]] raises KeyError in the reference (dataloader.py:55)
           else if (type_idx < 0) { ok = false; snprintf(msg, sizeof msg, "line %zu: unknown variant type in tag", li); }
+        }
+        if (ok && job->tag_blocks) {
+          // the dictionaries' key and what pred_vcf_records_none branches on (call.py:343-350): chrom.pos.REF.ALT.type...
+          (*job->tag_blocks)[(size_t)(k0 / 64)].append(tb, (size_t)(te - tb)).push_back('\n');
+          const char* d1 = (const char*)memchr(tb, '.', (size_t)(te - tb));
+          const char* d2 = (const char*)memchr(d1 + 1, '.', (size_t)(te - d1 - 1));
+          const char* d3 = (const char*)memchr(d2 + 1, '.', (size_t)(te - d2 - 1));
+          job->tag_lens[2 * k] = (int32_t)(d3 - d2 - 1);
+          job->tag_lens[2 * k + 1] = (int32_t)(dots[4] - d3 - 1);
         }
       }
       if (ok && job->text) {
@@ -414,7 +425,9 @@ int64_t nsc_tsv_range_bytes(const nsc_tsv* t, int64_t first, int64_t n) {
 }
 
 int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* text, int64_t text_cap, uint32_t* spans, int32_t* meta,
-                  float* anns255, int32_t* labels, int num_threads) {
+                  float* anns255, int32_t* labels, int num_threads, char* tag_buf, int64_t tag_cap, int64_t* tag_needed, int32_t* tag_lens) {
+  if (tag_buf != nullptr && (tag_needed == nullptr || tag_lens == nullptr)) { nsc::set_error("tag_buf without tag_needed / tag_lens"); return NSC_E_INVALID; }
+  if (tag_needed) *tag_needed = 0;
   if (!t || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("candidate range out of bounds"); return NSC_E_INVALID; }
   if (n == 0) return NSC_OK;
   if (!text || !spans || !meta || num_anns < 0 || (num_anns > 0 && !anns255)) { nsc::set_error("NULL output buffer"); return NSC_E_INVALID; }
@@ -427,7 +440,22 @@ int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* t
   job.text = text;
   job.text_base = t->line_start[(size_t)first];
   job.spans = spans;
-  return run_job(job, n, num_threads);
+  std::vector<std::string> blocks;
+  if (tag_buf != nullptr) {
+    blocks.resize((size_t)((n + 63) / 64));
+    job.tag_blocks = &blocks;
+    job.tag_lens = tag_lens;
+  }
+  const int rc = run_job(job, n, num_threads);
+  if (rc != NSC_OK || tag_buf == nullptr) return rc;
+  int64_t o = 0;
+  for (const std::string& b : blocks) {
+    if (o + (int64_t)b.size() <= tag_cap) memcpy(tag_buf + o, b.data(), b.size());
+    o += (int64_t)b.size();
+  }
+  *tag_needed = o;
+  if (o > tag_cap) { nsc::set_error("tag buffer too small: %lld of %lld bytes", (long long)tag_cap, (long long)o); return NSC_E_INVALID; }
+  return NSC_OK;
 }
 
 int nsc_tsv_tag(const nsc_tsv* t, int64_t i, const char** tag, int32_t* len) {

@@ -97,13 +97,26 @@ class CandidateTSV:
         n = len(self) - first if n is None else n
         return int(self.lib.nsc_tsv_range_bytes(self.h, first, n))
 
-    def stage(self, first, n, text, spans, meta, anns255=None, labels=None):
+    def stage(self, first, n, text, spans, meta, anns255=None, labels=None, with_tags=False):
         """Everything of ``decode`` except the inflate, for ``Engine.score_host_b64``: copies the lines verbatim into ``text``
         (uint8, >= range_bytes + 16), fills ``spans`` [n,2] uint32 (offset, characters of each image field), ``meta`` [n,3]
-        and ``anns255``."""
+        and ``anns255``.  with_tags: also returns (tags, allele lengths [n,2]) gathered in the same pass."""
         cap = int(text.numel() if hasattr(text, "numel") else text.size)
-        _lib.check(self.lib.nsc_tsv_stage(self.h, first, n, self.num_anns, _lib.ptr(text), cap, _lib.ptr(spans), _lib.ptr(meta),
-                                          _lib.ptr(anns255) if self.num_anns else None, _lib.ptr(labels), self.num_threads))
+        args = [self.h, first, n, self.num_anns, _lib.ptr(text), cap, _lib.ptr(spans), _lib.ptr(meta),
+                _lib.ptr(anns255) if self.num_anns else None, _lib.ptr(labels), self.num_threads]
+        if not with_tags or n == 0:
+            _lib.check(self.lib.nsc_tsv_stage(*args, None, 0, None, None))
+            return ([], np.empty((0, 2), np.int32)) if with_tags else None
+        lens = np.empty((n, 2), np.int32)
+        need = C.c_int64()
+        tcap = 96 * n + 64
+        buf = np.empty(tcap, np.uint8)
+        rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, tcap, C.byref(need), lens.ctypes.data)
+        if rc != 0 and need.value > tcap:
+            buf = np.empty(need.value, np.uint8)
+            rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, need.value, C.byref(need), lens.ctypes.data)
+        _lib.check(rc)
+        return buf[:need.value - 1].tobytes().decode().split("\n"), lens
 
     def decode_rows(self, rows):
         """uint8 [len(rows),5,32,23]: the matrices of the listed candidates only."""

@@ -196,6 +196,10 @@ def test_line_index_across_pieces_and_staging(tmp_path, built):
         np.testing.assert_array_equal(mat, cand.matrices[(first + k) % 256])
         i = (first + k) % 256
         assert list(meta[k]) == [cand.center[i], cand.tumor_cov[i], cand.normal_cov[i]]
+    tags, lens = t.stage(first, m, text, spans, meta, with_tags=True)       # the same pass also gathers the tags and allele lengths
+    t2, l2 = t.tags_lens(first, m)
+    assert tags == t2 == [cand.tags[(first + k) % 256] for k in range(m)]
+    np.testing.assert_array_equal(lens, l2)
     rows = np.array([5, 69999, 25000, 5, 31234], np.int64)
     np.testing.assert_array_equal(t.decode_rows(rows), cand.matrices[rows % 256])
     with pytest.raises(Exception):

@@ -19,6 +19,7 @@ from neusomatic_b200.call import CandidateScorer, PIPELINE_TIMES  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
     passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    batches = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32768]
     pool = synth.structured_pileups(4096, seed=4321)
     td = tempfile.mkdtemp(prefix="nsc_probe_")
     path = os.path.join(td, "candidates_0.tsv")
@@ -30,11 +31,13 @@ def main():
             f.write("%d\t1\t%s\t%s\n" % (i, ".".join(tf), blobs[i % 4096]))
     ck = os.path.join(ROOT, "tests", "golden", "std_v010.pth")
     sc = CandidateScorer(ck, device=0)
-    for _ in range(passes):
-        t0 = time.perf_counter()
-        fp, npred = sc.call_tsv(path, batch=32768, num_threads=os.cpu_count() or 1)
-        dt = time.perf_counter() - t0
-        print("%d candidates in %.3f s = %.0f candidates/s; stages %s" % (n, dt, n / dt, {k: round(v, 4) for k, v in PIPELINE_TIMES.items()}), flush=True)
+    for batch in batches:
+        for _ in range(passes):
+            t0 = time.perf_counter()
+            fp, npred = sc.call_tsv(path, batch=batch, num_threads=os.cpu_count() or 1)
+            dt = time.perf_counter() - t0
+            print("slices of %d: %d candidates in %.3f s = %.0f candidates/s; stages %s" % (
+                batch, n, dt, n / dt, {k: round(v, 4) for k, v in PIPELINE_TIMES.items()}), flush=True)
     sc.engine.close()
     os.unlink(path)
     os.rmdir(td)
