@@ -243,10 +243,11 @@ int nsc_tsv_decode(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* 
  * [first, first + n) are copied verbatim to text (text_cap >= nsc_tsv_range_bytes(t, first, n) + 16), spans [n,2] uint32
  * receive (offset in text, characters) of each image field, meta / anns255 / labels as above.  tag_buf (optional, with
  * tag_needed and tag_lens [n,2]): what nsc_tsv_tags_lens returns, gathered by the same threads in the same pass; when
- * tag_cap is too small the call fails with *tag_needed set. */
+ * tag_cap is too small the call fails with *tag_needed set.  tag_hashes (optional, [n]): 64-bit FNV-1a of each tag --
+ * pairwise distinct hashes prove that no tag repeats, which lets the caller skip building a dictionary to find out. */
 int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* text, int64_t text_cap, uint32_t* spans,
                   int32_t* meta, float* anns255, int32_t* labels, int num_threads,
-                  char* tag_buf, int64_t tag_cap, int64_t* tag_needed, int32_t* tag_lens);
+                  char* tag_buf, int64_t tag_cap, int64_t* tag_needed, int32_t* tag_lens, uint64_t* tag_hashes);
 /* bytes of the lines of candidates [first, first + n) (-1: range out of bounds) */
 int64_t nsc_tsv_range_bytes(const nsc_tsv* t, int64_t first, int64_t n);
 /* matrices [n,5,32,23] of the listed candidates only (the images call.py:89-95 keeps for the called variants) */

@@ -56,7 +56,7 @@ SIGNATURES = {
     "nsc_tsv_open": (_i32, [C.POINTER(_vp), C.c_char_p]),
     "nsc_tsv_count": (_i64, [_vp]),
     "nsc_tsv_decode": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _i32]),
-    "nsc_tsv_stage": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(_i64), _vp]),
+    "nsc_tsv_stage": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(_i64), _vp, _vp]),
     "nsc_tsv_range_bytes": (_i64, [_vp, _i64, _i64]),
     "nsc_tsv_decode_rows": (_i32, [_vp, _vp, _i64, _vp, _i32]),
     "nsc_tsv_tag": (_i32, [_vp, _i64, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),

@@ -122,17 +122,19 @@ class PredTable(collections.abc.Mapping):
         self._cat = None
         self._index = {}
         self._indexed = 0
+        self._hashes = []                 # per add(): uint64 hashes of the paths, or None
+        self._unique = None
 
-    def add(self, paths, a1, o2, a3, p1, p3, o1, o3, lens=None):
-        """Rows of one batch; the probability / logit arrays are rounded here (np.round on float32 == round(x, 4))."""
+    def add(self, paths, a1, o2, a3, p1, p3, o1, o3, lens=None, hashes=None):
+        """Rows of one batch; the probability / logit arrays are rounded here (np.round on float32 == round(x, 4)).
+        ``hashes``: 64-bit hashes of the paths (nsc_tsv_stage) -- if every row of the table came with one and they are
+        pairwise distinct, no tag repeats and ``none_records`` need not build the tag dictionary to resolve duplicates."""
         if len(paths) == 0:
             return
         f32 = lambda a: np.asarray(a, np.float32)
-        base = len(self._paths)
         self._paths.extend(paths)
-        if self._indexed == base:            # keep the tag -> row index current (a later duplicate replaces the earlier row)
-            self._index.update(zip(paths, range(base, base + len(paths))))
-            self._indexed = base + len(paths)
+        self._hashes.append(None if hashes is None else np.asarray(hashes, np.uint64))
+        self._unique = None
         self._parts.append((np.asarray(a1, np.int64), f32(o2).reshape(len(paths), -1), np.asarray(a3, np.int64),
                             np.round(f32(p1), 4), np.round(f32(p3), 4), np.round(f32(o1), 4), np.round(f32(o3), 4),
                             None if lens is None else np.asarray(lens, np.int32)))
@@ -174,10 +176,18 @@ class PredTable(collections.abc.Mapping):
 
     def none_records(self, chroms):
         """call.py:336-354 on arrays: prob by allele-length class in float32, keep prob > 0.005, materialise only those."""
-        idx = self._idx()
-        if not idx:
+        if not self._paths:
             return {}.items()
-        rows = np.fromiter(idx.values(), np.int64, len(idx))
+        if self._unique is None:
+            self._unique = False
+            if self._hashes and all(h is not None for h in self._hashes):
+                h = np.sort(np.concatenate(self._hashes))
+                self._unique = bool((h[1:] != h[:-1]).all())
+        if self._unique:                      # no tag repeats: every row is its own entry, in arrival order
+            rows = np.arange(len(self._paths), dtype=np.int64)
+        else:                                 # a later row replaces an earlier one with the same tag, like assignment into a dict
+            idx = self._idx()
+            rows = np.fromiter(idx.values(), np.int64, len(idx))
         _, _, _, P1, P3, _, _, lens = self._arrays()
         if lens is None:
             lens = np.array([[len(f[2]), len(f[3])] for f in (p.split(".") for p in self._paths)], np.int32).reshape(-1, 2)
@@ -417,7 +427,7 @@ class CandidateScorer:
         return final_preds, none_preds
 
 
-def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds, true_path):
+def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds, true_path, hashes=None):
     """Files one scored slice: rows predicted NONE go to ``none_preds``, the others to ``final_preds`` (call.py:88-114);
     ``true_path`` receives the non_transformed image of every non-NONE candidate (call.py:89-95)."""
     a1 = np.asarray(r["arg1"])
@@ -427,12 +437,20 @@ def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds,
         tags = [t[t.rfind("/") + 1:] for t in tags]                  # path_.split("/")[-1]
     cols = ("arg1", "o2", "arg3", "p1", "p3", "o1", "o3")
     if len(var) == 0:
-        none_preds.add(tags, *[np.array(r[c]) for c in cols], lens=lens)
+        none_preds.add(tags, *[np.array(r[c]) for c in cols], lens=lens, hashes=hashes)
         return
-    non = np.nonzero(a1 == none_idx)[0]
     vt = [tags[i] for i in var]
     final_preds.add(vt, *[np.asarray(r[c])[var] for c in cols], lens=None if lens is None else lens[var])
-    none_preds.add([tags[i] for i in non], *[np.asarray(r[c])[non] for c in cols], lens=None if lens is None else lens[non])
+    if 8 * len(var) < len(tags):             # few called variants (the usual case): cut them out instead of gathering the rest
+        nt = list(tags)
+        for i in var[::-1]:
+            del nt[i]
+        cut = lambda a: None if a is None else np.delete(np.asarray(a), var, axis=0)
+        none_preds.add(nt, *[cut(r[c]) for c in cols], lens=cut(lens), hashes=cut(hashes))
+    else:
+        non = np.nonzero(a1 == none_idx)[0]
+        sel = lambda a: None if a is None else np.asarray(a)[non]
+        none_preds.add([tags[i] for i in non], *[sel(r[c]) for c in cols], lens=sel(lens), hashes=sel(hashes))
     if true_path is not None:
         # ``matrices`` may be a function of the row indices (the device-inflate pipeline keeps no decoded matrices on the host:
         # only the called variants' images are decoded here)
@@ -549,7 +567,7 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             path, f0, n = slices[k]
             t0 = time.perf_counter()
             try:
-                return tsvs[path].tags_lens(f0, n)
+                return tsvs[path].tags_lens(f0, n) + (None,)
             finally:
                 times["tags"] += time.perf_counter() - t0
 
@@ -557,13 +575,13 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
             path, f0, n = slices[k]
             tl = ftags.result()
             outs = fsc.result()                  # (after the slice's decode stage: slot.tags is this slice's)
-            tags, lens = tl if tl is not None else slots[k % len(slots)].tags
+            tags, lens, hashes = tl if tl is not None else slots[k % len(slots)].tags
             t0 = time.perf_counter()
             slot = slots[k % len(slots)]
             names = ["o1", "o2", "o3", "p1", "p3", "arg1", "arg3"]
             r = {nm: t.numpy() for nm, t in zip(names, outs)}
             mats = (lambda rows: tsvs[path].decode_rows(f0 + np.asarray(rows, np.int64))) if device_inflate else slot.matrices[:n].numpy()
-            _split_into_tables(r, tags, lens, mats, slot.meta[:n, 0].numpy(), final_preds, none_preds, true_path)
+            _split_into_tables(r, tags, lens, mats, slot.meta[:n, 0].numpy(), final_preds, none_preds, true_path, hashes)
             times["file"] += time.perf_counter() - t0
 
         TPE = concurrent.futures.ThreadPoolExecutor

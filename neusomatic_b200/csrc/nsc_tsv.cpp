@@ -168,6 +168,7 @@ struct DecodeJob {
   uint32_t* spans = nullptr;         // ... and [n][2] = (offset in text, characters) of every image field
   std::vector<std::string>* tag_blocks = nullptr;   // per block of 64 candidates: the tags, each followed by '\n' (no directory part)
   int32_t* tag_lens = nullptr;       // [n][2] = (len(ref), len(alt)) of the tags
+  uint64_t* tag_hashes = nullptr;    // [n] FNV-1a of the tags (distinct hashes prove distinct tags without a dictionary)
   std::atomic<int64_t> next{0};
   std::atomic<int> failed{0};
   std::string err;
@@ -230,6 +231,11 @@ void decode_range(DecodeJob* job) {
           const char* d3 = (const char*)memchr(d2 + 1, '.', (size_t)(te - d2 - 1));
           job->tag_lens[2 * k] = (int32_t)(d3 - d2 - 1);
           job->tag_lens[2 * k + 1] = (int32_t)(dots[4] - d3 - 1);
+          if (job->tag_hashes) {
+            uint64_t h = 14695981039346656037ull;
+            for (const char* q = tb; q < te; ++q) h = (h ^ (uint8_t)*q) * 1099511628211ull;
+            job->tag_hashes[k] = h;
+          }
         }
       }
       if (ok && job->text) {
@@ -425,7 +431,8 @@ int64_t nsc_tsv_range_bytes(const nsc_tsv* t, int64_t first, int64_t n) {
 }
 
 int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* text, int64_t text_cap, uint32_t* spans, int32_t* meta,
-                  float* anns255, int32_t* labels, int num_threads, char* tag_buf, int64_t tag_cap, int64_t* tag_needed, int32_t* tag_lens) {
+                  float* anns255, int32_t* labels, int num_threads, char* tag_buf, int64_t tag_cap, int64_t* tag_needed, int32_t* tag_lens,
+                  uint64_t* tag_hashes) {
   if (tag_buf != nullptr && (tag_needed == nullptr || tag_lens == nullptr)) { nsc::set_error("tag_buf without tag_needed / tag_lens"); return NSC_E_INVALID; }
   if (tag_needed) *tag_needed = 0;
   if (!t || first < 0 || n < 0 || first + n > nsc_tsv_count(t)) { nsc::set_error("candidate range out of bounds"); return NSC_E_INVALID; }
@@ -445,6 +452,7 @@ int nsc_tsv_stage(nsc_tsv* t, int64_t first, int64_t n, int num_anns, uint8_t* t
     blocks.resize((size_t)((n + 63) / 64));
     job.tag_blocks = &blocks;
     job.tag_lens = tag_lens;
+    job.tag_hashes = tag_hashes;
   }
   const int rc = run_job(job, n, num_threads);
   if (rc != NSC_OK || tag_buf == nullptr) return rc;

@@ -100,23 +100,24 @@ class CandidateTSV:
     def stage(self, first, n, text, spans, meta, anns255=None, labels=None, with_tags=False):
         """Everything of ``decode`` except the inflate, for ``Engine.score_host_b64``: copies the lines verbatim into ``text``
         (uint8, >= range_bytes + 16), fills ``spans`` [n,2] uint32 (offset, characters of each image field), ``meta`` [n,3]
-        and ``anns255``.  with_tags: also returns (tags, allele lengths [n,2]) gathered in the same pass."""
+        and ``anns255``.  with_tags: also returns (tags, allele lengths [n,2], uint64 tag hashes [n]) gathered in the same pass."""
         cap = int(text.numel() if hasattr(text, "numel") else text.size)
         args = [self.h, first, n, self.num_anns, _lib.ptr(text), cap, _lib.ptr(spans), _lib.ptr(meta),
                 _lib.ptr(anns255) if self.num_anns else None, _lib.ptr(labels), self.num_threads]
         if not with_tags or n == 0:
-            _lib.check(self.lib.nsc_tsv_stage(*args, None, 0, None, None))
-            return ([], np.empty((0, 2), np.int32)) if with_tags else None
+            _lib.check(self.lib.nsc_tsv_stage(*args, None, 0, None, None, None))
+            return ([], np.empty((0, 2), np.int32), np.empty(0, np.uint64)) if with_tags else None
         lens = np.empty((n, 2), np.int32)
+        hashes = np.empty(n, np.uint64)
         need = C.c_int64()
         tcap = 96 * n + 64
         buf = np.empty(tcap, np.uint8)
-        rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, tcap, C.byref(need), lens.ctypes.data)
+        rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, tcap, C.byref(need), lens.ctypes.data, hashes.ctypes.data)
         if rc != 0 and need.value > tcap:
             buf = np.empty(need.value, np.uint8)
-            rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, need.value, C.byref(need), lens.ctypes.data)
+            rc = self.lib.nsc_tsv_stage(*args, buf.ctypes.data, need.value, C.byref(need), lens.ctypes.data, hashes.ctypes.data)
         _lib.check(rc)
-        return buf[:need.value - 1].tobytes().decode().split("\n"), lens
+        return buf[:need.value - 1].tobytes().decode().split("\n"), lens, hashes
 
     def decode_rows(self, rows):
         """uint8 [len(rows),5,32,23]: the matrices of the listed candidates only."""

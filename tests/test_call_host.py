@@ -81,6 +81,41 @@ def test_none_records_on_arrays_equal_the_scalar_filter():
             _entries_equal(got[k][5][1], ref[k][5][1])
 
 
+def test_none_records_with_tag_hashes_and_repeated_tags():
+    """Rows that arrive with 64-bit tag hashes (nsc_tsv_stage): distinct hashes -> the filter skips the tag dictionary and gives
+    the same records; a repeated tag (equal hashes) -> the dictionary path, where the later row replaces the earlier one at
+    the earlier one's place (call.py:96-114 assigns into a dict)."""
+    import zlib
+    rng = np.random.Generator(np.random.PCG64(9))
+    n = 2000
+    tags = list(synth.structured_pileups(n, seed=78).tags)
+    p1 = rng.dirichlet([0.05, 0.05, 1.0, 0.05], size=n).astype(np.float32)
+    p3 = rng.dirichlet([0.5] * 4, size=n).astype(np.float32)
+    o1, o3 = np.log(p1 + 1e-6).astype(np.float32), np.log(p3 + 1e-6).astype(np.float32)
+    o2 = rng.normal(16, 2, size=(n, 1)).astype(np.float32)
+    a1, a3 = np.full(n, 2), p3.argmax(1)
+    chroms = ["c%d" % i for i in range(30)]
+    hashes = lambda ts: np.array([zlib.crc32(t.encode()) | (zlib.adler32(t.encode()) << 32) for t in ts], np.uint64)
+    for repeat in (False, True):
+        tg = list(tags)
+        if repeat:
+            tg[1500] = tg[3]                   # a later candidate with an earlier one's tag
+            tg[1999] = tg[1998]
+        _, plain = build_pred_dicts(o1, o2, o3, p1, p3, a1, a3, tg)
+        ref = dict(vcf.pred_vcf_records_none(plain, chroms))
+        tab = PredTable()
+        for lo in range(0, n, 512):            # in slices, as the pipeline files them
+            hi = min(n, lo + 512)
+            tab.add(tg[lo:hi], a1[lo:hi], o2[lo:hi], a3[lo:hi], p1[lo:hi], p3[lo:hi], o1[lo:hi], o3[lo:hi], hashes=hashes(tg[lo:hi]))
+        got = dict(vcf.pred_vcf_records_none(tab, chroms))
+        assert tab._unique is (not repeat)
+        assert list(got.keys()) == list(ref.keys()) and len(got) > 30
+        for k in ref:
+            assert got[k][:5] == ref[k][:5]
+            _entries_equal(got[k][5][1], ref[k][5][1])
+        assert len(tab) == len(plain) and list(tab) == list(plain)
+
+
 def test_plan_call_groups_follows_the_reference_rule():
     # call.py:468-507 with max_load_candidates = 1000: files above 500 are cut into pieces of 500, pieces sorted by size,
     # a group closes once it holds more than 100 candidates

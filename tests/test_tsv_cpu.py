@@ -196,10 +196,17 @@ def test_line_index_across_pieces_and_staging(tmp_path, built):
         np.testing.assert_array_equal(mat, cand.matrices[(first + k) % 256])
         i = (first + k) % 256
         assert list(meta[k]) == [cand.center[i], cand.tumor_cov[i], cand.normal_cov[i]]
-    tags, lens = t.stage(first, m, text, spans, meta, with_tags=True)       # the same pass also gathers the tags and allele lengths
+    tags, lens, hashes = t.stage(first, m, text, spans, meta, with_tags=True)     # the same pass gathers tags, allele lengths, tag hashes
     t2, l2 = t.tags_lens(first, m)
     assert tags == t2 == [cand.tags[(first + k) % 256] for k in range(m)]
     np.testing.assert_array_equal(lens, l2)
+    def fnv(txt):
+        h = 14695981039346656037
+        for c in txt.encode():
+            h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    assert [int(h) for h in hashes[:300]] == [fnv(x) for x in tags[:300]]
+    assert len(set(hashes[:256].tolist())) == 256 and hashes[0] == hashes[256]     # distinct tags, and the repeat 256 lines later
     rows = np.array([5, 69999, 25000, 5, 31234], np.int64)
     np.testing.assert_array_equal(t.decode_rows(rows), cand.matrices[rows % 256])
     with pytest.raises(Exception):
