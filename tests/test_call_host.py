@@ -103,17 +103,22 @@ def test_none_records_with_tag_hashes_and_repeated_tags():
             tg[1999] = tg[1998]
         _, plain = build_pred_dicts(o1, o2, o3, p1, p3, a1, a3, tg)
         ref = dict(vcf.pred_vcf_records_none(plain, chroms))
-        tab = PredTable()
-        for lo in range(0, n, 512):            # in slices, as the pipeline files them
-            hi = min(n, lo + 512)
-            tab.add(tg[lo:hi], a1[lo:hi], o2[lo:hi], a3[lo:hi], p1[lo:hi], p3[lo:hi], o1[lo:hi], o3[lo:hi], hashes=hashes(tg[lo:hi]))
-        got = dict(vcf.pred_vcf_records_none(tab, chroms))
-        assert tab._unique is (not repeat)
-        assert list(got.keys()) == list(ref.keys()) and len(got) > 30
-        for k in ref:
-            assert got[k][:5] == ref[k][:5]
-            _entries_equal(got[k][5][1], ref[k][5][1])
-        assert len(tab) == len(plain) and list(tab) == list(plain)
+        lens = np.array([[len(t.split(".")[2]), len(t.split(".")[3])] for t in tg], np.int32)
+        for with_lens in (True, False):        # with allele lengths the filter runs batch by batch inside add()
+            tab = PredTable()
+            for lo in range(0, n, 512):        # in slices, as the pipeline files them
+                hi = min(n, lo + 512)
+                tab.add(tg[lo:hi], a1[lo:hi], o2[lo:hi], a3[lo:hi], p1[lo:hi], p3[lo:hi], o1[lo:hi], o3[lo:hi],
+                        lens=lens[lo:hi] if with_lens else None, hashes=hashes(tg[lo:hi]))
+            got = dict(vcf.pred_vcf_records_none(tab, chroms))
+            assert tab._unique is (not repeat)
+            assert list(got.keys()) == list(ref.keys()) and len(got) > 30
+            for k in ref:
+                assert got[k][:5] == ref[k][:5] and type(got[k][4]) is np.float32
+                _entries_equal(got[k][5][1], ref[k][5][1])
+            assert len(tab) == len(plain) and list(tab) == list(plain)
+            for k in list(plain)[::97]:
+                _entries_equal(tab[k], plain[k])
 
 
 def test_plan_call_groups_follows_the_reference_rule():
