@@ -495,6 +495,7 @@ class _Slot:
         mk = lambda shape, dt: (torch.empty(shape, dtype=dt).pin_memory() if pin else torch.empty(shape, dtype=dt))
         self.n = n
         self.text_bytes = text_bytes
+        self.tags = None              # (tag strings, allele lengths, tag hashes) of the slice staged in this slot
         if text_bytes:        # device inflate: the slice's lines as they are in the file + (offset, characters) of each image field
             self.text = mk((text_bytes,), torch.uint8)
             self.spans = mk((n, 2), torch.int32)         # read as uint32 by the library

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 #include "nsc_common.h"
@@ -403,13 +404,13 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
 // The text buffer must extend 16 bytes past the last span.
 int inflate_b64_launch(uint8_t* text, const uint32_t* spans, uint32_t origin, int64_t n, uint8_t* out, int* declined, cudaStream_t s) {
   if (n <= 0) return NSC_OK;
-  static bool attr_done[64] = {};
+  static std::atomic<uint64_t> attr_set{0};      // bit d: the attribute is set on device d (it is per device)
   int dev = 0;
   NSC_CUDA_TRY(cudaGetDevice(&dev));
   const size_t smem = kZWarps * sizeof(ZWarp);
-  if (!attr_done[dev & 63]) {
+  if (!((attr_set.load() >> (dev & 63)) & 1)) {
     NSC_CUDA_TRY(cudaFuncSetAttribute(inflate_b64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done[dev & 63] = true;
+    attr_set.fetch_or(1ull << (dev & 63));
   }
   NSC_CUDA_TRY(cudaMemsetAsync(declined, 0, sizeof(int), s));
   inflate_b64_kernel<<<(unsigned)((n + kZWarps - 1) / kZWarps), kZWarps * 32, smem, s>>>(text, spans, origin, (int)n, out, declined);

@@ -209,3 +209,35 @@ def test_call_tsv_device_inflate_equals_host_inflate(tmp_path, monkeypatch, ense
     for k in t1:
         np.testing.assert_array_equal(t1[k], t0[k])
     sc.engine.close()
+
+
+def test_score_host_b64_argument_errors():
+    import ctypes as C
+    from neusomatic_b200._lib import NscError
+    lib = _lib.load()
+    cand = synth.structured_pileups(64, seed=2)
+    eng = Engine(synth.random_state_dict(26, seed=1), 26)
+    text, spans = _staged(cand)
+    text = np.frombuffer(bytes(text), np.uint8).copy()
+    meta = np.stack([cand.center, cand.tumor_cov, cand.normal_cov], 1).astype(np.int32)
+    outs, nhost = eng.score_host_b64(text, spans[:0].view(np.int32), meta[:0], None, 100.0)          # empty batch
+    assert outs[0].shape == (0, 4) and nhost == 0
+    bad = spans.copy()
+    bad[10, 0] = text.size                                                                              # span outside the text
+    with pytest.raises(NscError, match="span outside"):
+        eng.score_host_b64(text, bad.view(np.int32), meta, None, 100.0)
+    o = Engine._host_out(64, True, False)
+    args = [eng.h, text.ctypes.data, text.size, None, meta.ctypes.data, None, C.c_float(100.0), 64] + [_lib.ptr(t) for t in o] + [None]
+    assert lib.nsc_score_host_b64(*args) != 0 and b"spans" in lib.nsc_last_error()                      # NULL spans
+    args[3], args[4] = spans.ctypes.data, None
+    assert lib.nsc_score_host_b64(*args) != 0                                                           # NULL meta
+    args[4], args[6] = meta.ctypes.data, C.c_float(0.0)
+    assert lib.nsc_score_host_b64(*args) != 0                                                           # coverage_thr must be positive
+    ens = Engine(synth.random_state_dict(119, seed=1), 119)
+    with pytest.raises(NscError, match="anns255"):
+        ens.score_host_b64(text, spans.view(np.int32), meta, None, 100.0)                               # the ensemble needs annotations
+    ens.close()
+    got, _ = eng.score_host_b64(text, spans.view(np.int32), meta, None, 100.0)                          # and the handle is intact
+    want = eng.score_host_u8(cand.matrices, meta, None, 100.0)
+    np.testing.assert_array_equal(got[0].numpy(), want[0].numpy())
+    eng.close()
