@@ -315,15 +315,31 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
       }
       w = window(b);
       uint32_t e = z.lit[w & ((1u << kLitBits) - 1u)];
-      int l = (int)(e & 15u), sym = (int)(e >> 4);
+      uint32_t lu = e & 15u;
+      if (e < (256u << 4) && lu != 0) {
+        // a literal whose code is in the table -- the common case, kept free of exits: a literal past the end of the matrix
+        // is not stored and `op` keeps counting (checked after the block)
+        b.pos += lu;
+        if (lane == 0 && op < kZOut) z.out[op] = (uint8_t)(e >> 4);
+        ++op;
+        w >>= lu;                                            // >= 17 valid bits are left: enough for one more code
+        e = z.lit[w & ((1u << kLitBits) - 1u)];
+        lu = e & 15u;
+        if (e < (256u << 4) && lu != 0) {
+          b.pos += lu;
+          if (lane == 0 && op < kZOut) z.out[op] = (uint8_t)(e >> 4);
+          ++op;
+        }
+        continue;                                            // (anything else is decoded again from a fresh window)
+      }
+      int l = (int)lu, sym = (int)(e >> 4);
       if (l == 0) {
         sym = walk(w, z.cnt[0], z.lit_sorted, &l);
         if (sym < 0) { ok = false; break; }
       }
       b.pos += (uint32_t)l;
       if (sym < 256) {
-        if (op >= kZOut) { ok = false; break; }
-        if (lane == 0) z.out[op] = (uint8_t)sym;
+        if (lane == 0 && op < kZOut) z.out[op] = (uint8_t)sym;
         ++op;
         continue;
       }
@@ -361,6 +377,7 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
       }
       op += len;
     }
+    if (op > kZOut) ok = false;
   }
   __syncwarp();
   if (ok) {
