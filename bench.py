@@ -542,6 +542,44 @@ def measure_tsv(args, rk, local_rank, n=524288):
                 "sample": "oracle: TSV line decode + channel assembly + torch_port forward + call_variants loop, " + cpu_sample}}
 
 
+def measure_tsv_ensemble(args, rk, local_rank, n=131072):
+    """The same real-file call for the ensemble network (BASELINE configs[3]): 93 annotation fields per line, parsed by the
+    staging threads; device inflate only."""
+    import base64
+    import zlib
+    from neusomatic_b200 import synth
+    from neusomatic_b200.call import CandidateScorer, PIPELINE_TIMES
+    from neusomatic_b200.vcf import pred_vcf_records_none
+    pool = synth.structured_pileups(4096, seed=4321, ensemble=True)
+    td = tempfile.mkdtemp(prefix="nsc_bench_")
+    path = os.path.join(td, "candidates_0.tsv")
+    blobs = [base64.b64encode(zlib.compress(np.ascontiguousarray(pool.matrices[i]))).decode("ascii") for i in range(4096)]
+    anns = ["\t".join(("%.4f" % a).rstrip("0").rstrip(".") or "0" for a in pool.anns[i]) for i in range(4096)]      # short decimals, as in real files
+    with open(path, "w") as f:
+        for i in range(n):
+            tf = pool.tags[i % 4096].split(".")
+            tf[1] = str(1000 + i)
+            f.write("%d\t1\t%s\t%s\t%s\n" % (i, ".".join(tf), blobs[i % 4096], anns[i % 4096]))
+    size = os.path.getsize(path)
+    sc = CandidateScorer(CKPT_ENS, device=local_rank, precision=args.precision)
+    threads = os.cpu_count() or 1
+    chroms = ["chr%d" % i for i in range(30)]
+    sc.call_tsv(path, batch=32768, num_threads=threads)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        fp, npred = sc.call_tsv(path, batch=32768, num_threads=threads)
+        len(dict(pred_vcf_records_none(npred, chroms)))
+        ts.append(time.perf_counter() - t0)
+    sc.engine.close()
+    os.unlink(path)
+    os.rmdir(td)
+    el = float(np.median(ts))
+    return {"value": n / el, "unit": "candidates/s", "candidates": n, "tsv_bytes": size, "host_threads": threads, "seconds": el,
+            "h2d_bytes_per_candidate": size / n, "stage_busy_seconds": {k: round(v, 4) for k, v in PIPELINE_TIMES.items()},
+            "what": "e2e_tsv for the ensemble network: C=119, 93 annotation fields per line (BASELINE.json configs[3])"}
+
+
 def roofline_record(m, B, steps, world, C):
     """Tensor roofline of the dominant kernel family (the eight 64->64 convolutions) from the live per-kernel event times."""
     pk = peaks()
@@ -655,6 +693,7 @@ def main():
         if world == 1:
             extra["gpu_incumbent"] = measure_incumbent(args, rk, local_rank)
             extra["e2e_tsv"] = measure_tsv(args, rk, local_rank)
+            extra["e2e_tsv_ensemble"] = measure_tsv_ensemble(args, rk, local_rank)
 
     roof = roofline_record(m, B, args.steps, world, C)
 

@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neusomatic_b200 import synth  # noqa: E402
-from neusomatic_b200.call import CandidateScorer, PIPELINE_TIMES  # noqa: E402
+from neusomatic_b200.call import CandidateScorer, PIPELINE_TIMES, PredTable, run_tsv_pipeline  # noqa: E402
 
 
 def main():
@@ -30,15 +30,20 @@ def main():
             tf[1] = str(1000 + i)
             f.write("%d\t1\t%s\t%s\n" % (i, ".".join(tf), blobs[i % 4096]))
     ck = os.path.join(ROOT, "tests", "golden", "std_v010.pth")
-    sc = CandidateScorer(ck, device=0)
+    import torch
+    n_dev = int(sys.argv[4]) if len(sys.argv) > 4 else 1          # GPUs driven by the one pipeline (slices round-robin)
+    n_dev = min(n_dev, torch.cuda.device_count())
+    scorers = [CandidateScorer(ck, device=d) for d in range(n_dev)]
     for batch in batches:
         for _ in range(passes):
             t0 = time.perf_counter()
-            fp, npred = sc.call_tsv(path, batch=batch, num_threads=os.cpu_count() or 1)
+            fp, npred = PredTable(), PredTable()
+            run_tsv_pipeline(scorers, [(path, 0, None)], batch, os.cpu_count() or 1, fp, npred)
             dt = time.perf_counter() - t0
-            print("slices of %d: %d candidates in %.3f s = %.0f candidates/s; stages %s" % (
-                batch, n, dt, n / dt, {k: round(v, 4) for k, v in PIPELINE_TIMES.items()}), flush=True)
-    sc.engine.close()
+            print("%d GPU(s), slices of %d: %d candidates in %.3f s = %.0f candidates/s; stages %s" % (
+                n_dev, batch, n, dt, n / dt, {k: round(v, 4) for k, v in PIPELINE_TIMES.items()}), flush=True)
+    for sc in scorers:
+        sc.engine.close()
     os.unlink(path)
     os.rmdir(td)
 
