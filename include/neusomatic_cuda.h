@@ -136,7 +136,8 @@ int nsc_score_host_u8(nsc_model* m, const uint8_t* matrices_host, const int32_t*
  * zlib.decompress(base64.b64decode(field))) runs ON THE DEVICE, so a candidate crosses PCIe as ~1.3 KB of text.
  * text_host: bytes holding the fields (nsc_tsv_stage copies the file's lines there verbatim; pinned memory keeps the
  * copies asynchronous); spans_host [B][2] uint32 = (offset in text_host, characters) of every candidate's
- * base64(zlib(uint8[5,32,23])) field; meta / anns255 / outputs as in nsc_score_host_u8.  A field the device decoder
+ * base64(zlib(uint8[5,32,23])) field, pairwise disjoint (the device decodes every field in place in ITS copy of the text;
+ * text_host itself is only read); meta / anns255 / outputs as in nsc_score_host_u8.  A field the device decoder
  * declines (malformed or unusual stream) is decoded by zlib on the host before its slice is scored: results never depend
  * on where a candidate was inflated, and a field zlib rejects fails the call (NSC_E_INVALID) like the reference's worker.
  * host_decoded (optional): how many candidates of this call went that way. */
