@@ -542,7 +542,7 @@ def measure_tsv(args, rk, local_rank, n=524288):
                 "sample": "oracle: TSV line decode + channel assembly + torch_port forward + call_variants loop, " + cpu_sample}}
 
 
-def measure_tsv_ensemble(args, rk, local_rank, n=131072):
+def measure_tsv_ensemble(args, rk, local_rank, n=262144):
     """The same real-file call for the ensemble network (BASELINE configs[3]): 93 annotation fields per line, parsed by the
     staging threads; device inflate only."""
     import base64

@@ -65,6 +65,19 @@ def matrices_of_many_shapes():
     datas.append((np.arange(N) % 3).astype(np.uint8).tobytes())                                                    # distance-3 matches
     datas.append((np.arange(N) % 251).astype(np.uint8).tobytes())
     datas.append(np.repeat(rng.integers(0, 256, N // 40, dtype=np.uint8), 40).tobytes())                           # runs of 40
+    # geometric symbol frequencies (1, 1, 2, 4, ... 1024 occurrences): Huffman codes up to 12-13 bits, longer than the decoder's
+    # 10-bit look-up table -> the bit-by-bit canonical walk; the matching distances of the shuffled copy do the same to the
+    # 8-bit distance table
+    geo = np.concatenate([np.full(max(1, 1 << max(k - 1, 0)), 200 - k, np.uint8) for k in range(12)])
+    geo = np.concatenate([geo, np.full(N - geo.size, 7, np.uint8)])
+    for seed in (1, 2, 3):
+        datas.append(np.random.Generator(np.random.PCG64(seed)).permutation(geo).tobytes())
+    far = rng.integers(0, 256, N, dtype=np.uint8)
+    for k in range(0, N - 40, 97):                                                                                 # matches at many distinct distances
+        d = int(rng.integers(1, k + 1)) if k else 1
+        if k >= d + 8:
+            far[k:k + 8] = far[k - d:k - d + 8]
+    datas.append(far.tobytes())
     return datas
 
 
