@@ -30,6 +30,7 @@ constexpr int kZOut = kH * kW * kStoredCh;        // 3680
 constexpr int kZOutPad = 3680;
 constexpr int kLitBits = 10, kDistBits = 8, kPreBits = 7;
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kMaxChars = 8192;              // an incompressible matrix is ~4.9 k characters; longer fields go to the host
 
 __constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -168,6 +169,10 @@ inflate_b64_kernel(uint8_t* text, const uint32_t* __restrict__ spans, uint32_t o
   bool ok = true;
   uint8_t* src = text + (spans[2 * k] - origin);
   uint32_t nch = spans[2 * k + 1];
+  if (nch > kMaxChars) {
+    nch = 0;                                      // bounded work per warp whatever the span says
+    ok = false;
+  }
   while (nch > 0 && src[nch - 1] == '=') --nch;
   if (nch < 16) ok = false;
   uint32_t clen = 0;

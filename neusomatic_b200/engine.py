@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-VARTYPE_CLASSES = ["DEL", "INS", "NONE", "SNP"]   # call.py:407
+from .predtable import VARTYPE_CLASSES          # noqa: E402  ["DEL", "INS", "NONE", "SNP"], call.py:407
 BN_EPS = 1e-5                                      # nn.BatchNorm2d default (network.py:24)
 
 

@@ -8,11 +8,13 @@ import os
 
 
 class FastaFile:
-    def __init__(self, path):
+    def __init__(self, path, index=None):
         self.path = path
         self._index = {}            # name -> (length, offset of the first base, bases per line, bytes per line)
         fai = path + ".fai"
-        if os.path.exists(fai):
+        if index is not None:       # handed over by a process that has already read or built it
+            self._index = dict(index)
+        elif os.path.exists(fai):
             for line in open(fai):
                 f = line.rstrip("\n").split("\t")
                 if len(f) >= 5:
@@ -89,8 +91,9 @@ class MemoryFasta:
 _OPEN = {}
 
 
-def open_fasta(ref):
-    """``ref``: a path (one reader per path and process is kept open) or an object that already has ``fetch``."""
+def open_fasta(ref, index=None):
+    """``ref``: a path (one reader per path and process is kept open) or an object that already has ``fetch``.
+    ``index``: the ``fasta_index`` of another process's reader of the same file (saves the scan when there is no .fai)."""
     if hasattr(ref, "fetch"):
         return ref
     key = (os.getpid(), ref)
@@ -100,6 +103,11 @@ def open_fasta(ref):
             import pysam
             r = pysam.FastaFile(ref)
         except ImportError:
-            r = FastaFile(ref)
+            r = FastaFile(ref, index)
         _OPEN[key] = r
     return r
+
+
+def fasta_index(reader):
+    """The index of this module's own reader (None for pysam's, which reads the .fai itself)."""
+    return getattr(reader, "_index", None)

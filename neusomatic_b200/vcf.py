@@ -25,7 +25,7 @@ import traceback
 
 import numpy as np
 
-from .fasta import open_fasta
+from .fasta import fasta_index, open_fasta
 
 ACGT = "ACGT"
 # constants of the centre refinement (call.py:148-151)
@@ -242,22 +242,108 @@ def pred_vcf_records_path(record):
         return None
 
 
-def pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, num_threads):
-    """call.py:308-333.  ``true_path[path]`` holds the uint8 [5,32,3] matrix (or a PNG file name).  The records are built
-    in this process when ``num_threads`` <= 1 or the batch is small, otherwise in a pool like the reference."""
-    fasta = open_fasta(ref_file)
-    args = [[path, true_path[path], final_preds[path], chroms, vartype_classes, fasta] for path in final_preds.keys()]
-    if num_threads > 1 and len(args) >= 4096 and isinstance(ref_file, str):
-        for a in args:
-            a[5] = ref_file                    # every worker opens its own reader
-        with multiprocessing.Pool(num_threads) as pool:
-            out = pool.map(pred_vcf_records_path, args, chunksize=256)
-    else:
-        out = [pred_vcf_records_path(a) for a in args]
-    for o in out:
+POOL_CHUNK = 512          # called variants per pool task
+POOL_MIN = 2048           # the pool is started once this many records have been asked for (forking costs ~0.3 s)
+
+
+def _records_chunk(job):
+    """Pool task: the records of one chunk of called variants.  The chunk arrives as arrays (tags, images, the columns of
+    the table) -- pickling per-candidate lists of np.float32 scalars costs more than building the records."""
+    paths, images, cols, chroms, vartype_classes, ref_file, index, with_pred = job
+    from .predtable import PredTable
+    fasta = open_fasta(ref_file, index)
+    tab = PredTable(vartype_classes)
+    tab.add(paths, *cols)
+    out = []
+    for i, path in enumerate(paths):
+        o = pred_vcf_records_path([path, images[i], tab[path], chroms, vartype_classes, fasta])
         if o is None:
-            raise Exception("pred_vcf_records_path failed!")
-    return list(filter(None, out))
+            return None
+        if o and not with_pred:
+            o[1][5] = None                 # [path, pred]: dropped by get_vcf_records, expensive to send back
+        out.append(o)
+    return out
+
+
+class RecordPool:
+    """call.py:308-333 as a service: ``submit(final_preds, true_path)`` starts building the VCF records of one group of
+    candidates and returns a handle, ``collect(handle)`` returns them in the order of ``final_preds``.  With
+    ``num_threads`` > 1, a PredTable and a FASTA path, the records are built by a process pool like the reference's -- in
+    chunks of 512 candidates shipped as arrays, while the caller goes on scoring the next group; the pool is forked once
+    2048 records have been asked for, before that (and in every other case) ``submit`` builds the records itself."""
+
+    def __init__(self, ref_file, chroms, vartype_classes, num_threads, with_pred=True):
+        self.ref_file, self.chroms, self.classes = ref_file, chroms, vartype_classes
+        self.num_threads, self.with_pred = int(num_threads), with_pred
+        self.pool = None
+        self.asked = 0
+
+    def _serial(self, final_preds, true_path, paths):
+        fasta = open_fasta(self.ref_file)
+        out = []
+        for path in paths:
+            o = pred_vcf_records_path([path, true_path[path], final_preds[path], self.chroms, self.classes, fasta])
+            if o is None:
+                raise Exception("pred_vcf_records_path failed!")
+            if o and not self.with_pred:
+                o[1][5] = None
+            out.append(o)
+        return out
+
+    def submit(self, final_preds, true_path):
+        paths = list(final_preds.keys())
+        self.asked += len(paths)
+        poolable = self.num_threads > 1 and isinstance(self.ref_file, str) and hasattr(final_preds, "columns_of")
+        if not poolable or (self.pool is None and self.asked < POOL_MIN) or not paths:
+            return ("done", self._serial(final_preds, true_path, paths))
+        if self.pool is None:
+            self.pool = multiprocessing.Pool(min(self.num_threads, 32))
+        index = fasta_index(open_fasta(self.ref_file))
+        pending = []
+        for lo in range(0, len(paths), POOL_CHUNK):
+            ps = paths[lo:lo + POOL_CHUNK]
+            imgs = [true_path[p] for p in ps]
+            if all(isinstance(im, np.ndarray) for im in imgs):
+                imgs = np.stack(imgs)
+            job = (ps, imgs, final_preds.columns_of(ps), self.chroms, self.classes, self.ref_file, index, self.with_pred)
+            pending.append(self.pool.apply_async(_records_chunk, (job,)))
+        return ("pending", pending)
+
+    def collect(self, handle):
+        kind, h = handle
+        if kind == "pending":
+            parts = [r.get() for r in h]
+            if any(part is None for part in parts):
+                raise Exception("pred_vcf_records_path failed!")
+            h = [o for part in parts for o in part]
+        return list(filter(None, h))
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.pool is not None and exc[0] is not None:
+            self.pool.terminate()
+            self.pool = None
+        self.close()
+        return False
+
+
+def pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, num_threads, with_pred=True):
+    """call.py:308-333.  ``true_path[path]`` holds the uint8 [5,32,3] matrix (or a PNG file name).  One-shot use of
+    ``RecordPool``.  ``with_pred=False`` leaves out the trailing ``[path, pred]`` of every record, which
+    ``get_vcf_records`` drops anyway (call.py:357-363)."""
+    with RecordPool(ref_file, chroms, vartype_classes, num_threads, with_pred) as rp:
+        rp.asked = POOL_MIN                    # one request: no later group to amortise the pool over, so decide now
+        if len(final_preds) < POOL_MIN:
+            rp.num_threads = 1
+        return rp.collect(rp.submit(final_preds, true_path))
 
 
 def pred_vcf_records_none(none_preds, chroms):

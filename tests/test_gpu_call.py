@@ -59,3 +59,33 @@ def test_call_neusomatic_needs_cuda_flag(tmp_path):
     from neusomatic_b200.call import call_neusomatic
     with pytest.raises(RuntimeError):
         call_neusomatic([], "x.fa", str(tmp_path), os.path.join(GOLDEN, "std_v014.pth"), 1, 100, 1000, 0.7, 0.4, False, False)
+
+
+def test_call_neusomatic_with_the_record_pool(tmp_path):
+    """A call large enough for the process pool of the VCF stage (call.py:308-333): several groups, > 2048 called variants,
+    the pool forked after CUDA is up and fed while the next group is scored.  Same pred.vcf / none.vcf bytes as the same call
+    with the records built in the calling process."""
+    from neusomatic_b200 import synth
+    from neusomatic_b200.call import call_neusomatic
+    n = 24000
+    cand, seqs, chroms = synth.genome_candidates(n, seed=31)
+    fa = str(tmp_path / "ref.fa")
+    with open(fa, "w") as f:
+        for c in chroms:
+            f.write(">%s\n" % c)
+            f.writelines(seqs[c][i:i + 60] + "\n" for i in range(0, len(seqs[c]), 60))
+    tsvs = []
+    for k, (lo, hi) in enumerate(((0, 9000), (9000, 17000), (17000, n))):
+        tsvs.append(str(tmp_path / ("candidates_%d.tsv" % k)))
+        with open(tsvs[-1], "w") as f:
+            for i in range(lo, hi):
+                f.write(oracle.encode_tsv_line(i - lo, cand.tags[i], cand.matrices[i]))
+    ck = os.path.join(GOLDEN, "std_v014.pth")
+    outs = {}
+    for threads in (1, 4):
+        out_dir = str(tmp_path / ("out%d" % threads))
+        # max_load_candidates 16000: every file is its own piece, groups end after > 1600 candidates -> three groups
+        call_neusomatic(tsvs, fa, out_dir, ck, threads, 100, 16000, 0.7, 0.4, False, True)
+        outs[threads] = (open(out_dir + "/pred.vcf").read(), open(out_dir + "/none.vcf").read())
+    assert outs[4][0].count("\n") > 2048
+    assert outs[1] == outs[4]

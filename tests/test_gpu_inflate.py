@@ -113,6 +113,9 @@ def test_device_inflate_never_returns_wrong_bytes():
         cases.append(s[:-1] + bytes([s[-1] ^ 1]))                                                           # wrong Adler-32
         co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_DEFAULT_STRATEGY, d[:64])                     # preset dictionary
         cases.append(co.compress(d) + co.flush())
+        cf = zlib.compressobj(6)                                                                            # a valid stream of > 8192 characters
+        cases.append(b"".join(cf.compress(d[k:k + 4]) + cf.flush(zlib.Z_SYNC_FLUSH) for k in range(0, len(d), 4)) + cf.flush())
+        assert len(base64.b64encode(cases[-1])) > 8192 and zlib.decompress(cases[-1]) == d
         for _ in range(120):                                                                                # bit flips
             b = bytearray(s)
             for _k in range(int(rng.integers(1, 4))):

@@ -117,3 +117,65 @@ def test_fasta_reader(tmp_path):
         f.write("chr1\t168\t23\t50\t51\nchrM\t7\t%d\t7\t8\n" % (23 + 168 + 4 + 23))
     with FastaFile(str(p)) as fa:
         assert fa.fetch("chr1", 49, 120) == seqs["chr1"][49:120] and fa.fetch("chrM", 0, 7) == "GATTACA"
+
+
+def _planted_tables(n, seed, groups):
+    """Genome-consistent candidates with planted (noisy) predictions, the called ones dealt into ``groups`` PredTables:
+    ([(PredTable, images)], chroms, seqs)."""
+    from neusomatic_b200 import synth
+    from neusomatic_b200.call import PredTable, non_transformed_images
+    cand, seqs, chroms = synth.genome_candidates(n, seed=seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a1 = np.array([oracle.VARTYPE_CLASSES.index(t.split(".")[4]) for t in cand.tags])
+    ln = np.array([min(int(t.split(".")[6]), 3) for t in cand.tags])
+    p1 = rng.dirichlet([0.3] * 4, size=n).astype(np.float32)
+    p1[np.arange(n), a1] += 2
+    p1 /= p1.sum(1, keepdims=True)
+    p3 = rng.dirichlet([0.3] * 4, size=n).astype(np.float32)
+    p3[np.arange(n), ln] += 2
+    p3 /= p3.sum(1, keepdims=True)
+    o2 = (np.asarray(cand.center, np.float32) + rng.normal(0, 0.6, n).astype(np.float32)).reshape(-1, 1)
+    called = np.nonzero(a1 != 2)[0]
+    out = []
+    for keep in np.array_split(called, groups):
+        tab = PredTable()
+        for lo in range(0, len(keep), 700):                  # several parts, as the pipeline files them
+            k = keep[lo:lo + 700]
+            tab.add([cand.tags[i] for i in k], a1[k], o2[k], ln[k], p1[k], p3[k], np.log(p1[k]), np.log(p3[k]))
+        img = non_transformed_images(cand.matrices[keep], np.asarray(cand.center)[keep])
+        out.append((tab, {cand.tags[i]: im for i, im in zip(keep, img)}))
+    return out, chroms, seqs
+
+
+def _same(x, y):
+    if isinstance(x, (list, tuple)):
+        return len(x) == len(y) and all(_same(u, v) for u, v in zip(x, y))
+    if isinstance(x, np.ndarray):
+        return x.dtype == y.dtype and np.array_equal(x, y)
+    return type(x) is type(y) and x == y
+
+
+def test_record_pool_equals_the_serial_stage(tmp_path, monkeypatch):
+    """call.py:308-333 builds the records in a process pool; here the pool gets chunks of the table as arrays and works
+    while the caller scores the next group.  Same records, same order, same element types as the in-process loop -- also
+    for a FASTA without .fai (the parent's index travels with the jobs) and with the [path, pred] tail left out."""
+    tabs, chroms, seqs = _planted_tables(5200, 3, 2)
+    fa = str(tmp_path / "genome.fa")
+    with open(fa, "w") as f:
+        for c in chroms:
+            f.write(">%s\n" % c)
+            f.writelines(seqs[c][i:i + 60] + "\n" for i in range(0, len(seqs[c]), 60))
+    monkeypatch.setattr(vcf, "POOL_MIN", 1000)
+    serial = [vcf.pred_vcf_records(MemoryFasta(seqs), t[0], t[1], chroms, oracle.VARTYPE_CLASSES, 1) for t in tabs]
+    assert all(len(s) > 800 for s in serial)
+    one_shot = vcf.pred_vcf_records(fa, tabs[0][0], tabs[0][1], chroms, oracle.VARTYPE_CLASSES, 3)
+    assert _same(one_shot, serial[0])
+    with vcf.RecordPool(fa, chroms, oracle.VARTYPE_CLASSES, 3, with_pred=False) as rp:
+        handles = [rp.submit(t[0], t[1]) for t in tabs]      # the second is submitted while the first is being built
+        assert handles[0][0] == "pending" and rp.pool is not None
+        got = [rp.collect(h) for h in handles]
+    for g, s in zip(got, serial):
+        assert len(g) == len(s)
+        assert all(x[0] == y[0] and _same(x[1][:5], y[1][:5]) and x[1][5] is None for x, y in zip(g, s))
+    lines = lambda recs: "".join(vcf.vcf_lines(vcf.get_vcf_records(dict(recs)), {c: i for i, c in enumerate(chroms)}, 0.7, 0.4))
+    assert lines(got[0]) == lines(serial[0]) and lines(got[1]) == lines(serial[1])
