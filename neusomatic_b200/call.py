@@ -584,12 +584,19 @@ def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, 
                     logger.warning("Skip {} with 0 candidates".format(group[-1][0]))
                     continue
                 final_preds, none_preds, true_path = PredTable(vartype_classes), PredTable(vartype_classes), {}
+                t0 = time.perf_counter()
                 run_tsv_pipeline(scorers, group, slice_size, num_threads, final_preds, none_preds, true_path)
+                t1 = time.perf_counter()
                 logger.info("Called {} candidates in this batch.".format(n_group))
                 handles.append(records.submit(final_preds, true_path))
-                all_vcf_records_none.extend(pred_vcf_records_none(none_preds, chroms))
+                t2 = time.perf_counter()
+                all_vcf_records_none.extend(pred_vcf_records_none(none_preds, chroms, with_pred=False))
+                logger.info("{} candidates scored in {:.3f} s; {} called variants handed to the VCF stage in {:.3f} s; none.vcf "
+                            "filter {:.3f} s".format(n_group, t1 - t0, len(true_path), t2 - t1, time.perf_counter() - t2))
+            t0 = time.perf_counter()
             for h in handles:
                 all_vcf_records.extend(records.collect(h))
+            logger.info("VCF records collected after {:.3f} s more".format(time.perf_counter() - t0))
     finally:
         for sc in scorers:
             sc.engine.close()

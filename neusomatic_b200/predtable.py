@@ -99,7 +99,7 @@ class PredTable(collections.abc.Mapping):
     def __contains__(self, path):
         return path in self._idx()
 
-    def none_records(self, chroms):
+    def none_records(self, chroms, with_pred=True):
         """call.py:336-354 on arrays: prob by allele-length class in float32, keep prob > 0.005, materialise only those."""
         if not self._paths:
             return {}.items()
@@ -128,7 +128,7 @@ class PredTable(collections.abc.Mapping):
         for r, pr in zip(sel, prob):
             path = self._paths[r]
             chrom, pos, ref, alt = path.split(".")[:4]
-            records[path] = [chroms[int(chrom)], pos, ref, alt, pr, [path, self._entry(r)]]
+            records[path] = [chroms[int(chrom)], pos, ref, alt, pr, [path, self._entry(r)] if with_pred else None]
         return records.items()
 
     def columns_of(self, paths):

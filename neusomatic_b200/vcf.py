@@ -346,10 +346,11 @@ def pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, 
         return rp.collect(rp.submit(final_preds, true_path))
 
 
-def pred_vcf_records_none(none_preds, chroms):
-    """call.py:336-354: candidates called NONE whose variant probability is still above 0.005 go to none.vcf."""
+def pred_vcf_records_none(none_preds, chroms, with_pred=True):
+    """call.py:336-354: candidates called NONE whose variant probability is still above 0.005 go to none.vcf.
+    ``with_pred=False`` (PredTable only) leaves out the trailing ``[path, pred]`` that get_vcf_records drops."""
     if hasattr(none_preds, "none_records"):         # call.PredTable: the same filter on whole arrays
-        return none_preds.none_records(chroms)
+        return none_preds.none_records(chroms, with_pred)
     records = {}
     for path, pred in none_preds.items():
         chrom, pos, ref, alt, _, _, _, _, _ = path.split(".")
@@ -369,9 +370,8 @@ def get_vcf_records(all_vcf_records):
     return [all_vcf_records[path][:-1] for path in all_vcf_records if all_vcf_records[path]]
 
 
-def vcf_lines(vcf_records, chroms_order, pass_threshold, lowqual_threshold):
-    """The lines write_vcf emits (call.py:366-387), in order, first occurrence of a repeated line only."""
-    records = sorted((r for r in vcf_records if len(r) > 0), key=lambda x: [chroms_order[x[0]], x[1]])
+def _vcf_lines_scalar(records, pass_threshold, lowqual_threshold):
+    """call.py:366-387 record by record, in the reference's own expressions."""
     lines, seen = [], set()
     for chrom_, pos_, ref_, alt_, prob in records:
         if ref_ == alt_:
@@ -379,6 +379,42 @@ def vcf_lines(vcf_records, chroms_order, pass_threshold, lowqual_threshold):
         filter_ = "PASS" if prob >= pass_threshold else ("LowQual" if prob >= lowqual_threshold else "REJECT")
         line = "\t".join([chrom_, str(pos_), ".", ref_, alt_, "{:.4f}".format(np.round(prob2phred(prob), 4)), filter_,
                           "SCORE={:.4f}".format(np.round(prob, 4)), "GT", "0/1"]) + "\n"
+        if line not in seen:
+            seen.add(line)
+            lines.append(line)
+    return lines
+
+
+def vcf_lines(vcf_records, chroms_order, pass_threshold, lowqual_threshold):
+    """The lines write_vcf emits (call.py:366-387), in order, first occurrence of a repeated line only.
+
+    When every probability is an np.float32 scalar in [0, 1] (what this package's dictionaries hold), the two roundings and
+    the threshold comparisons run on whole arrays: np.round on a float32 array is the same multiply / rint / divide as on a
+    float32 scalar, and formatting goes through the same Python float.  log10 stays a scalar call per record -- an array
+    loop may use a different (SIMD) implementation whose last bit can differ, which would show in the fourth decimal of QUAL.
+    Anything else (Python floats, out-of-range values) takes the record-by-record path."""
+    records = sorted((r for r in vcf_records if len(r) > 0), key=lambda x: [chroms_order[x[0]], x[1]])
+    records = [r for r in records if r[2] != r[3]]
+    if not records or not all(type(r[4]) is np.float32 for r in records):
+        return _vcf_lines_scalar(records, pass_threshold, lowqual_threshold)
+    prob = np.array([r[4] for r in records], np.float32)
+    if not ((prob >= 0) & (prob <= 1)).all():
+        return _vcf_lines_scalar(records, pass_threshold, lowqual_threshold)        # prob2phred asserts
+    one_minus = np.float32(1) - prob
+    log10 = np.log10
+    q = np.empty(len(records), np.float32)
+    for i, v in enumerate(one_minus):                      # utils.py:84-95 with p an np.float32: float32 throughout
+        q[i] = -10 * log10(v) if v > 0 else 100
+    q[prob == 0] = 0
+    q = np.where(q > 100, np.float32(100), q)
+    qual = np.round(q, 4).astype(np.float64).tolist()
+    score = np.round(prob, 4).astype(np.float64).tolist()
+    is_pass = (prob >= pass_threshold).tolist()
+    is_low = (prob >= lowqual_threshold).tolist()
+    lines, seen = [], set()
+    for r, ql, sc, ps, lq in zip(records, qual, score, is_pass, is_low):
+        line = "%s\t%s\t.\t%s\t%s\t%.4f\t%s\tSCORE=%.4f\tGT\t0/1\n" % (
+            r[0], r[1], r[2], r[3], ql, "PASS" if ps else ("LowQual" if lq else "REJECT"), sc)
         if line not in seen:
             seen.add(line)
             lines.append(line)

@@ -179,3 +179,23 @@ def test_record_pool_equals_the_serial_stage(tmp_path, monkeypatch):
         assert all(x[0] == y[0] and _same(x[1][:5], y[1][:5]) and x[1][5] is None for x, y in zip(g, s))
     lines = lambda recs: "".join(vcf.vcf_lines(vcf.get_vcf_records(dict(recs)), {c: i for i, c in enumerate(chroms)}, 0.7, 0.4))
     assert lines(got[0]) == lines(serial[0]) and lines(got[1]) == lines(serial[1])
+
+
+def test_vcf_lines_array_path_equals_the_record_by_record_path():
+    """write_vcf's lines (call.py:366-387): the whole-array rounding / formatting path against the reference's expressions
+    applied record by record, on 6 x 10^4 records including the exact thresholds, 0, 1 and probabilities within 1e-12 of 1."""
+    rng = np.random.Generator(np.random.PCG64(0))
+    n = 60000
+    p = rng.random(n).astype(np.float32)
+    p[:200], p[200:400] = np.float32(0), np.float32(1)
+    p[400:2000] = (1 - 10 ** (-rng.uniform(3, 12, 1600))).astype(np.float32)
+    p[2000:4000] = rng.choice(np.array([0.7, 0.4, 0.69995, 0.70005, 0.39995, 0.40005], np.float32), 2000)
+    recs = [["chr%d" % (i % 3), int(rng.integers(1, 10 ** 5)), "A", "AC"[i % 2], p[i]] for i in range(n)]
+    order = {"chr0": 0, "chr1": 1, "chr2": 2}
+    srt = [r for r in sorted(recs, key=lambda x: [order[x[0]], x[1]]) if r[2] != r[3]]
+    want = vcf._vcf_lines_scalar(srt, 0.7, 0.4)
+    assert vcf.vcf_lines(recs, order, 0.7, 0.4) == want and len(want) > 25000
+    mixed = [list(r) for r in recs[:500]]
+    mixed[7][4] = float(mixed[7][4])                         # one Python float: the whole call takes the scalar path
+    srt = [r for r in sorted(mixed, key=lambda x: [order[x[0]], x[1]]) if r[2] != r[3]]
+    assert vcf.vcf_lines(mixed, order, 0.7, 0.4) == vcf._vcf_lines_scalar(srt, 0.7, 0.4)
