@@ -516,6 +516,10 @@ def run_tsv_pipeline(scorers, pieces, batch, num_threads, final_preds, none_pred
 PIPELINE_TIMES = {}      # busy seconds per stage of the last run_tsv_pipeline call (waits for the neighbouring stages excluded)
 
 
+PREFORK_CANDIDATES = 200000       # calls at least this large start the VCF stage's process pool up front
+RUN_CANDIDATES = 1000000          # consecutive groups share one run of the pipeline up to this many candidates
+
+
 def plan_call_groups(counts, max_load_candidates):
     """The grouping of call.py:468-507 on candidate counts: files longer than max_load_candidates / 2 are cut into pieces
     of max(1, max_load_candidates / 2) candidates (the reference re-writes them with merge_tsvs; here a piece is a range of
@@ -543,63 +547,87 @@ def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, 
                     pass_threshold, lowqual_threshold, ensemble, use_cuda):
     """call.py:389-554, same arguments and outputs (``{out_dir}/pred.vcf`` -- returned -- and ``{out_dir}/none.vcf``).
 
-    Differences in mechanism, none in results: the candidates are decoded by the C++ reader into pinned batches and scored
-    through ``nsc_score_host_u8`` on every visible GPU (candidate slices round-robin; the reference wraps the module in
-    nn.DataParallel, call.py:417-419); oversized TSVs are read in ranges instead of being re-written by merge_tsvs; the
-    pileup images go to pred_vcf_records_path in memory instead of through PNG files; ``batch_size`` only bounds the slice
-    size from below (a slice is the unit of the decode / score / file pipeline, not of the arithmetic)."""
+    Differences in mechanism, none in results: the candidates' lines are staged by the C++ reader into pinned batches, their
+    image fields inflated on the device and scored (``nsc_score_host_b64``) on every visible GPU (candidate slices
+    round-robin; the reference wraps the module in nn.DataParallel, call.py:417-419); oversized TSVs are read in ranges
+    instead of being re-written by merge_tsvs, and consecutive groups of call.py:468-507 share one run of the pipeline; the
+    pileup images go to pred_vcf_records_path in memory instead of through PNG files, and the records are built by the
+    process pool while later candidates are being scored; ``batch_size`` only bounds the slice size from below (a slice is
+    the unit of the stage / score / file pipeline, not of the arithmetic)."""
     from .tsv import CandidateTSV
     if not use_cuda:
         raise RuntimeError("neusomatic_b200 scores on CUDA only (no CPU fallback); the reference's CPU path is call.py itself")
     logger.info("-----------------Call Somatic Mutations--------------------")
+    t_start = time.perf_counter()
     fasta = open_fasta(ref_file)
     chroms = list(fasta.references)
     chroms_order = {c: i for i, c in enumerate(chroms)}
     vartype_classes = list(VARTYPE_CLASSES)
     ck = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location="cpu", weights_only=True)
+    num_channels = load_checkpoint(ck)[0]["conv1.weight"].shape[1]
+    counts = []
+    for f in candidates_tsv:
+        t = CandidateTSV(f, num_anns=num_channels - 26)
+        counts.append((f, len(t)))
+        t.close()
+    # the records of the called variants (call.py:308-333) are built by a process pool WHILE later candidates are scored;
+    # for a large call the pool is forked here, before this function touches CUDA
+    records = RecordPool(ref_file, chroms, vartype_classes, num_threads, with_pred=False)
+    if sum(c[1] for c in counts) >= PREFORK_CANDIDATES:
+        records.prefork()
     n_dev = max(1, torch.cuda.device_count())
     if n_dev > 1:
         logger.info("We use {} GPUs!".format(n_dev))
-    scorers = [CandidateScorer(ck, ensemble=ensemble, device=d) for d in range(n_dev)]
-    logger.info("tag: {}".format(scorers[0].meta["tag"]))
-    if not os.path.exists(out_dir):
-        os.mkdir(out_dir)
+    scorers = []
     try:
-        counts = []
-        for f in candidates_tsv:
-            t = CandidateTSV(f, num_anns=scorers[0].C - 26)
-            counts.append((f, len(t)))
-            t.close()
+        scorers = [CandidateScorer(ck, ensemble=ensemble, device=d) for d in range(n_dev)]
+        logger.info("tag: {}".format(scorers[0].meta["tag"]))
+        logger.info("model on {} GPU(s) after {:.3f} s".format(n_dev, time.perf_counter() - t_start))
+        if not os.path.exists(out_dir):
+            os.mkdir(out_dir)
         all_vcf_records, all_vcf_records_none = [], []
         slice_size = int(min(65536, max(batch_size, 16384)))
-        # the records of a group's called variants (call.py:308-333) are built by a process pool WHILE the next group is
-        # scored; collected in group order at the end
-        with RecordPool(ref_file, chroms, vartype_classes, num_threads, with_pred=False) as records:
-            handles = []
-            for group in plan_call_groups(counts, max_load_candidates):
+        handles = []
+        with records:
+            # the reference's groups (call.py:468-507), in its order; consecutive groups share one run of the pipeline until
+            # the run holds RUN_CANDIDATES: a later candidate still replaces an earlier one with the same tag, exactly as the
+            # per-group dictionaries merged by dict() do, and no run pays its fill / drain for a few thousand candidates
+            run, run_n = [], 0
+            groups = plan_call_groups(counts, max_load_candidates)
+            for gi, group in enumerate(groups):
                 logger.info("Run for candidate files: {}".format(sorted({g[0] for g in group})))
                 n_group = sum(g[2] for g in group)
                 logger.info("N_dataset: {}".format(n_group))
                 if n_group == 0:
                     logger.warning("Skip {} with 0 candidates".format(group[-1][0]))
-                    continue
-                final_preds, none_preds, true_path = PredTable(vartype_classes), PredTable(vartype_classes), {}
-                t0 = time.perf_counter()
-                run_tsv_pipeline(scorers, group, slice_size, num_threads, final_preds, none_preds, true_path)
-                t1 = time.perf_counter()
-                logger.info("Called {} candidates in this batch.".format(n_group))
-                handles.append(records.submit(final_preds, true_path))
-                t2 = time.perf_counter()
-                all_vcf_records_none.extend(pred_vcf_records_none(none_preds, chroms, with_pred=False))
-                logger.info("{} candidates scored in {:.3f} s; {} called variants handed to the VCF stage in {:.3f} s; none.vcf "
-                            "filter {:.3f} s".format(n_group, t1 - t0, len(true_path), t2 - t1, time.perf_counter() - t2))
+                else:
+                    run += group
+                    run_n += n_group
+                if run and (run_n >= RUN_CANDIDATES or gi == len(groups) - 1):
+                    final_preds, none_preds, true_path = PredTable(vartype_classes), PredTable(vartype_classes), {}
+                    t0 = time.perf_counter()
+                    run_tsv_pipeline(scorers, run, slice_size, num_threads, final_preds, none_preds, true_path)
+                    t1 = time.perf_counter()
+                    logger.info("Called {} candidates in this batch.".format(run_n))
+                    handles.append(records.submit(final_preds, true_path))
+                    t2 = time.perf_counter()
+                    all_vcf_records_none.extend(pred_vcf_records_none(none_preds, chroms, with_pred=False))
+                    logger.info("{} candidates scored in {:.3f} s; {} called variants handed to the VCF stage in {:.3f} s; "
+                                "none.vcf filter {:.3f} s".format(run_n, t1 - t0, len(true_path), t2 - t1, time.perf_counter() - t2))
+                    run, run_n = [], 0
             t0 = time.perf_counter()
             for h in handles:
                 all_vcf_records.extend(records.collect(h))
             logger.info("VCF records collected after {:.3f} s more".format(time.perf_counter() - t0))
+    except BaseException:
+        if records.pool is not None:
+            records.pool.terminate()
+            records.pool = None
+        raise
     finally:
         for sc in scorers:
             sc.engine.close()
+    logger.info("all groups done after {:.3f} s".format(time.perf_counter() - t_start))
     all_vcf_records = dict(all_vcf_records)
     all_vcf_records_none = dict(all_vcf_records_none)
     logger.info("Prepare Output VCF")
@@ -608,5 +636,5 @@ def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, 
     logger.info("Prepare Non-Somatics VCF")
     write_vcf(get_vcf_records(all_vcf_records_none), "{}/none.vcf".format(out_dir), chroms_order, pass_threshold,
               lowqual_threshold)
-    logger.info("Calling is Done.")
+    logger.info("Calling is Done. ({:.3f} s)".format(time.perf_counter() - t_start))
     return output_vcf

@@ -278,6 +278,12 @@ class RecordPool:
         self.pool = None
         self.asked = 0
 
+    def prefork(self):
+        """Start the pool now (a caller that knows a large call is coming forks before CUDA is initialised: cheaper, and no
+        other thread is running yet)."""
+        if self.pool is None and self.num_threads > 1 and isinstance(self.ref_file, str):
+            self.pool = multiprocessing.Pool(min(self.num_threads, 32))
+
     def _serial(self, final_preds, true_path, paths):
         fasta = open_fasta(self.ref_file)
         out = []
