@@ -346,9 +346,14 @@ def _split_into_tables(r, tags, lens, matrices, center, final_preds, none_preds,
     vt = [tags[i] for i in var]
     final_preds.add(vt, *[np.asarray(r[c])[var] for c in cols], lens=None if lens is None else lens[var])
     if 8 * len(var) < len(tags):             # few called variants (the usual case): cut them out instead of gathering the rest
-        nt = list(tags)
-        for i in var[::-1]:
-            del nt[i]
+        if len(var) <= 64:
+            nt = list(tags)
+            for i in var[::-1]:                  # (each del moves the tail of the list: only worth it for a handful)
+                del nt[i]
+        else:
+            keep = np.ones(len(tags), bool)
+            keep[var] = False
+            nt = [t for t, k in zip(tags, keep.tolist()) if k]
         cut = lambda a: None if a is None else np.delete(np.asarray(a), var, axis=0)
         none_preds.add(nt, *[cut(r[c]) for c in cols], lens=cut(lens), hashes=cut(hashes))
     else:
