@@ -28,7 +28,10 @@ Printed JSON (one line, rank 0):
   extra     records measured in the same run with the same build: `ensemble` (BASELINE configs[3], C=119: value + e2e),
             `train` (configs[4]: one train.py step per GPU + NCCL all-reduce), `gpu_incumbent` (the stock nn.Module in
             eager PyTorch on the same GPU: fp32 and TF32-allowed, inference and fwd+bwd+SGD -- informational, N=1 only),
-            `e2e_tsv` (a reference-format candidate TSV -> dictionaries through the decode/score/file pipeline, N=1 only)
+            `e2e_tsv` (a reference-format candidate TSV -> dictionaries + none.vcf filter through the stage / device-inflate +
+            score / file pipeline, with the same call on the host-inflate path and the oracle's chain beside it),
+            `e2e_tsv_ensemble` (the same for C=119 lines with 93 annotation fields), `whole_call` (call_neusomatic end to end:
+            TSVs + FASTA + checkpoint -> pred.vcf + none.vcf) -- these three N=1 only
 `--impl reference` times the CPU port alone on the host cores (tier rule: the reference is Python over PyTorch CPU
 kernels and has no setup.py to install; nothing of ours is on that path).
 """
@@ -580,6 +583,63 @@ def measure_tsv_ensemble(args, rk, local_rank, n=262144):
             "what": "e2e_tsv for the ensemble network: C=119, 93 annotation fields per line (BASELINE.json configs[3])"}
 
 
+def measure_whole_call(args, rk, local_rank, n_none=500000, n_gen=12000):
+    """The reference's program end to end (call.py:389-554): candidate TSVs + FASTA + checkpoint -> pred.vcf + none.vcf through
+    ``call_neusomatic``, on a generated workload with a realistic share of called variants (tools/whole_call_probe.py)."""
+    import base64
+    import shutil
+    import zlib
+    from neusomatic_b200 import synth
+    from neusomatic_b200.call import call_neusomatic
+    td = tempfile.mkdtemp(prefix="nsc_bench_call_")
+    cand, seqs, chroms = synth.genome_candidates(n_gen, seed=41)
+    fa = os.path.join(td, "ref.fa")
+    with open(fa, "w") as f:
+        for c in chroms:
+            f.write(">%s\n" % c)
+            f.writelines(seqs[c][i:i + 60] + "\n" for i in range(0, len(seqs[c]), 60))
+    pool = synth.structured_pileups(12000, seed=4321)
+    sel = [i for i, t in enumerate(pool.tags) if t.split(".")[4] == "NONE"][:4096]          # pileups without a variant signal
+    blobs = [base64.b64encode(zlib.compress(np.ascontiguousarray(pool.matrices[i]))).decode("ascii") for i in sel]
+    tags = [pool.tags[i] for i in sel]
+    gblobs = [base64.b64encode(zlib.compress(np.ascontiguousarray(cand.matrices[i]))).decode("ascii") for i in range(n_gen)]
+    files, per = [], (n_none + n_gen + 3) // 4
+    every = max(1, (n_none + n_gen) // max(n_gen, 1))
+    k = g = 0
+    for fi in range(4):
+        files.append(os.path.join(td, "candidates_%d.tsv" % fi))
+        with open(files[-1], "w") as f:
+            for i in range(per):
+                j = fi * per + i
+                if j >= n_none + n_gen:
+                    break
+                if j % every == 0 and g < n_gen:
+                    f.write("%d\t1\t%s\t%s\n" % (i, cand.tags[g], gblobs[g]))
+                    g += 1
+                else:
+                    tf = tags[k % len(sel)].split(".")
+                    tf[0], tf[1] = "0", str(10 ** 7 + k)
+                    f.write("%d\t1\t%s\t%s\n" % (i, ".".join(tf), blobs[k % len(sel)]))
+                    k += 1
+    total = k + g
+    threads = os.cpu_count() or 1
+    ck = os.path.join(ROOT, "tests", "golden", "std_v014.pth")
+    times = []
+    for it in range(3):                              # the first call pays the workspace / pinned-slot / pool start-up
+        out = os.path.join(td, "out%d" % it)
+        t0 = time.perf_counter()
+        call_neusomatic(files, fa, out, ck, threads, 1000, 400000, 0.7, 0.4, False, True)
+        times.append(time.perf_counter() - t0)
+    n_pred = sum(1 for ln in open(out + "/pred.vcf") if not ln.startswith("#"))
+    n_none_rec = sum(1 for ln in open(out + "/none.vcf") if not ln.startswith("#"))
+    shutil.rmtree(td, ignore_errors=True)
+    el = float(min(times[1:]))
+    return {"value": total / el, "unit": "candidates/s", "candidates": total, "seconds": el, "first_call_seconds": times[0],
+            "pred_vcf_records": n_pred, "none_vcf_records": n_none_rec, "host_threads": threads,
+            "what": "call_neusomatic (call.py:389-554): 4 candidate TSVs + FASTA + v0.1.4 checkpoint -> pred.vcf + none.vcf; device "
+                    "inflate + scoring, the VCF records of the called variants built by a process pool meanwhile"}
+
+
 def roofline_record(m, B, steps, world, C):
     """Tensor roofline of the dominant kernel family (the eight 64->64 convolutions) from the live per-kernel event times."""
     pk = peaks()
@@ -694,6 +754,7 @@ def main():
             extra["gpu_incumbent"] = measure_incumbent(args, rk, local_rank)
             extra["e2e_tsv"] = measure_tsv(args, rk, local_rank)
             extra["e2e_tsv_ensemble"] = measure_tsv_ensemble(args, rk, local_rank)
+            extra["whole_call"] = measure_whole_call(args, rk, local_rank)
 
     roof = roofline_record(m, B, args.steps, world, C)
 
