@@ -199,3 +199,21 @@ def test_vcf_lines_array_path_equals_the_record_by_record_path():
     mixed[7][4] = float(mixed[7][4])                         # one Python float: the whole call takes the scalar path
     srt = [r for r in sorted(mixed, key=lambda x: [order[x[0]], x[1]]) if r[2] != r[3]]
     assert vcf.vcf_lines(mixed, order, 0.7, 0.4) == vcf._vcf_lines_scalar(srt, 0.7, 0.4)
+
+
+def test_record_pool_propagates_a_failed_record(tmp_path, monkeypatch):
+    """call.py:326-329: a worker that fails returns None and the stage raises -- in the pool as in the calling process."""
+    tabs, chroms, seqs = _planted_tables(2600, 6, 1)
+    tab, images = tabs[0]
+    fa = str(tmp_path / "genome.fa")
+    with open(fa, "w") as f:
+        for c in chroms:
+            f.write(">%s\n" % c)
+            f.writelines(seqs[c][i:i + 60] + "\n" for i in range(0, len(seqs[c]), 60))
+    victim = list(tab.keys())[1500]
+    images[victim] = str(tmp_path / "no_such_image.png")      # the reference's PNG hand-over with a missing file: raises inside
+    monkeypatch.setattr(vcf, "POOL_MIN", 1000)
+    for threads in (1, 3):
+        with pytest.raises(Exception, match="pred_vcf_records_path failed"):
+            vcf.pred_vcf_records(fa, tab, {k: (v if k != victim else images[victim]) for k, v in images.items()}, chroms,
+                                 oracle.VARTYPE_CLASSES, threads)
