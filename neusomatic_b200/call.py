@@ -575,8 +575,8 @@ def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, 
         t = CandidateTSV(f, num_anns=num_channels - 26)
         counts.append((f, len(t)))
         t.close()
-    # the records of the called variants (call.py:308-333) are built by a process pool WHILE later candidates are scored;
-    # for a large call the pool is forked here, before this function touches CUDA
+    # the records of the called variants (call.py:308-333) are built by a pool of worker processes WHILE later candidates are
+    # scored; for a large call the workers are started here, so that they load while the model is set up
     records = RecordPool(ref_file, chroms, vartype_classes, num_threads, with_pred=False)
     if sum(c[1] for c in counts) >= PREFORK_CANDIDATES:
         records.prefork()
@@ -625,9 +625,7 @@ def call_neusomatic(candidates_tsv, ref_file, out_dir, checkpoint, num_threads, 
                 all_vcf_records.extend(records.collect(h))
             logger.info("VCF records collected after {:.3f} s more".format(time.perf_counter() - t0))
     except BaseException:
-        if records.pool is not None:
-            records.pool.terminate()
-            records.pool = None
+        records.close(kill=True)
         raise
     finally:
         for sc in scorers:

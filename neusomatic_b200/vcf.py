@@ -21,6 +21,13 @@ from __future__ import annotations
 
 import logging
 import multiprocessing
+import os
+import pickle
+import queue
+import struct
+import subprocess
+import sys
+import threading
 import traceback
 
 import numpy as np
@@ -243,7 +250,7 @@ def pred_vcf_records_path(record):
 
 
 POOL_CHUNK = 512          # called variants per pool task
-POOL_MIN = 2048           # the pool is started once this many records have been asked for (forking costs ~0.3 s)
+POOL_MIN = 2048           # the workers are started once this many records have been asked for
 
 
 def _records_chunk(job):
@@ -265,24 +272,113 @@ def _records_chunk(job):
     return out
 
 
+def _worker_main():
+    """A pool worker: length-prefixed pickled jobs on stdin, results on stdout, until stdin closes.  Started as a fresh
+    interpreter (``python -c``): it imports numpy and this module, never torch or CUDA, and shares nothing with its parent."""
+    inp, out = sys.stdin.buffer, sys.stdout.buffer
+    sys.stdout = sys.stderr                # a stray print must not end up in the result stream
+    while True:
+        hdr = inp.read(8)
+        if len(hdr) < 8:
+            return
+        job = pickle.loads(inp.read(struct.unpack("<Q", hdr)[0]))
+        blob = pickle.dumps(_records_chunk(job), protocol=pickle.HIGHEST_PROTOCOL)
+        out.write(struct.pack("<Q", len(blob)))
+        out.write(blob)
+        out.flush()
+
+
+class _Workers:
+    """``n`` worker interpreters fed from one queue (a feeder thread per worker: send a job, wait for its result)."""
+
+    def __init__(self, n):
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        cmd = [sys.executable, "-c", "from neusomatic_b200.vcf import _worker_main; _worker_main()"]
+        self.jobs = queue.Queue()
+        self.results, self.failed, self.cv = {}, None, threading.Condition()
+        self.procs = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env) for _ in range(n)]
+        self.threads = [threading.Thread(target=self._feed, args=(p,), daemon=True) for p in self.procs]
+        for t in self.threads:
+            t.start()
+
+    def _feed(self, proc):
+        while True:
+            item = self.jobs.get()
+            if item is None:
+                return
+            seq, job = item
+            try:
+                blob = pickle.dumps(job, protocol=pickle.HIGHEST_PROTOCOL)
+                proc.stdin.write(struct.pack("<Q", len(blob)))
+                proc.stdin.write(blob)
+                proc.stdin.flush()
+                hdr = proc.stdout.read(8)
+                if len(hdr) < 8:
+                    raise RuntimeError("a VCF-stage worker exited (code %s)" % proc.poll())
+                res = pickle.loads(proc.stdout.read(struct.unpack("<Q", hdr)[0]))
+                with self.cv:
+                    self.results[seq] = res
+                    self.cv.notify_all()
+            except Exception as ex:      # noqa: BLE001
+                with self.cv:
+                    self.failed = ex
+                    self.cv.notify_all()
+                return
+
+    def wait(self, seqs):
+        with self.cv:
+            while self.failed is None and not all(q in self.results for q in seqs):
+                self.cv.wait()
+            if self.failed is not None:
+                raise RuntimeError("VCF stage: %s" % self.failed)
+            return [self.results.pop(q) for q in seqs]
+
+    def stop(self, kill=False):
+        for _ in self.threads:
+            self.jobs.put(None)
+        for p in self.procs:
+            try:
+                if kill:
+                    p.kill()
+                else:
+                    p.stdin.close()
+            except Exception:      # noqa: BLE001
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:      # noqa: BLE001
+                p.kill()
+        for p in self.procs:
+            for f in (p.stdin, p.stdout):
+                try:
+                    f.close()
+                except Exception:      # noqa: BLE001
+                    pass
+
+
 class RecordPool:
     """call.py:308-333 as a service: ``submit(final_preds, true_path)`` starts building the VCF records of one group of
     candidates and returns a handle, ``collect(handle)`` returns them in the order of ``final_preds``.  With
-    ``num_threads`` > 1, a PredTable and a FASTA path, the records are built by a process pool like the reference's -- in
-    chunks of 512 candidates shipped as arrays, while the caller goes on scoring the next group; the pool is forked once
-    2048 records have been asked for, before that (and in every other case) ``submit`` builds the records itself."""
+    ``num_threads`` > 1, a PredTable and a FASTA path, the records are built by a pool of worker processes like the
+    reference's -- fed with chunks of 512 candidates shipped as arrays, while the caller goes on scoring the next group.
+    The workers are fresh interpreters (no fork of a process that holds a CUDA context and threads; they import numpy and
+    this module only); they are started by ``prefork`` or once 2048 records have been asked for -- before that, and in every
+    other case, ``submit`` builds the records itself."""
 
     def __init__(self, ref_file, chroms, vartype_classes, num_threads, with_pred=True):
         self.ref_file, self.chroms, self.classes = ref_file, chroms, vartype_classes
         self.num_threads, self.with_pred = int(num_threads), with_pred
         self.pool = None
         self.asked = 0
+        self.seq = 0
 
     def prefork(self):
-        """Start the pool now (a caller that knows a large call is coming forks before CUDA is initialised: cheaper, and no
-        other thread is running yet)."""
+        """Start the workers now: they load while the caller sets up its model and scores the first candidates."""
         if self.pool is None and self.num_threads > 1 and isinstance(self.ref_file, str):
-            self.pool = multiprocessing.Pool(min(self.num_threads, 32))
+            self.pool = _Workers(min(self.num_threads, 32))
 
     def _serial(self, final_preds, true_path, paths):
         fasta = open_fasta(self.ref_file)
@@ -302,52 +398,50 @@ class RecordPool:
         poolable = self.num_threads > 1 and isinstance(self.ref_file, str) and hasattr(final_preds, "columns_of")
         if not poolable or (self.pool is None and self.asked < POOL_MIN) or not paths:
             return ("done", self._serial(final_preds, true_path, paths))
-        if self.pool is None:
-            self.pool = multiprocessing.Pool(min(self.num_threads, 32))
+        self.prefork()
         index = fasta_index(open_fasta(self.ref_file))
-        pending = []
+        seqs = []
         for lo in range(0, len(paths), POOL_CHUNK):
             ps = paths[lo:lo + POOL_CHUNK]
             imgs = [true_path[p] for p in ps]
             if all(isinstance(im, np.ndarray) for im in imgs):
                 imgs = np.stack(imgs)
             job = (ps, imgs, final_preds.columns_of(ps), self.chroms, self.classes, self.ref_file, index, self.with_pred)
-            pending.append(self.pool.apply_async(_records_chunk, (job,)))
-        return ("pending", pending)
+            self.pool.jobs.put((self.seq, job))
+            seqs.append(self.seq)
+            self.seq += 1
+        return ("pending", seqs)
 
     def collect(self, handle):
         kind, h = handle
         if kind == "pending":
-            parts = [r.get() for r in h]
+            parts = self.pool.wait(h)
             if any(part is None for part in parts):
                 raise Exception("pred_vcf_records_path failed!")
             h = [o for part in parts for o in part]
         return list(filter(None, h))
 
-    def close(self):
+    def close(self, kill=False):
         if self.pool is not None:
-            self.pool.close()
-            self.pool.join()
+            self.pool.stop(kill)
             self.pool = None
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
-        if self.pool is not None and exc[0] is not None:
-            self.pool.terminate()
-            self.pool = None
-        self.close()
+        self.close(kill=exc[0] is not None)
         return False
 
 
 def pred_vcf_records(ref_file, final_preds, true_path, chroms, vartype_classes, num_threads, with_pred=True):
     """call.py:308-333.  ``true_path[path]`` holds the uint8 [5,32,3] matrix (or a PNG file name).  One-shot use of
-    ``RecordPool``.  ``with_pred=False`` leaves out the trailing ``[path, pred]`` of every record, which
-    ``get_vcf_records`` drops anyway (call.py:357-363)."""
+    ``RecordPool`` (worker processes for 4 x 2048 records or more: starting them costs about as much as 3000 records).
+    ``with_pred=False`` leaves out the trailing ``[path, pred]`` of every record, which ``get_vcf_records`` drops anyway
+    (call.py:357-363)."""
     with RecordPool(ref_file, chroms, vartype_classes, num_threads, with_pred) as rp:
-        rp.asked = POOL_MIN                    # one request: no later group to amortise the pool over, so decide now
-        if len(final_preds) < POOL_MIN:
+        rp.asked = POOL_MIN                    # one request: no later group to amortise the workers over, so decide now
+        if len(final_preds) < 4 * POOL_MIN:
             rp.num_threads = 1
         return rp.collect(rp.submit(final_preds, true_path))
 

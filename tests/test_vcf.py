@@ -168,8 +168,10 @@ def test_record_pool_equals_the_serial_stage(tmp_path, monkeypatch):
     monkeypatch.setattr(vcf, "POOL_MIN", 1000)
     serial = [vcf.pred_vcf_records(MemoryFasta(seqs), t[0], t[1], chroms, oracle.VARTYPE_CLASSES, 1) for t in tabs]
     assert all(len(s) > 800 for s in serial)
+    monkeypatch.setattr(vcf, "POOL_MIN", 250)                # (the one-shot form starts workers from 4 x POOL_MIN records)
     one_shot = vcf.pred_vcf_records(fa, tabs[0][0], tabs[0][1], chroms, oracle.VARTYPE_CLASSES, 3)
     assert _same(one_shot, serial[0])
+    monkeypatch.setattr(vcf, "POOL_MIN", 1000)
     with vcf.RecordPool(fa, chroms, oracle.VARTYPE_CLASSES, 3, with_pred=False) as rp:
         handles = [rp.submit(t[0], t[1]) for t in tabs]      # the second is submitted while the first is being built
         assert handles[0][0] == "pending" and rp.pool is not None
@@ -212,7 +214,7 @@ def test_record_pool_propagates_a_failed_record(tmp_path, monkeypatch):
             f.writelines(seqs[c][i:i + 60] + "\n" for i in range(0, len(seqs[c]), 60))
     victim = list(tab.keys())[1500]
     images[victim] = str(tmp_path / "no_such_image.png")      # the reference's PNG hand-over with a missing file: raises inside
-    monkeypatch.setattr(vcf, "POOL_MIN", 1000)
+    monkeypatch.setattr(vcf, "POOL_MIN", 250)
     for threads in (1, 3):
         with pytest.raises(Exception, match="pred_vcf_records_path failed"):
             vcf.pred_vcf_records(fa, tab, {k: (v if k != victim else images[victim]) for k, v in images.items()}, chroms,
