@@ -292,16 +292,30 @@ class _Workers:
     """``n`` worker interpreters fed from one queue (a feeder thread per worker: send a job, wait for its result)."""
 
     def __init__(self, n):
+        self.jobs = queue.Queue()
+        self.results, self.failed, self.cv = {}, None, threading.Condition()
+        self.procs, self.threads = [], []
+        # the interpreters are started from a thread of their own: the caller gets on with its model while they load
+        self.launcher = threading.Thread(target=self._launch, args=(n,), daemon=True)
+        self.launcher.start()
+
+    def _launch(self, n):
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         env = dict(os.environ)
         env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
         cmd = [sys.executable, "-c", "from neusomatic_b200.vcf import _worker_main; _worker_main()"]
-        self.jobs = queue.Queue()
-        self.results, self.failed, self.cv = {}, None, threading.Condition()
-        self.procs = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env) for _ in range(n)]
-        self.threads = [threading.Thread(target=self._feed, args=(p,), daemon=True) for p in self.procs]
-        for t in self.threads:
-            t.start()
+        try:
+            for _ in range(n):
+                p = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env)
+                t = threading.Thread(target=self._feed, args=(p,), daemon=True)
+                self.procs.append(p)
+                self.threads.append(t)
+                t.start()
+        except Exception as ex:      # noqa: BLE001
+            with self.cv:
+                if not self.threads:                 # nobody to do the work: whoever waits must hear about it
+                    self.failed = ex
+                self.cv.notify_all()
 
     def _feed(self, proc):
         while True:
@@ -336,6 +350,7 @@ class _Workers:
             return [self.results.pop(q) for q in seqs]
 
     def stop(self, kill=False):
+        self.launcher.join()
         for _ in self.threads:
             self.jobs.put(None)
         for p in self.procs:
