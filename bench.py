@@ -522,6 +522,25 @@ def measure_tsv(args, rk, local_rank, n=524288):
     prof = sc.engine.get_profile()
     sc.engine.set_profile(False)
     os.environ.pop("NSC_TSV_HOST_DECODE", None)
+    # the C-ABI call of that path alone: one staged slice of 65 536 candidates (pinned text + spans + tag fields) through
+    # nsc_score_host_b64, H2D of the text, device inflate, the network and D2H of the results inside the timed region
+    from neusomatic_b200.tsv import CandidateTSV
+    from neusomatic_b200.engine import Engine
+    t = CandidateTSV(path, num_threads=threads)
+    nb = 65536
+    text = torch.empty(t.range_bytes(0, nb) + 64, dtype=torch.uint8).pin_memory()
+    spans = torch.empty((nb, 2), dtype=torch.int32).pin_memory()
+    meta = torch.empty((nb, 3), dtype=torch.int32).pin_memory()
+    t.stage(0, nb, text, spans, meta)
+    nbytes = t.range_bytes(0, nb)
+    t.close()
+    outs = Engine._host_out(nb, True, True)
+    for _ in range(3):
+        sc.engine.score_host_b64(text[:nbytes], spans, meta, None, sc.coverage_thr, out=outs)
+    t0 = time.perf_counter()
+    for _ in range(16):
+        sc.engine.score_host_b64(text[:nbytes], spans, meta, None, sc.coverage_thr, out=outs)
+    b64_rate = 16 * nb / (time.perf_counter() - t0)
     sc.engine.close()
     infl_ms = prof.get("inflate_b64", (0.0, 0))[0]
     cpu_rate, cpu_sample = (None, None)
@@ -535,6 +554,8 @@ def measure_tsv(args, rk, local_rank, n=524288):
                     "then the network) -> PredTable dictionaries + the none.vcf filter on arrays; stage, score and filing overlapped "
                     "(call.py:504-534 + 336-354)",
             "h2d_bytes_per_candidate": size / n,
+            "b64_call": {"value": b64_rate, "unit": "candidates/s", "h2d_bytes_per_step": nbytes + nb * 20, "d2h_bytes_per_step": nb * 76,
+                         "api": "nsc_score_host_b64 (pinned TSV text + spans + tag fields in, host results out; inflate on the device)"},
             "seconds": el, "stage_busy_seconds": stages,
             "inflate_kernel": {"ms_per_pass": infl_ms, "candidates_per_s": (n / (infl_ms * 1e-3)) if infl_ms > 0 else None,
                                "output_GBps": (n * 3680 / (infl_ms * 1e-3) / 1e9) if infl_ms > 0 else None},
