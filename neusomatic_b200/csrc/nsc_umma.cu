@@ -1053,11 +1053,22 @@ pack_nchw_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16
   const int nslice = Cpad / 32;
   const int slice = blockIdx.x % nslice, gh = blockIdx.x / nslice;
   const int grp = gh / kH, h = gh % kH;
-  for (int i = threadIdx.x; i < 8 * 32 * 32; i += 256) {
-    const int w = i & 31, c = (i >> 5) & 31, g = i >> 10;
+  // 16-byte loads (a row of 32 columns is 128 contiguous bytes): eight per thread, all issued before the first use
+  float4 r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int w4 = i & 7, c = (i >> 3) & 31, g = i >> 8;
     const int64_t b = (int64_t)grp * 8 + g;
     const int cc = slice * 32 + c;
-    t[g * PS + c * 33 + w] = (b < B && cc < C) ? __ldg(in + ((b * C + cc) * kH + h) * 32 + w) : 0.f;
+    r[k] = (b < B && cc < C) ? __ldg(reinterpret_cast<const float4*>(in + ((b * C + cc) * kH + h) * 32) + w4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int w4 = i & 7, c = (i >> 3) & 31, g = i >> 8;
+    float* d = t + g * PS + c * 33 + w4 * 4;
+    d[0] = r[k].x; d[1] = r[k].y; d[2] = r[k].z; d[3] = r[k].w;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 8 * 4; i += 256) {
