@@ -70,3 +70,64 @@ def test_two_rank_sharded_call_equals_single_process(n):
     for k, v in {**f1, **n1}.items():
         assert [float(x) for x in v[3]] == probs[k]
     assert sum(b - a for a, b in shard_ranges(n, 2)) == n
+
+
+def _tsv_worker(rank, world, port, path, q):
+    """One rank of a sharded real-file call: its range of the TSV through run_tsv_pipeline; the
+    scorer is the CPU stand-in of tests/test_call_host.py (on the GPU box it is CandidateScorer)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_call_host import _OracleScorer
+    from neusomatic_b200.call import PredTable, run_tsv_pipeline
+    from neusomatic_b200.tsv import CandidateTSV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, ck = load_golden("std_v014")
+    t = CandidateTSV(path)
+    lo, hi = shard_ranges(len(t), world)[rank]
+    t.close()
+    fp, npd, tp = PredTable(), PredTable(), {}
+    run_tsv_pipeline([_OracleScorer(ck, 26)], [(path, lo, hi - lo)], 32, 1, fp, npd, tp)
+    mine = {"final": list(fp), "none": list(npd), "probs": {k: [float(x) for x in v[3]] for k, v in {**dict(fp), **dict(npd)}.items()},
+            "images": sorted(tp)}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)          # control plane only: tags and a few floats, no data-path collective
+    if rank == 0:
+        q.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_tsv_call_equals_single_process(tmp_path):
+    from test_call_host import _OracleScorer
+    from neusomatic_b200.call import PredTable, run_tsv_pipeline
+    n = 150
+    cand = synth.structured_pileups(n, seed=17)
+    path = str(tmp_path / "candidates.tsv")
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(oracle.encode_tsv_line(i, cand.tags[i], cand.matrices[i]))
+    _, ck = load_golden("std_v014")
+    fp, npd, tp = PredTable(), PredTable(), {}
+    run_tsv_pipeline([_OracleScorer(ck, 26)], [(path, 0, None)], 32, 1, fp, npd, tp)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tsv_worker, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # rank order = candidate order: the concatenation of the ranks' tables is the single-process table
+    assert parts[0]["final"] + parts[1]["final"] == list(fp) and parts[0]["none"] + parts[1]["none"] == list(npd)
+    assert sorted(parts[0]["images"] + parts[1]["images"]) == sorted(tp) and len(fp) + len(npd) == n
+    probs = {**parts[0]["probs"], **parts[1]["probs"]}
+    for k, v in {**dict(fp), **dict(npd)}.items():          # (PyTorch's CPU kernels are not bit-stable across batch shapes: one unit
+        assert np.abs(np.asarray(v[3], np.float64) - np.asarray(probs[k])).max() <= 1.01e-4      # of the 4th decimal at most)
