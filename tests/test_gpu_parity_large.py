@@ -39,3 +39,40 @@ def test_large_n_parity(family):
         assert r["flips_type"] <= 1e-4 * N and r["flips_len"] <= 1e-4 * N, (name, r)          # >= 99.99 % identical
         assert r["max_dprob"] <= 2e-3 and r["max_dpos"] <= 1e-3, (name, r)
         assert r["mismatch_4dp_entries"] <= MAX_MM4[mode], (name, r)
+
+
+FULL_N = 1 << 20     # BASELINE.json configs[2]: a 1M-candidate standalone call
+
+
+def test_full_size_call_is_position_and_chunk_invariant():
+    """BASELINE configs[2] at its full size through ``nsc_score_host_u8``: 1 048 576 candidates made of an 8191-candidate
+    block repeated 128.01 times (8191 is odd, so no copy is aligned with the 8-candidate groups of the kernels, the 32 768-
+    candidate device chunks or the staging slices).  Size-independent properties of the path: a candidate's result does not
+    depend on where it stands in the call (every copy == the block scored alone, bit for bit, all seven outputs), the
+    fused softmax rows sum to one, the fused argmax is the argmax of the returned logits -- and the block itself meets the
+    north-star tolerances against the oracle, so the million rows do."""
+    from oracle import nsnet_oracle as oracle
+    from neusomatic_b200 import Engine, synth
+    from neusomatic_b200.call import load_checkpoint
+    sd, meta = load_checkpoint(os.path.join(ROOT, "tests", "golden", "std_v010.pth"))
+    thr = float(meta["coverage_thr"])
+    blk = synth.structured_pileups(8191, seed=77)
+    idx = np.arange(FULL_N) % 8191
+    mats, m3 = np.ascontiguousarray(blk.matrices[idx]), np.ascontiguousarray(blk.meta[idx])
+    eng = Engine(sd, 26)
+    small = [t.numpy().copy() for t in eng.score_host_u8(blk.matrices, blk.meta, None, thr)]
+    full = [t.numpy() for t in eng.score_host_u8(mats, m3, None, thr)]
+    assert len(small) == 7 and all(len(t) == FULL_N for t in full)
+    for a, b in zip(full, small):
+        for lo in range(0, FULL_N, 1 << 18):                    # compare in slices: no second million-row temporary
+            np.testing.assert_array_equal(a[lo:lo + (1 << 18)], b[idx[lo:lo + (1 << 18)]])
+    o1, o2, o3, p1, p3, a1, a3 = full
+    assert np.abs(p1.sum(1) - 1).max() <= 2e-6 and np.abs(p3.sum(1) - 1).max() <= 2e-6
+    assert (a1 == o1.argmax(1)).all() and (a3 == o3.argmax(1)).all()
+    # the block against the oracle (512 candidates: the numpy oracle finishes in seconds)
+    x = oracle.assemble_channels(blk.matrices[:512], blk.center[:512], blk.tumor_cov[:512], blk.normal_cov[:512], None, int(thr))
+    (r1, r2, r3), _ = oracle.forward(oracle.normalize_state_dict(sd), x, return_internals=True)
+    assert (small[0][:512].argmax(1) == r1.argmax(1)).all() and (small[2][:512].argmax(1) == r3.argmax(1)).all()
+    assert np.abs(small[3][:512] - oracle.softmax(r1)).max() <= 2e-3 and np.abs(small[4][:512] - oracle.softmax(r3)).max() <= 2e-3
+    assert np.abs(small[1][:512] - r2).max() <= 1e-3
+    eng.close()
