@@ -22,7 +22,9 @@ Printed JSON (one line, rank 0):
             matrices + tag fields in (what the TSV decoder yields, dataloader.py:38-58), host results out, H2D/D2H inside
             the timed region, channel assembly on the device; e2e_f32: the same through nsc_score_host_f32
   roofline  tensor roofline of the dominant kernel family (the eight 64->64 convolutions), timed live with CUDA events,
-            against BOTH measured bf16 peaks (sustained = `frac`, burst = `frac_burst`)
+            against BOTH measured bf16 peaks (sustained = `frac`, burst = `frac_burst`); `cublas_bf16_same_box` = what an
+            8192^3 bf16 cuBLAS GEMM sustains on this box right after the timed regions (informational: the boxes of the pool
+            hold different clocks under the power cap), `executed_vs_cublas_same_box` = executed tensor instructions vs that
   cpu_baseline  oracle/torch_port.py (the reference's forward restated on the PyTorch CPU operators the reference itself
             runs) on a bounded sample, rank 0 / N=1 only
   extra     records measured in the same run with the same build: `ensemble` (BASELINE configs[3], C=119: value + e2e),
@@ -663,6 +665,30 @@ def measure_whole_call(args, rk, local_rank, n_none=500000, n_gen=12000):
                     "inflate + scoring, the VCF records of the called variants built by a process pool meanwhile"}
 
 
+def cublas_bf16_same_box(dev, seconds=1.5, n=8192):
+    """Informational: the rate a dense bf16 cuBLAS GEMM (n^3, torch.matmul) sustains on THIS box in THIS run -- the same
+    measurement MEASURED_PEAKS.json's sustained figure comes from, but under this box's own power cap and clocks (boxes of
+    the pool differ by 5-10 %).  Not on the product path; `roofline.peak` stays the driver-written number."""
+    a = torch.randn(n, n, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(n, n, device=dev, dtype=torch.bfloat16)
+    c = torch.empty(n, n, device=dev, dtype=torch.bfloat16)
+    for _ in range(20):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters, total_ms, done = 200, 0.0, 0
+    while total_ms < seconds * 1000.0 and done < 20000:
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        done += iters
+    return {"tflops": 2.0 * n ** 3 * done / (total_ms / 1000.0) / 1e12, "seconds": total_ms / 1000.0, "n": n,
+            "what": "torch.matmul bf16 %d^3 (cuBLAS) run back to back for >= %.1f s right after the timed regions, same process" % (n, seconds)}
+
+
 def roofline_record(m, B, steps, world, C):
     """Tensor roofline of the dominant kernel family (the eight 64->64 convolutions) from the live per-kernel event times."""
     pk = peaks()
@@ -753,6 +779,12 @@ def main():
     B = args.batch
     m = measure_scoring(args, rk, local_rank, args.ensemble, B, args.steps)
     C = m["C"]
+    same = None
+    if not args.no_extra:
+        try:                         # right after the timed regions: the GPU is in the power / thermal state they ran in
+            same = cublas_bf16_same_box(dev)
+        except Exception as ex:      # noqa: BLE001  (informational)
+            same = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     extra = {}
     if not args.no_extra:
@@ -783,6 +815,12 @@ def main():
                     extra[name] = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     roof = roofline_record(m, B, args.steps, world, C)
+    if roof is not None and same is not None:
+        roof["cublas_bf16_same_box"] = same
+        if "tflops" in same:
+            roof["frac_of_cublas_same_box"] = roof["achieved"] / same["tflops"]
+            if roof.get("executed_tensor_tflops_fp16_slots"):
+                roof["executed_vs_cublas_same_box"] = roof["executed_tensor_tflops_fp16_slots"] / same["tflops"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
