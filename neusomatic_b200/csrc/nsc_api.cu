@@ -387,11 +387,14 @@ static int score_host(nsc_model* m, int kind, const void* in_host, const int32_t
   }
   DeviceGuard g(m->device);
   if (!g.ok) { set_error("cudaSetDevice(%d) failed", m->device); return NSC_E_CUDA; }
-  if ((rc = ensure_workspace(m, std::min<int64_t>(B, u8 ? 16384 : 8192))) != NSC_OK) return rc;
+  // candidates per slice of the copy / compute pipeline (NSC_HOST_SLICE overrides it for experiments)
+  static const int64_t slice_env = getenv("NSC_HOST_SLICE") ? std::max<int64_t>(1024, atoll(getenv("NSC_HOST_SLICE"))) : 0;
+  const int64_t slice_cap = slice_env ? slice_env : (u8 ? 16384 : 8192);
+  if ((rc = ensure_workspace(m, std::min<int64_t>(B, slice_cap))) != NSC_OK) return rc;
   if ((rc = ensure_host_path(m)) != NSC_OK) return rc;
   // slice size of the copy/compute pipeline: small enough that the first H2D does not delay the first kernel,
   // large enough to keep the layer kernels efficient
-  const int64_t cap = std::min<int64_t>(std::min<int64_t>(m->chunk_cap, u8 ? 16384 : 8192), std::max<int64_t>(B, 1024));
+  const int64_t cap = std::min<int64_t>(std::min<int64_t>(m->chunk_cap, slice_cap), std::max<int64_t>(B, 1024));
   const int na = m->C - kBaseCh;
   const size_t in_per = u8 ? (size_t)kH * kW * kStoredCh : (size_t)m->C * kH * kW * sizeof(float);
   const size_t meta_per = u8 ? 3 * sizeof(int32_t) : 0;
