@@ -197,9 +197,10 @@ def run_reference(args, rank, world):
         return
     C = 119 if args.ensemble else 26
     rates, secs = [], []
+    t_budget_w = args.ref_seconds if args.ref_seconds else 1.0
     for _ in range(args.warmup):
-        cpu_port_rate(C, seconds=1.0, batch=args.ref_batch)
-    t_budget = max(3.0, min(20.0, 120.0 / max(args.steps, 1)))
+        cpu_port_rate(C, seconds=min(1.0, t_budget_w), batch=args.ref_batch)
+    t_budget = args.ref_seconds if args.ref_seconds else max(3.0, min(20.0, 120.0 / max(args.steps, 1)))
     sample = ""
     threads = os.cpu_count() or 1
     for _ in range(args.steps):
@@ -736,6 +737,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="candidates per GPU per step")
     ap.add_argument("--precision", type=int, default=None, help="NSC_PREC_* (default: library default)")
     ap.add_argument("--ref-batch", type=int, default=1000)
+    ap.add_argument("--ref-seconds", type=float, default=None, help="--impl reference: CPU seconds per step (default: 120 / steps, "
+                    "clamped to 3..20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--min-timed-ms", type=float, default=MIN_TIMED_MS, help="repeat the K-step region until this much is timed "
