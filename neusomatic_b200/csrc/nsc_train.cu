@@ -181,7 +181,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ u, const float* __rest
     const int c = (int)((i / HW4) & 63);
     const float mean = stats[c], istd = stats[64 + c], ga = gamma[c], be = beta[c];
     const float4 u4 = __ldg(reinterpret_cast<const float4*>(u) + i);
-    float v[4] = {(u4.x - mean) * istd * ga + be, (u4.y - mean) * istd * ga + be, (u4.z - mean) * istd * ga + be, (u4.w - mean) * istd * ga + be};
+    float v[4] = {bn_affine(u4.x, mean, istd, ga, be), bn_affine(u4.y, mean, istd, ga, be), bn_affine(u4.z, mean, istd, ga, be),
+                  bn_affine(u4.w, mean, istd, ga, be)};
     if (relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
     if (resid != nullptr) {
       const float4 r4 = __ldg(reinterpret_cast<const float4*>(resid) + i);
@@ -272,15 +273,17 @@ __global__ void pool_bwd_kernel(const float* __restrict__ in, const float* __res
   }
 }
 
-// per-channel sums for the BatchNorm backward: sum(dy), sum(dy * xhat), sum(xhat); dy is masked by (mask_src > 0) when
-// given.  sum(xhat) (rounding noise of the fp32 mean) gives the gradient of the convolution bias in front of the
+// per-channel sums for the BatchNorm backward: sum(dy), sum(dy * xhat), sum(xhat); for a layer with a ReLU (relu_beta given)
+// dy is masked where the pre-activation bn_affine(u) was not positive -- recomputed from u, the activation is not read.  sum(xhat) (rounding noise of the fp32 mean) gives the gradient of the convolution bias in front of the
 // BatchNorm without another pass: sum(du) = -gamma * invstd * sum(dy * xhat) * sum(xhat) / M.  max |dy| and max |xhat| bound
 // |du| from above before du exists, which lets bn_bwd_apply_pack_kernel write du already rescaled and packed.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ dy,
-                     const float* __restrict__ mask_src, int N, int HW, double* __restrict__ sums /*[64][splits][5]*/) {
+                     const float* __restrict__ gamma, const float* __restrict__ relu_beta, int N, int HW,
+                     double* __restrict__ sums /*[64][splits][5]*/) {
   const int c = blockIdx.x, sp = blockIdx.y;
   const float mean = stats[c], invstd = stats[64 + c];
+  const float ga = gamma[c], be = relu_beta != nullptr ? relu_beta[c] : 0.f;
   double s = 0.0, sx = 0.0, sh1 = 0.0;
   float gmax = 0.f, xmax = 0.f;
   const int HW4 = HW >> 2, total4 = N * HW4;      // 16-byte loads, 32-bit index arithmetic
@@ -290,12 +293,11 @@ bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ stat
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + o) + r);
     const float4 u4 = __ldg(reinterpret_cast<const float4*>(u + o) + r);
     float g[4] = {g4.x, g4.y, g4.z, g4.w};
-    if (mask_src != nullptr) {
-      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask_src + o) + r);
-      if (!(m4.x > 0.f)) g[0] = 0.f;
-      if (!(m4.y > 0.f)) g[1] = 0.f;
-      if (!(m4.z > 0.f)) g[2] = 0.f;
-      if (!(m4.w > 0.f)) g[3] = 0.f;
+    if (relu_beta != nullptr) {
+      if (!(bn_affine(u4.x, mean, invstd, ga, be) > 0.f)) g[0] = 0.f;
+      if (!(bn_affine(u4.y, mean, invstd, ga, be) > 0.f)) g[1] = 0.f;
+      if (!(bn_affine(u4.z, mean, invstd, ga, be) > 0.f)) g[2] = 0.f;
+      if (!(bn_affine(u4.w, mean, invstd, ga, be) > 0.f)) g[3] = 0.f;
     }
     const float xh[4] = {(u4.x - mean) * invstd, (u4.y - mean) * invstd, (u4.z - mean) * invstd, (u4.w - mean) * invstd};
 #pragma unroll
@@ -358,14 +360,14 @@ __global__ void bn_bwd_final_kernel(const double* __restrict__ part, double* __r
 // du = gamma * invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M); also writes dgamma, dbeta and the gradient of the
 // convolution bias in front of the BatchNorm, sum(du) = -gamma * invstd * sum(dy*xhat) * sum(xhat) / M
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                    const float* __restrict__ dy, const float* __restrict__ mask_src, const double* __restrict__ sums,
+                                    const float* __restrict__ dy, const float* __restrict__ relu_beta, const double* __restrict__ sums,
                                     float* __restrict__ du, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     float* __restrict__ dbias, int64_t total, int HW, double inv_m, unsigned int* __restrict__ amax) {
   float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / HW) % 64);
     float g = dy[i];
-    if (mask_src != nullptr && !(mask_src[i] > 0.f)) g = 0.f;
+    if (relu_beta != nullptr && !(bn_affine(u[i], stats[c], stats[64 + c], gamma[c], relu_beta[c]) > 0.f)) g = 0.f;
     const float xhat = (u[i] - stats[c]) * stats[64 + c];
     const float dv = gamma[c] * stats[64 + c] * (float)((double)g - sums[c * 3] * inv_m - (double)xhat * sums[c * 3 + 1] * inv_m);
     du[i] = dv;
@@ -961,12 +963,14 @@ static int train_backward(nsc_trainer* t, const float* params, const float* x_de
   float* g = t->gA;       // gradient w.r.t. the current block output
   NSC_RUN(run_gemm(N, kFcIn, kFcHidden, t->dh, kFcHidden, 1, W1, kFcIn, 1, g, kFcIn, nullptr, 0, s));
   // ---------------- backward: convolution stack ----------------
-  // BatchNorm + conv backward of layer li: dy (masked by relu_src > 0) -> du (in `du_buf`), parameter gradients
-  auto bn_conv_bwd = [&](int li, const float* u, const float* dy, const float* relu_src, const float* conv_in, float* du_buf) -> int {
+  // BatchNorm + conv backward of layer li: dy (masked where the ReLU was off) -> du (in `du_buf`), parameter gradients
+  // has_relu: the layer's output went through a ReLU; its mask is recomputed from u (bn_affine(u) > 0), not read from the activation
+  auto bn_conv_bwd = [&](int li, const float* u, const float* dy, bool has_relu, const float* conv_in, float* du_buf) -> int {
     const TLayer& L = t->L[li];
     const int HW = kH * L.W;
     const int64_t total = (int64_t)N * 64 * HW;
-    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, relu_src, N, HW, t->red + 512);
+    const float* relu_beta = has_relu ? params + L.be_off : nullptr;
+    bn_bwd_reduce_kernel<<<dim3(64, kRedSplits), 256, 0, s>>>(u, t->stats + li * 128, dy, params + L.g_off, relu_beta, N, HW, t->red + 512);
     NSC_LAUNCH_OK();
     // default path: du is never written in fp32 -- its bound is known from the sums, and it is written rescaled, split
     // and packed for the weight- and data-gradient kernels (umma_train_bn_bwd_pack)
@@ -975,11 +979,11 @@ static int train_backward(nsc_trainer* t, const float* params, const float* x_de
                                          du_packed ? 1 : 0);
     NSC_LAUNCH_OK();
     if (du_packed) {
-      int r = umma_train_bn_bwd_pack(&t->dummy, L.W, u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, grads + L.g_off,
+      int r = umma_train_bn_bwd_pack(&t->dummy, L.W, u, t->stats + li * 128, params + L.g_off, dy, relu_beta, t->red + 16, grads + L.g_off,
                                      grads + L.be_off, grads + L.b_off, N, 1.0 / ((double)N * HW), s);
       if (r != NSC_OK) return r;
     } else {
-      bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_src, t->red + 16, du_buf,
+      bn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>(u, t->stats + li * 128, params + L.g_off, dy, relu_beta, t->red + 16, du_buf,
                                                           grads + L.g_off, grads + L.be_off, grads + L.b_off, total, HW,
                                                           1.0 / ((double)N * HW), amax_du);
       NSC_LAUNCH_OK();
@@ -1007,16 +1011,16 @@ static int train_backward(nsc_trainer* t, const float* params, const float* x_de
     else pool_bwd_kernel<2><<<grid_for(rows * Wd), 256, 0, s>>>(t->z[i], g, gz, rows, Wd);
     NSC_LAUNCH_OK();
     // bn_r2 (no ReLU), conv_r2: du2 in gu; d a1 = dgrad(du2) -> g (reused)
-    NSC_RUN(bn_conv_bwd(2 + 2 * i, t->u2[i], gz, nullptr, t->a1[i], gu));
+    NSC_RUN(bn_conv_bwd(2 + 2 * i, t->u2[i], gz, false, t->a1[i], gu));
     NSC_RUN(dgrad(2 + 2 * i, gu, nullptr, g));
     // relu + bn_r1 + conv_r1: du1 in gu; d x[i] = dgrad(du1) + gz -> g
-    NSC_RUN(bn_conv_bwd(1 + 2 * i, t->u1[i], g, t->a1[i], t->x[i], gu));
+    NSC_RUN(bn_conv_bwd(1 + 2 * i, t->u1[i], g, true, t->x[i], gu));
     NSC_RUN(dgrad(1 + 2 * i, gu, gz, g));
   }
   // stem: pool1 (stride 1), ReLU, bn1, conv1
   pool_bwd_kernel<1><<<grid_for((int64_t)N * 64 * kH * 32), 256, 0, s>>>(t->a0, g, gz, (int64_t)N * 64 * kH, 32);
   NSC_LAUNCH_OK();
-  NSC_RUN(bn_conv_bwd(0, t->u0, gz, t->a0, x_dev, gu));
+  NSC_RUN(bn_conv_bwd(0, t->u0, gz, true, x_dev, gu));
   return NSC_OK;
 }
 

@@ -2053,15 +2053,19 @@ int umma_train_wgrad(nsc_model* m, int k, int dil, int W, const float* x, const 
 // rescaled (power of two from the bound at scl[0]), split and packed; candidates >= B are zero.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_pack_kernel(const float* __restrict__ u, const float* __restrict__ stats, const float* __restrict__ gamma,
-                         const float* __restrict__ dy, const float* __restrict__ mask_src, const double* __restrict__ sums,
+                         const float* __restrict__ dy, const float* __restrict__ relu_beta, const double* __restrict__ sums,
                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dbias, int B, int Bpad, int W, double inv_m, float* __restrict__ scl) {
   __shared__ float cg[64], cm[64], ci[64], c0s[64], c1s[64];      // gamma * invstd, mean, invstd, sum(dy)/M, sum(dy xhat)/M
+  __shared__ float cga[64], cbe[64];                              // gamma, beta: the ReLU mask is bn_affine(u) > 0, recomputed
+  const bool has_relu = relu_beta != nullptr;
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
     cm[c] = stats[c];
     ci[c] = stats[64 + c];
     cg[c] = gamma[c] * stats[64 + c];
+    cga[c] = gamma[c];
+    cbe[c] = has_relu ? relu_beta[c] : 0.f;
     c0s[c] = (float)(sums[c * 3] * inv_m);
     c1s[c] = (float)(sums[c * 3 + 1] * inv_m);
     if (blockIdx.x == 0) {
@@ -2093,8 +2097,9 @@ bn_bwd_apply_pack_kernel(const float* __restrict__ u, const float* __restrict__ 
       if (b < B) {
         const int64_t idx = ((b * 64 + c) * kH + h) * W + w;
         float g = __ldg(dy + idx);
-        if (mask_src != nullptr && !(__ldg(mask_src + idx) > 0.f)) g = 0.f;
-        const float xhat = (__ldg(u + idx) - cm[c]) * ci[c];
+        const float uv = __ldg(u + idx);
+        if (has_relu && !(bn_affine(uv, cm[c], ci[c], cga[c], cbe[c]) > 0.f)) g = 0.f;
+        const float xhat = (uv - cm[c]) * ci[c];
         dv = cg[c] * (g - c0s[c] - xhat * c1s[c]);
       }
       v[j] = dv * scale;
@@ -2108,14 +2113,14 @@ bn_bwd_apply_pack_kernel(const float* __restrict__ u, const float* __restrict__ 
 }
 
 int umma_train_bn_bwd_pack(nsc_model* m, int W, const float* u_, const float* stats, const float* gamma, const float* dy,
-                           const float* relu_src, const double* sums, float* dgamma, float* dbeta, float* dbias, int64_t n,
+                           const float* relu_beta, const double* sums, float* dgamma, float* dbeta, float* dbias, int64_t n,
                            double inv_m, cudaStream_t s) {
   UmmaState& u = m->umma;
   if (n > u.cap || u.xin[0] == nullptr) { set_error("umma_train_bn_bwd_pack: workspace not initialised for batch %lld", (long long)n); return NSC_E_STATE; }
   const int bpad = (int)((n + 15) / 16 * 16);
   const int64_t items = (int64_t)bpad * kH * W * 8;
   bn_bwd_apply_pack_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 148 * 16), 256, 0, s>>>(
-      u_, stats, gamma, dy, relu_src, sums, u.xin[0], u.xin[1], dgamma, dbeta, dbias, (int)n, bpad, W, inv_m, u.fc_in);
+      u_, stats, gamma, dy, relu_beta, sums, u.xin[0], u.xin[1], dgamma, dbeta, dbias, (int)n, bpad, W, inv_m, u.fc_in);
   NSC_CUDA_TRY(cudaGetLastError());
   m->launches += 1;
   return NSC_OK;
