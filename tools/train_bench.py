@@ -2,14 +2,15 @@
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from neusomatic_b200 import synth
+from neusomatic_b200 import Engine, synth
 from neusomatic_b200.train import Trainer
-from oracle import nsnet_oracle as oracle
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda", 0)
 cand = synth.structured_pileups(B, seed=100)
-x = torch.from_numpy(oracle.assemble_channels(cand.matrices, cand.center, cand.tumor_cov, cand.normal_cov, None, 100)).to(dev)
+_eng = Engine(synth.random_state_dict(26, seed=1), 26, device=0)      # channel assembly by the library, on the device
+x = _eng.assemble(torch.from_numpy(cand.matrices).to(dev), torch.from_numpy(cand.meta).to(dev), None, 100.0).clone()
+_eng.close()
 vt = torch.tensor([synth.VARTYPE_CLASSES.index(t.split(".")[4]) for t in cand.tags], dtype=torch.int32, device=dev)
 ln = torch.tensor([min(int(t.split(".")[6]), 3) for t in cand.tags], dtype=torch.int32, device=dev)
 ce = torch.from_numpy(cand.center).float().to(dev)
